@@ -1,0 +1,132 @@
+/* molgym_b200.h — C ABI of the B200-native PPO policy/value hot path of gncs/molgym.
+ *
+ * Plain pointers and sizes only (no torch types).  All `const float*` / `float*` / `int*` arguments named d_* are
+ * DEVICE pointers on the current CUDA device; `stream` is a cudaStream_t passed as void*.  Every entry point
+ * returns 0 on success, a negative mgb_status otherwise; mgb_last_error() returns a message for the calling thread.
+ *
+ * Which reference interface each entry replaces (paths relative to the reference tree):
+ *   mgb_cov_forward / mgb_cov_backward   — CovariantAC.step(observations, actions) in evaluate mode and its autograd
+ *                                          backward: molgym/agents/covariant/agent.py:209-334 (cormorant stack
+ *                                          molgym/agents/covariant/modules.py:97-135,180-190; invariants
+ *                                          so3_tools.py:147-190; spherical distribution spherical_dists.py:182-286)
+ *   mgb_ppo_loss                         — ppo.compute_loss arithmetic, molgym/ppo.py:28-52
+ *   mgb_pack_observations                — CovariantAC.parse_observations + tools.process_atoms_list + spaces parse:
+ *                                          agent.py:165-197, covariant/tools.py:8-49, spaces.py:55-61,106-107
+ *   mgb_cov_param_count / layout         — the nn.Module parameter inventory of CovariantAC (agent.py:59-143)
+ */
+#ifndef MOLGYM_B200_H
+#define MOLGYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_MAX_SPECIES 16
+#define MGB_MAX_LEVELS 4
+#define MGB_MAXL 4
+
+typedef enum {
+  MGB_OK = 0,
+  MGB_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  MGB_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed */
+  MGB_ERR_WORKSPACE = -3, /* workspace too small */
+  MGB_ERR_STATE = -4      /* backward called without a matching forward */
+} mgb_status;
+
+/* Hyper-parameters of the covariant agent — same meaning as the CovariantAC constructor (agent.py:21-35). */
+typedef struct {
+  int32_t canvas_size;                 /* N: observation_space.canvas_space.size */
+  int32_t num_species;                 /* Z: len(zs) */
+  int32_t zs[MGB_MAX_SPECIES];         /* atomic numbers, zs[k] == 0 is the null symbol */
+  int32_t maxl;                        /* must be 4 in this build */
+  int32_t num_cg_levels;               /* 1..MGB_MAX_LEVELS */
+  int32_t num_channels_hidden;         /* C */
+  int32_t num_channels_per_element;    /* CPE; output channels = Z * CPE */
+  int32_t num_gaussians;               /* G */
+  int32_t network_width;               /* MLP width */
+  float min_distance, max_distance;    /* min_max_distance */
+  float bag_scale;
+  int32_t has_beta;                    /* 0: SO3Distribution (beta=None); 1: ExpSO3Distribution */
+  float beta;
+  int32_t rel_sh_normalize;            /* `normalize` of the relative spherical harmonics (oracle switch #1; 0) */
+} mgb_cov_config;
+
+typedef struct mgb_cov_plan mgb_cov_plan;
+
+const char* mgb_last_error(void);
+int mgb_version(void);
+/* 1 when the library was built by nvcc for sm_100a, 0 for the CPU kernel emulator used by the test-suite. */
+int mgb_is_cuda_build(void);
+
+/* Plan: immutable per-(config, device) state — Clebsch-Gordan term tables, Lebedev-71 quadrature harmonics.
+ * lebedev_xyz[G*3], lebedev_w[G] (weights summing to 1) are HOST arrays (quadpy lebedev_071 ==
+ * scipy.integrate.lebedev_rule(71) / 4 pi, spherical_dists.py:208-215). */
+int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* lebedev_xyz, const double* lebedev_w, int32_t n_grid,
+                        mgb_cov_plan** out);
+void mgb_cov_plan_destroy(mgb_cov_plan* plan);
+
+/* Flat fp32 parameter buffer.  Tensors appear in this order, each in the reference's own shape/row-major layout:
+ *   input.weight[2C,4Z] input.bias[2C]
+ *   per level k: rad.scales[8] rad.phases[8] rad.linear[l].weight[2C,32] (l=0..L) rad.linear[l].bias[2C] (l=0..L)
+ *                edge.weights[l][C,catE_kl,2] (l=0..L) atom.weights[l][Cout_k,catA_kl,2] (l=0..L)
+ *   mixer.weights[l][CPE,catM_l,2] (l=0..L)
+ *   phi_focus, phi_element, phi_d, phi_trans, phi_v: each weight0,bias0,weight1,bias1 ; distance_log_stds[G]
+ * mgb_cov_param_layout fills offsets[i], numels[i] (floats) for i < mgb_cov_param_count(). */
+int mgb_cov_param_count(const mgb_cov_plan* plan);
+int mgb_cov_param_layout(const mgb_cov_plan* plan, int64_t* offsets, int64_t* numels, int64_t* total);
+/* cat sizes: out[(k*(L+1)+l)*2+0] = catE_kl, +1 = catA_kl ; then L+1 entries catM_l */
+int mgb_cov_cat_sizes(const mgb_cov_plan* plan, int32_t* out);
+
+size_t mgb_cov_workspace_bytes(const mgb_cov_plan* plan, int32_t batch);
+
+/* Per-canvas outputs of the forward (all device, fp32 unless noted).  Any pointer except logp/ent/v may be NULL. */
+typedef struct {
+  float* logp;            /* [B]  sum of the four sub-action log-probabilities (agent.py:295-301) */
+  float* ent;             /* [B]  focus + element entropies (agent.py:304-308) */
+  float* v;               /* [B]  state value (agent.py:313-316) */
+  float* logp_parts;      /* [B,4] focus, element, distance, orientation */
+  float* focus_probs;     /* [B,N] */
+  float* element_probs;   /* [B,Z] */
+  float* gmm;             /* [B,3,G] normalised log mixture weights, means, stds */
+  float* coefficients;    /* [B,25,CPE,2] normalised a_lm (lm-major, channel, re/im)  (so3_dist.coefficients) */
+  float* log_z;           /* [B] (has_beta only) */
+  float* covariats;       /* [B,N,25,Z*CPE,2] last-level atom representations (lm-major, channel-minor) */
+} mgb_cov_outputs;
+
+/* Forward in evaluate mode.  d_positions[B,N,3] f32, d_charges[B,N] i32 (0 = padding, real atoms first),
+ * d_bags[B,Z] f32, d_actions[B,6] f32 = focus, element, distance, ox, oy, oz (agent.py:230,249,271,288).
+ * Saves what backward needs inside the workspace. */
+int mgb_cov_forward(mgb_cov_plan* plan, int32_t batch, const float* d_positions, const int32_t* d_charges,
+                    const float* d_bags, const float* d_actions, const float* d_params, void* d_workspace,
+                    size_t workspace_bytes, const mgb_cov_outputs* out, void* stream);
+
+/* Backward of the same call: cotangents d_g_logp/d_g_ent/d_g_v [B] -> d_grad_params (flat, same layout as params).
+ * accumulate != 0 adds into d_grad_params, else it is overwritten. */
+int mgb_cov_backward(mgb_cov_plan* plan, int32_t batch, const float* d_positions, const int32_t* d_charges,
+                     const float* d_bags, const float* d_actions, const float* d_params, void* d_workspace,
+                     size_t workspace_bytes, const float* d_g_logp, const float* d_g_ent, const float* d_g_v,
+                     float* d_grad_params, int32_t accumulate, void* stream);
+
+/* PPO-clip loss (ppo.py:28-52) and its cotangents in one launch.  logp/ent/v/old_logp fp32, adv/ret fp64 (the
+ * reference hands float64 advantages/returns to torch, buffer.py:106-114, so the loss is float64).
+ * inv_global_batch = 1 / (minibatch size across all ranks) so that sharded ranks produce gradient *sums*.
+ * d_info[8] (fp64): loss, policy_loss, entropy_loss, vf_loss, approx_kl, clip_fraction, 0, 0 — local partial sums
+ * already scaled by inv_global_batch.  Gradient outputs may be NULL (loss only). */
+int mgb_ppo_loss(int32_t batch, const float* d_logp, const float* d_ent, const float* d_v, const float* d_old_logp,
+                 const double* d_adv, const double* d_ret, double clip_ratio, double vf_coef, double entropy_coef,
+                 double inv_global_batch, double* d_info, float* d_g_logp, float* d_g_ent, float* d_g_v, void* stream);
+
+/* Host-side observation packer (no device work).  labels[B,N] are indices into zs, xyz[B,N,3] float64 canvas
+ * coordinates, as found in ObservationType tuples.  Null-symbol items are dropped and the rest compacted to the
+ * front (spaces.py:55-61), padding is zero (covariant/tools.py:18-31). Outputs are HOST arrays
+ * positions[B,N,3] f32, charges[B,N] i32.  Returns MGB_ERR_INVALID for a negative or out-of-range label. */
+int mgb_pack_observations(const mgb_cov_config* cfg, int32_t batch, const int32_t* labels, const double* xyz,
+                          float* positions, int32_t* charges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLGYM_B200_H */

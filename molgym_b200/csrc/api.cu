@@ -1,0 +1,291 @@
+// api.cu — the C ABI (include/molgym_b200.h): plan construction, workspace carving, kernel launch sequences.
+// Compiled by nvcc for sm_100a (product) or by g++ -DMGB_CUSIM against tests/cusim/cusim.h (kernel-logic tests).
+#include "plan.cuh"
+#include "cov_backward.cuh"
+
+using namespace mgb;
+
+#define MGB_LAUNCH_OK(what)                                                                             \
+  do {                                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                                \
+    if (e_ != cudaSuccess) return fail(MGB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <int NLM2>
+static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
+                           cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const LevelDesc& L = d.lv[level];
+  const size_t smem = sizeof(float) * atom_smem_floats(L);
+  const int co = pick_co(L.Cout);
+#define MGB_ATOM_CASE(CO)                                                                                          \
+  case CO: {                                                                                                       \
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_fwd<NLM2, CO, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MGB_LAUNCH((k_atom_fwd<NLM2, CO, 3>), B * d.N, kAtomThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms,  \
+               w.A[level], w.E[level], w.cat[level], w.A[level + 1]);                                             \
+  } break;
+  switch (co) {
+    MGB_ATOM_CASE(10)
+    MGB_ATOM_CASE(8)
+    MGB_ATOM_CASE(6)
+    MGB_ATOM_CASE(5)
+    MGB_ATOM_CASE(4)
+  }
+#undef MGB_ATOM_CASE
+  MGB_LAUNCH_OK("k_atom_fwd");
+  return MGB_OK;
+}
+
+extern "C" {
+
+const char* mgb_last_error(void) { return g_err; }
+int mgb_version(void) { return 100; }
+int mgb_is_cuda_build(void) {
+#ifdef MGB_CUSIM
+  return 0;
+#else
+  return 1;
+#endif
+}
+
+int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const double* leb_w, int32_t n_grid,
+                        mgb_cov_plan** out) {
+  if (!cfg || !out) return fail(MGB_ERR_INVALID, "null argument");
+  if (cfg->maxl != kL) return fail(MGB_ERR_INVALID, "this build supports maxl == %d only (got %d)", kL, cfg->maxl);
+  if (cfg->num_cg_levels < 1 || cfg->num_cg_levels > kMaxLevels) return fail(MGB_ERR_INVALID, "num_cg_levels out of range");
+  if (cfg->num_species < 1 || cfg->num_species > MGB_MAX_SPECIES) return fail(MGB_ERR_INVALID, "num_species out of range");
+  if (cfg->canvas_size < 1 || cfg->canvas_size > 64) return fail(MGB_ERR_INVALID, "canvas_size must be in 1..64");
+  if (cfg->num_channels_hidden < 1 || cfg->num_channels_hidden * kM > kAtomThreads)
+    return fail(MGB_ERR_INVALID, "num_channels_hidden must be in 1..%d", kAtomThreads / kM);
+  if (cfg->num_channels_per_element < 1 || cfg->num_channels_per_element > 4)
+    return fail(MGB_ERR_INVALID, "num_channels_per_element must be in 1..4");
+  if (cfg->num_species * cfg->num_channels_per_element > 32) return fail(MGB_ERR_INVALID, "too many output channels");
+  if (cfg->num_gaussians < 1 || cfg->num_gaussians > 8) return fail(MGB_ERR_INVALID, "num_gaussians must be in 1..8");
+  if (cfg->network_width < 1 || cfg->network_width > 1024) return fail(MGB_ERR_INVALID, "network_width out of range");
+  if (cfg->rel_sh_normalize) return fail(MGB_ERR_INVALID, "rel_sh_normalize=1 is not supported");
+  if (cfg->has_beta && (n_grid <= 0 || !leb_xyz || !leb_w)) return fail(MGB_ERR_INVALID, "beta needs the Lebedev grid");
+
+  std::unique_ptr<mgb_cov_plan> plan(new mgb_cov_plan());
+  plan->cfg = *cfg;
+  CovDesc& d = plan->desc;
+  std::memset(&d, 0, sizeof(d));
+  d.N = cfg->canvas_size; d.Z = cfg->num_species; d.K = cfg->num_cg_levels;
+  d.C = cfg->num_channels_hidden; d.CPE = cfg->num_channels_per_element; d.Cout = d.Z * d.CPE;
+  d.G = cfg->num_gaussians; d.Wd = cfg->network_width;
+  d.lat = (kL + 2) * d.Cout * 2; d.latE = (kL + 2) * d.CPE * 2;
+  d.S_in = d.Z * 3 + d.Z;
+  int zmax = 1;
+  for (int z = 0; z < d.Z; ++z) { d.zs[z] = cfg->zs[z]; zmax = std::max(zmax, cfg->zs[z]); }
+  d.charge_scale = (float)zmax;                                   // agent.py:71 charge_scale=max(zs)
+  d.bag_scale = cfg->bag_scale;
+  d.cut_rad = std::max(1e-3f, std::fabs(std::min(cfg->max_distance, 2.1f)));   // agent.py:66-69 + MaskLevel eps
+  d.cut_width = std::max(1e-3f, 0.2f);
+  d.dmin = cfg->min_distance; d.dmax = cfg->max_distance;
+  d.has_beta = cfg->has_beta; d.beta = cfg->beta;
+  d.n_grid = cfg->has_beta ? n_grid : 0;
+
+  // ---- parameter layout (see include/molgym_b200.h) + transposed-weights scratch layout
+  long long p = 0, wt = 0;
+  auto param = [&](long long numel) { plan->p_offsets.push_back(p); plan->p_numels.push_back(numel); long long o = p; p += numel; return o; };
+  const int C = d.C, C2 = 2 * C;
+  d.p_inW = param((long long)C2 * d.S_in);
+  d.p_inb = param(C2);
+  TableArena arena;
+  std::vector<PendingTable> pending;
+  HostCgTable sq_full = build_cg_table(kNL, kNL);
+  for (int k = 0; k < d.K; ++k) {
+    LevelDesc& L = d.lv[k];
+    L.nLin = k == 0 ? 1 : kNL;
+    L.nlm_in = L.nLin * L.nLin;
+    L.C = C;
+    L.Cout = (k == d.K - 1) ? d.Cout : C;
+    L.has_prev = k > 0;
+    HostCgTable ag = build_cg_table(kNL, L.nLin), sq = build_cg_table(L.nLin, L.nLin);
+    int eo = 0, ao = 0, wo = 0;
+    L.sumCatE = 0;
+    for (int l = 0; l < kNL; ++l) {
+      L.catE[l] = (L.has_prev ? C : 0) + (l < L.nLin ? L.nLin * C : 0) + C;
+      L.offE[l] = eo; eo += C * L.catE[l];
+      L.sumCatE += L.catE[l];
+      const bool has_in = l < L.nLin;
+      L.in_block[l] = has_in ? ag.n_blocks[l] : -1;
+      L.sq_block[l] = ag.n_blocks[l] + (has_in ? 1 : 0);
+      L.catA[l] = C * (ag.n_blocks[l] + (has_in ? 1 : 0) + sq.n_blocks[l]);
+      L.offA[l] = ao; ao += L.catA[l] * (2 * l + 1);
+      L.offWA[l] = wo; wo += L.Cout * L.catA[l];
+    }
+    L.totE = eo; L.totA = ao; L.totWA = wo;
+    L.p_scales = param(kTrig);
+    L.p_phases = param(kTrig);
+    L.p_radW = p;
+    for (int l = 0; l < kNL; ++l) param((long long)C2 * kRadFeat);
+    L.p_radb = p;
+    for (int l = 0; l < kNL; ++l) param(C2);
+    L.p_edgeW = p;
+    for (int l = 0; l < kNL; ++l) param((long long)C * L.catE[l] * 2);
+    L.p_atomW = p;
+    for (int l = 0; l < kNL; ++l) param((long long)L.Cout * L.catA[l] * 2);
+    // transposed copies: edge weights [l][k][c'][2] then radial weights [l][t][2C]
+    d.wt_edge[k] = wt;
+    for (int l = 0; l < kNL; ++l)
+      plan->segs.push_back(TransposeSeg{L.p_edgeW + 2ll * L.offE[l], wt + 2ll * L.offE[l], C, L.catE[l], 2});
+    wt += 2ll * L.totE;
+    for (int l = 0; l < kNL; ++l)
+      plan->segs.push_back(TransposeSeg{L.p_radW + (long long)l * C2 * kRadFeat, wt + (long long)l * C2 * kRadFeat, C2, kRadFeat, 1});
+    wt += (long long)kNL * C2 * kRadFeat;
+    pending.push_back(stage_table(arena, ag, &L.ag));
+    pending.push_back(stage_table(arena, sq, &L.sq));
+  }
+  {  // mixer
+    int ao = 0, wo = 0;
+    for (int l = 0; l < kNL; ++l) {
+      d.catM[l] = d.CPE * (1 + sq_full.n_blocks[l] + 1);
+      d.inM_block[l] = 1 + sq_full.n_blocks[l];
+      d.offM[l] = ao; ao += d.catM[l] * (2 * l + 1);
+      d.offWM[l] = wo; wo += d.CPE * d.catM[l];
+    }
+    d.totM = ao; d.totWM = wo;
+    d.p_mixW = p;
+    for (int l = 0; l < kNL; ++l) param((long long)d.CPE * d.catM[l] * 2);
+    pending.push_back(stage_table(arena, sq_full, &d.mix_sq));
+  }
+  auto mlp = [&](MlpDesc& m, int in, int hidden, int outn) {
+    fill_mlp(m, in, hidden, outn, p, wt);
+    plan->p_offsets.push_back(m.W0); plan->p_numels.push_back((long long)hidden * in);
+    plan->p_offsets.push_back(m.b0); plan->p_numels.push_back(hidden);
+    plan->p_offsets.push_back(m.W1); plan->p_numels.push_back((long long)outn * hidden);
+    plan->p_offsets.push_back(m.b1); plan->p_numels.push_back(outn);
+    plan->segs.push_back(TransposeSeg{m.W0, m.W0t, hidden, in, 1});
+    plan->segs.push_back(TransposeSeg{m.W1, m.W1t, outn, hidden, 1});
+  };
+  mlp(d.focus, d.lat, d.Wd, 1);
+  mlp(d.element, d.lat, d.Wd, d.Z);
+  mlp(d.dist, d.latE, d.Wd, 2 * d.G);
+  mlp(d.trans, d.lat, d.Wd, d.Wd);
+  mlp(d.value, d.Wd, d.Wd, 1);
+  d.p_logstd = param(d.G);
+  d.n_params = p;
+  d.n_wt = wt;
+  d.n_units_hidden = build_mix_units(d.units_hidden, 3);
+  d.n_units_out = build_mix_units(d.units_out, 3);
+
+  // ---- Lebedev tables
+  size_t o_leb_y = 0, o_leb_w = 0;
+  if (d.has_beta) {
+    std::vector<float> ly((size_t)n_grid * kM * 2), lw(n_grid);
+    for (int g = 0; g < n_grid; ++g) {
+      double y[kM * 2];
+      double x = leb_xyz[g * 3], yy = leb_xyz[g * 3 + 1], z = leb_xyz[g * 3 + 2];
+      const double nr = std::sqrt(x * x + yy * yy + z * z);
+      if (nr > 0) { x /= nr; yy /= nr; z /= nr; }
+      host_sph_harm(x, yy, z, y);
+      for (int q = 0; q < kM * 2; ++q) ly[(size_t)g * kM * 2 + q] = (float)y[q];
+      lw[g] = (float)std::log((double)(float)leb_w[g]);   // torch.log(weights) on the float32 weights
+    }
+    o_leb_y = arena.add(ly.data(), ly.size() * sizeof(float));
+    o_leb_w = arena.add(lw.data(), lw.size() * sizeof(float));
+  }
+  MGB_CUDA_OK(cudaMalloc(&plan->d_tables, arena.host.size()));
+  MGB_CUDA_OK(cudaMemcpy(plan->d_tables, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice));
+  for (auto& pt : pending) resolve_table(pt, (const unsigned char*)plan->d_tables);
+  if (d.has_beta) {
+    d.leb_y = (const float*)((const unsigned char*)plan->d_tables + o_leb_y);
+    d.leb_logw = (const float*)((const unsigned char*)plan->d_tables + o_leb_w);
+  }
+  MGB_CUDA_OK(cudaMalloc((void**)&plan->d_desc, sizeof(CovDesc)));
+  MGB_CUDA_OK(cudaMemcpy(plan->d_desc, &d, sizeof(CovDesc), cudaMemcpyHostToDevice));
+  MGB_CUDA_OK(cudaMalloc((void**)&plan->d_segs, sizeof(TransposeSeg) * plan->segs.size()));
+  MGB_CUDA_OK(cudaMemcpy(plan->d_segs, plan->segs.data(), sizeof(TransposeSeg) * plan->segs.size(), cudaMemcpyHostToDevice));
+  *out = plan.release();
+  return MGB_OK;
+}
+
+void mgb_cov_plan_destroy(mgb_cov_plan* plan) {
+  if (!plan) return;
+  cudaFree(plan->d_tables);
+  cudaFree(plan->d_desc);
+  cudaFree(plan->d_segs);
+  delete plan;
+}
+
+int mgb_cov_param_count(const mgb_cov_plan* plan) { return plan ? (int)plan->p_offsets.size() : 0; }
+
+int mgb_cov_param_layout(const mgb_cov_plan* plan, int64_t* offsets, int64_t* numels, int64_t* total) {
+  if (!plan) return fail(MGB_ERR_INVALID, "null plan");
+  for (size_t i = 0; i < plan->p_offsets.size(); ++i) {
+    if (offsets) offsets[i] = plan->p_offsets[i];
+    if (numels) numels[i] = plan->p_numels[i];
+  }
+  if (total) *total = plan->desc.n_params;
+  return MGB_OK;
+}
+
+int mgb_cov_cat_sizes(const mgb_cov_plan* plan, int32_t* out) {
+  if (!plan || !out) return fail(MGB_ERR_INVALID, "null argument");
+  const CovDesc& d = plan->desc;
+  int q = 0;
+  for (int k = 0; k < d.K; ++k)
+    for (int l = 0; l < kNL; ++l) { out[q++] = d.lv[k].catE[l]; out[q++] = d.lv[k].catA[l]; }
+  for (int l = 0; l < kNL; ++l) out[q++] = d.catM[l];
+  return MGB_OK;
+}
+
+size_t mgb_cov_workspace_bytes(const mgb_cov_plan* plan, int32_t batch) {
+  if (!plan || batch <= 0) return 0;
+  return carve_workspace(plan->desc, batch, nullptr).bytes;
+}
+
+int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32_t* charges, const float* bags,
+                    const float* actions, const float* P, void* workspace, size_t workspace_bytes,
+                    const mgb_cov_outputs* out, void* stream) {
+  if (!plan || !pos || !charges || !bags || !actions || !P || !workspace || !out) return fail(MGB_ERR_INVALID, "null argument");
+  if (!out->logp || !out->ent || !out->v) return fail(MGB_ERR_INVALID, "logp/ent/v outputs are required");
+  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
+  const CovDesc& d = plan->desc;
+  const CovWs w = carve_workspace(d, B, workspace);
+  if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d.N;
+  MGB_LAUNCH(k_prep_params, (int)plan->segs.size(), 256, 0, st, plan->d_segs, P, w.Wt);
+  MGB_LAUNCH_OK("k_prep_params");
+  MGB_LAUNCH(k_input_fwd, B, 128, sizeof(float) * N * d.S_in, st, plan->d_desc, P, charges, bags, w.n_atoms, w.X, w.A[0]);
+  MGB_LAUNCH_OK("k_input_fwd");
+  for (int k = 0; k < d.K; ++k) {
+    const LevelDesc& L = d.lv[k];
+    const size_t esm = sizeof(float2) * (L.nlm_in * L.C + (kEdgeThreads / 32) * (L.sumCatE + 16));
+    if (k == 0) {
+      MGB_LAUNCH(k_edge_fwd<1>, B * N, kEdgeThreads, esm, st, plan->d_desc, k, P, w.Wt, pos, w.n_atoms, w.A[k], (const float*)nullptr, w.E[k]);
+    } else {
+      MGB_LAUNCH(k_edge_fwd<kNL>, B * N, kEdgeThreads, esm, st, plan->d_desc, k, P, w.Wt, pos, w.n_atoms, w.A[k], w.E[k - 1], w.E[k]);
+    }
+    MGB_LAUNCH_OK("k_edge_fwd");
+    int rc = k == 0 ? launch_atom_fwd<1>(plan, k, B, P, pos, w, st) : launch_atom_fwd<kM>(plan, k, B, P, pos, w, st);
+    if (rc != MGB_OK) return rc;
+  }
+  MGB_LAUNCH(k_scalars_fwd, B * N, 64, 0, st, plan->d_desc, w.n_atoms, w.A[d.K], w.inv);
+  MGB_LAUNCH_OK("k_scalars_fwd");
+  {
+    const long long rows = (long long)B * N;
+    dim3 grid((unsigned)((rows + kRowTile - 1) / kRowTile), 2);
+    const size_t sm = sizeof(float) * kRowTile * (d.lat + d.Wd);
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    MGB_LAUNCH(k_rows_mlp_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, w.n_atoms, rows, w.inv, w.hf, w.flogit, w.ht0, w.trans);
+    MGB_LAUNCH_OK("k_rows_mlp_fwd");
+  }
+  {
+    const size_t sm = sizeof(float) * policy_smem_floats(d);
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int grid = std::min(B, 148 * 4);
+    MGB_LAUNCH(k_policy_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
+               w.flogit, w.trans, *out);
+    MGB_LAUNCH_OK("k_policy_fwd");
+  }
+  if (out->covariats)
+    MGB_CUDA_OK(cudaMemcpyAsync(out->covariats, w.A[d.K], sizeof(float) * (size_t)B * N * kM * d.Cout * 2, cudaMemcpyDeviceToDevice, st));
+  plan->forward_batch = B;
+  return MGB_OK;
+}
+
+}  // extern "C"
+
+#include "api_backward.inl"

@@ -1,0 +1,160 @@
+// common.cuh — shared device helpers: complex arithmetic, spherical harmonics, block reductions, descriptors.
+#pragma once
+#include "portable.h"
+#include "../../include/molgym_b200.h"
+
+namespace mgb {
+
+constexpr int kL = 4;             // maxl supported by this build
+constexpr int kNL = kL + 1;       // number of ells
+constexpr int kM = 25;            // (kL+1)^2 spherical components, lm = l*l + l + m
+constexpr int kRadFeat = 32;      // 8 trig x 4 inverse powers (basis_set=[3,3], covariant/agent.py:73)
+constexpr int kTrig = 8;
+constexpr float kTwoPi = 6.283185307179586f;
+constexpr float kFourPi = 12.566370614359172f;
+
+__host__ __device__ __forceinline__ int lm_index(int l, int m) { return l * l + l + m; }
+__host__ __device__ __forceinline__ int ell_of_lm(int lm) { return lm >= 16 ? 4 : (lm >= 9 ? 3 : (lm >= 4 ? 2 : (lm >= 1 ? 1 : 0))); }
+
+// ---- complex helpers (float2 = re, im) ---------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {  // acc += a*b
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfmac(float2& acc, float2 a, float2 b) {  // acc += a*conj(b)
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
+}
+__device__ __forceinline__ void cfmacl(float2& acc, float2 a, float2 b) {  // acc += conj(a)*b
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
+}
+
+// ---- spherical harmonics -------------------------------------------------------------------------------------
+// Complex Y_lm(v) for l <= 4, Condon-Shortley phase, m = -l..l stored at lm = l*l+l+m, evaluated as solid
+// harmonics (|v|^l Y_lm(v/|v|)) so that an un-normalised argument reproduces Cormorant's recursion
+// Y_l ~ CG(Y_{l-1} x Y_1) (oracle/thirdparty/cormorant/cg_lib.py::spherical_harmonics).
+//   unit_norm: multiply each l by sqrt(4 pi / (2l+1))   (sh_norm='unit', else 'qm')
+//   conj:      complex conjugate                        (SphericalHarmonicsRel(conj=True), covariant/modules.py:52-56)
+__device__ __forceinline__ void sph_harm_l4(float x, float y, float z, bool unit_norm, bool conj, float2* out) {
+  const float r2 = x * x + y * y + z * z;
+  const float z2 = z * z;
+  // (x + i y)^m
+  float2 e1 = make_float2(x, y);
+  float2 e2 = cmul(e1, e1);
+  float2 e3 = cmul(e2, e1);
+  float2 e4 = cmul(e2, e2);
+  // D_lm(z, r) = r^(l-m) d^m P_l / du^m (u = z/r)
+  const float d00 = 1.f;
+  const float d10 = z, d11 = 1.f;
+  const float d20 = 0.5f * (3.f * z2 - r2), d21 = 3.f * z, d22 = 3.f;
+  const float d30 = 0.5f * z * (5.f * z2 - 3.f * r2), d31 = 0.5f * (15.f * z2 - 3.f * r2), d32 = 15.f * z, d33 = 15.f;
+  const float d40 = 0.125f * (35.f * z2 * z2 - 30.f * z2 * r2 + 3.f * r2 * r2);
+  const float d41 = 0.5f * z * (35.f * z2 - 15.f * r2), d42 = 0.5f * (105.f * z2 - 15.f * r2), d43 = 105.f * z, d44 = 105.f;
+  // N_lm = sqrt((2l+1)/(4 pi) (l-m)!/(l+m)!) for 'qm'; sqrt((l-m)!/(l+m)!) for 'unit'
+  const float q0 = unit_norm ? 1.f : 0.28209479177387814f;   // sqrt(1/4pi)
+  const float q1 = unit_norm ? 1.f : 0.4886025119029199f;    // sqrt(3/4pi)
+  const float q2 = unit_norm ? 1.f : 0.6307831305050401f;    // sqrt(5/4pi)
+  const float q3 = unit_norm ? 1.f : 0.7463526651802308f;    // sqrt(7/4pi)
+  const float q4 = unit_norm ? 1.f : 0.8462843753216345f;    // sqrt(9/4pi)
+  const float s = conj ? -1.f : 1.f;
+#define MGB_SET(l, m, nrm, d, e)                                                   \
+  {                                                                                \
+    const float a_ = (nrm) * (d);                                                  \
+    const float sg_ = ((m) & 1) ? -1.f : 1.f;                                      \
+    out[(l) * (l) + (l) + (m)] = make_float2(sg_ * a_ * (e).x, s * sg_ * a_ * (e).y); \
+    out[(l) * (l) + (l) - (m)] = make_float2(a_ * (e).x, -s * a_ * (e).y);          \
+  }
+  out[0] = make_float2(q0 * d00, 0.f);
+  out[2] = make_float2(q1 * d10, 0.f);
+  MGB_SET(1, 1, q1 * 0.7071067811865476f, d11, e1)
+  out[6] = make_float2(q2 * d20, 0.f);
+  MGB_SET(2, 1, q2 * 0.408248290463863f, d21, e1)      // sqrt(1/6)
+  MGB_SET(2, 2, q2 * 0.2041241452319315f, d22, e2)     // sqrt(1/24)
+  out[12] = make_float2(q3 * d30, 0.f);
+  MGB_SET(3, 1, q3 * 0.2886751345948129f, d31, e1)     // sqrt(2!/4!) = sqrt(1/12)
+  MGB_SET(3, 2, q3 * 0.09128709291752768f, d32, e2)    // sqrt(1/120)
+  MGB_SET(3, 3, q3 * 0.03726779962499649f, d33, e3)    // sqrt(1/720)
+  out[20] = make_float2(q4 * d40, 0.f);
+  MGB_SET(4, 1, q4 * 0.22360679774997896f, d41, e1)    // sqrt(3!/5!) = sqrt(1/20)
+  MGB_SET(4, 2, q4 * 0.05270462766947299f, d42, e2)    // sqrt(2!/6!) = sqrt(1/360)
+  MGB_SET(4, 3, q4 * 0.014085904245475277f, d43, e3)   // sqrt(1/5040)
+  MGB_SET(4, 4, q4 * 0.004980119205559973f, d44, e4)   // sqrt(1/40320)
+#undef MGB_SET
+}
+
+// ---- block-wide reductions (blockDim.x multiple of 32, <= 1024) ----------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// scratch: >= 32 floats of shared memory. All threads must call. Result broadcast to all threads.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : -3.0e38f;
+  r = warp_max(r);
+  return r;
+}
+
+// ---- Clebsch-Gordan term tables (device pointers; built on the host in plan.cuh) --------------------------------
+struct CgTable {
+  int n_out;               // number of (path, m) outputs
+  int n_pair;              // M1 * M2 input pairs
+  int nlm2;                // number of lm components of the second factor (1 or 25)
+  const int* out_l;        // [n_out] output ell
+  const int* out_m;        // [n_out] output m index 0..2l
+  const int* out_block;    // [n_out] channel-block index inside cat_l (slot = block*C + c)
+  const int* term_start;   // [n_out+1]
+  const int* term_lm1;     // [n_term]
+  const int* term_lm2;     // [n_term]
+  const float* term_coef;  // [n_term]
+  const int* pair_start;   // [n_pair+1]   transposed table: pair = lm1*nlm2 + lm2
+  const int* pair_out;     // [n_term]
+  const float* pair_coef;  // [n_term]
+};
+
+// One Cormorant level (edge network + atom network), everything the kernels need by value.
+struct LevelDesc {
+  int nLin;          // ells present in the input atom reps (1 at level 0, else 5)
+  int nlm_in;        // nLin^2
+  int C;             // input / edge channels
+  int Cout;          // atom-mix output channels
+  int has_prev;      // previous-level edge scalars feed the edge mix
+  int catE[kNL];     // edge cat sizes: [prev (C) | dot (nLin*C, only l < nLin) | radial (C)]
+  int offE[kNL];     // complex offset of l block inside the packed edge weights (sum C*catE)
+  int totE;          // total complex edge weights
+  int sumCatE;       // sum_l catE[l]
+  int catA[kNL];     // atom cat sizes: [ag paths | in (C, only l < nLin) | sq paths]
+  int offA[kNL];     // complex offset of l block inside a per-atom CAT row: sum_{l'<l} catA[l']*(2l'+1)
+  int totA;          // per-atom CAT size (complex)
+  int offWA[kNL];    // complex offset of l block inside the packed atom weights (sum Cout*catA)
+  int totWA;
+  int in_block[kNL]; // block index of the pass-through input rep inside cat_l (-1 if absent)
+  int sq_block[kNL]; // first block index of the CG-square paths inside cat_l
+  long long p_scales, p_phases, p_radW, p_radb, p_edgeW, p_atomW;  // float offsets into the flat parameter buffer
+  CgTable ag, sq;
+};
+
+}  // namespace mgb

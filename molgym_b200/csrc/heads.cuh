@@ -1,0 +1,565 @@
+// heads.cuh — policy/value heads of the covariant actor-critic: forward and backward.
+//
+// Reference: molgym/agents/covariant/agent.py:220-316 (focus / element / distance / orientation heads, value),
+// molgym/modules.py:26-50 (masked softmax, MLP), molgym/agents/covariant/gmm.py:8-18, so3_tools.py:47-132,
+// spherical_dists.py:79-115,182-215,273-286, covariant/modules.py:180-190 (CormorantMixer) and
+// torch.distributions.Categorical / Normal / MixtureSameFamily arithmetic.
+#pragma once
+#include "cov_forward.cuh"
+
+namespace mgb {
+
+constexpr int kRowTile = 8;
+constexpr int kHeadThreads = 128;
+constexpr float kF32Eps = 1.1920928955078125e-07f;
+constexpr float kLogSqrt2Pi = 0.9189385332046727f;
+constexpr float kLog4Pi = 2.5310242469692907f;
+
+enum RowMode { kRowsAll = 0, kRowsActive = 1, kRowsValid = 2 };
+__device__ __forceinline__ bool row_on(int mode, const int* __restrict__ n_atoms, int N, long long r) {
+  if (mode == kRowsAll) return true;
+  const int b = (int)(r / N), i = (int)(r % N), n = n_atoms[b];
+  return mode == kRowsActive ? (i < (n > 1 ? n : 1)) : (i < n);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Two-layer MLPs applied to atom rows (phi_focus, phi_trans):  H = relu(X W0^T + b0),  Y = H W1^T + b1.
+// grid = (row tiles, 2): y = 0 focus head on active rows, y = 1 value-transform on valid atoms.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kHeadThreads)
+k_rows_mlp_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt,
+               const int* __restrict__ n_atoms, long long rows, const float* __restrict__ X, float* __restrict__ H0,
+               float* __restrict__ Y0, float* __restrict__ H1, float* __restrict__ Y1) {
+  const CovDesc& d = *dp;
+  const MlpDesc& M = blockIdx.y == 0 ? d.focus : d.trans;
+  const int mode = blockIdx.y == 0 ? kRowsActive : kRowsValid;
+  float* H = blockIdx.y == 0 ? H0 : H1;
+  float* Y = blockIdx.y == 0 ? Y0 : Y1;
+  const int K = M.in, Wd = M.hidden, No = M.out;
+  MGB_DYN_SMEM(float, sm);
+  float* sx = sm;               // [kRowTile][K]
+  float* sh = sm + kRowTile * K;  // [kRowTile][Wd]
+  __shared__ int s_on[kRowTile];
+  const long long r0 = (long long)blockIdx.x * kRowTile;
+  if (threadIdx.x < kRowTile) {
+    const long long r = r0 + threadIdx.x;
+    s_on[threadIdx.x] = (r < rows && row_on(mode, n_atoms, d.N, r)) ? 1 : 0;
+  }
+  __syncthreads();
+  int any = 0;
+  for (int q = 0; q < kRowTile; ++q) any |= s_on[q];
+  if (!any) return;
+  for (int idx = threadIdx.x; idx < kRowTile * K; idx += blockDim.x) {
+    const int q = idx / K;
+    sx[idx] = s_on[q] ? X[(r0 + q) * K + (idx % K)] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < Wd; o += blockDim.x) {
+    float acc[kRowTile];
+    const float bias = P[M.b0 + o];
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q) acc[q] = bias;
+    const float* w = Wt + M.W0t + o;
+    for (int k = 0; k < K; ++k) {
+      const float wk = w[(long long)k * Wd];
+      MGB_UNROLL
+      for (int q = 0; q < kRowTile; ++q) acc[q] = fmaf(wk, sx[q * K + k], acc[q]);
+    }
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q) {
+      const float h = fmaxf(acc[q], 0.f);
+      sh[q * Wd + o] = h;
+      if (s_on[q]) H[(r0 + q) * Wd + o] = h;
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < No; o += blockDim.x) {
+    float acc[kRowTile];
+    const float bias = P[M.b1 + o];
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q) acc[q] = bias;
+    const float* w = Wt + M.W1t + o;
+    for (int k = 0; k < Wd; ++k) {
+      const float wk = w[(long long)k * No];
+      MGB_UNROLL
+      for (int q = 0; q < kRowTile; ++q) acc[q] = fmaf(wk, sh[q * Wd + k], acc[q]);
+    }
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q)
+      if (s_on[q]) Y[(r0 + q) * No + o] = acc[q];
+  }
+}
+
+// Backward of the same: dY -> dH (masked by relu) -> dX (+=).  dH is kept for the weight gradient.
+//   focus: dY0 [rows,1];  trans: dY = dvf[b,:] broadcast over the valid atoms of canvas b, also written to dY1 [rows,Wd].
+__global__ void __launch_bounds__(kHeadThreads)
+k_rows_mlp_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const int* __restrict__ n_atoms, long long rows,
+               const float* __restrict__ H0, const float* __restrict__ dY0, float* __restrict__ dH0,
+               const float* __restrict__ H1, const float* __restrict__ dvf, float* __restrict__ dY1, float* __restrict__ dH1,
+               float* __restrict__ dX) {
+  const CovDesc& d = *dp;
+  MGB_DYN_SMEM(float, sm);
+  const int Wd = d.focus.hidden, K = d.focus.in;
+  float* sdy = sm;                         // [kRowTile][Wd]  (trans) or [kRowTile] (focus)
+  float* sdh = sm + kRowTile * Wd;         // [2][kRowTile][Wd]
+  __shared__ int s_on[2][kRowTile];
+  const long long r0 = (long long)blockIdx.x * kRowTile;
+  if (threadIdx.x < 2 * kRowTile) {
+    const int which = threadIdx.x / kRowTile, q = threadIdx.x % kRowTile;
+    const long long r = r0 + q;
+    s_on[which][q] = (r < rows && row_on(which == 0 ? kRowsActive : kRowsValid, n_atoms, d.N, r)) ? 1 : 0;
+  }
+  __syncthreads();
+  int any = 0;
+  for (int q = 0; q < kRowTile; ++q) any |= s_on[0][q];
+  if (!any) return;
+  // trans: dY rows
+  for (int idx = threadIdx.x; idx < kRowTile * Wd; idx += blockDim.x) {
+    const int q = idx / Wd, o = idx % Wd;
+    float v = 0.f;
+    if (s_on[1][q]) {
+      v = dvf[((r0 + q) / d.N) * Wd + o];
+      dY1[(r0 + q) * Wd + o] = v;
+    }
+    sdy[idx] = v;
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+    // focus: dH0[r][h] = relu'(H0) * W1[0][h] * dY0[r]
+    const float w1 = P[d.focus.W1 + h];
+    float acc[kRowTile];
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q) acc[q] = 0.f;
+    // trans: dH1[r][h] = relu'(H1) * sum_o W1[o][h] dY[r][o]
+    const float* w = P + d.trans.W1 + h;
+    for (int o = 0; o < Wd; ++o) {
+      const float wo = w[(long long)o * Wd];
+      MGB_UNROLL
+      for (int q = 0; q < kRowTile; ++q) acc[q] = fmaf(wo, sdy[q * Wd + o], acc[q]);
+    }
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q) {
+      float g0 = 0.f, g1 = 0.f;
+      if (s_on[0][q]) {
+        g0 = H0[(r0 + q) * Wd + h] > 0.f ? w1 * dY0[r0 + q] : 0.f;
+        dH0[(r0 + q) * Wd + h] = g0;
+      }
+      if (s_on[1][q]) {
+        g1 = H1[(r0 + q) * Wd + h] > 0.f ? acc[q] : 0.f;
+        dH1[(r0 + q) * Wd + h] = g1;
+      }
+      sdh[q * Wd + h] = g0;
+      sdh[(kRowTile + q) * Wd + h] = g1;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc[kRowTile];
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q) acc[q] = 0.f;
+    const float* w0 = P + d.focus.W0 + k;
+    const float* w1 = P + d.trans.W0 + k;
+    for (int h = 0; h < Wd; ++h) {
+      const float a = w0[(long long)h * K], bq = w1[(long long)h * K];
+      MGB_UNROLL
+      for (int q = 0; q < kRowTile; ++q) acc[q] = fmaf(a, sdh[q * Wd + h], fmaf(bq, sdh[(kRowTile + q) * Wd + h], acc[q]));
+    }
+    MGB_UNROLL
+    for (int q = 0; q < kRowTile; ++q)
+      if (s_on[0][q]) dX[(r0 + q) * K + k] += acc[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Grouped weight gradient: for each problem p, dW[o][k] += sum_rows dY[r][o] X[r][k], db[o] += sum_rows dY[r][o].
+// grid = (chunks, problems); a CTA walks `rows_per_cta` rows, threads over k, register tile of 16 outputs.
+// ------------------------------------------------------------------------------------------------------------
+struct DwProblem {
+  const float* X;
+  const float* dY;
+  long long rows;
+  int K, No, mode;
+  long long dW, db;  // float offsets into the gradient buffer
+};
+constexpr int kDwThreads = 128;
+constexpr int kDwTileO = 16;
+constexpr int kDwRowChunk = 16;
+
+__global__ void __launch_bounds__(kDwThreads)
+k_dw_grouped(const DwProblem* __restrict__ probs, const int* __restrict__ n_atoms, int N, float* __restrict__ grad) {
+  const DwProblem pr = probs[blockIdx.y];
+  const long long per = (pr.rows + gridDim.x - 1) / gridDim.x;
+  const long long r_begin = per * blockIdx.x, r_end = (r_begin + per < pr.rows) ? r_begin + per : pr.rows;
+  if (r_begin >= r_end) return;
+  MGB_DYN_SMEM(float, sdy);  // [kDwRowChunk][No]
+  __shared__ int s_on[kDwRowChunk];
+  const int K = pr.K, No = pr.No;
+  for (int o0 = 0; o0 < No; o0 += kDwTileO) {
+    for (int k0 = 0; k0 < K + 1; k0 += blockDim.x) {  // k == K is the bias column
+      const int k = k0 + threadIdx.x;
+      float acc[kDwTileO];
+      MGB_UNROLL
+      for (int q = 0; q < kDwTileO; ++q) acc[q] = 0.f;
+      for (long long rc = r_begin; rc < r_end; rc += kDwRowChunk) {
+        const int nr = (int)((r_end - rc) < kDwRowChunk ? (r_end - rc) : kDwRowChunk);
+        __syncthreads();
+        if ((int)threadIdx.x < nr) s_on[threadIdx.x] = row_on(pr.mode, n_atoms, N, rc + threadIdx.x) ? 1 : 0;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nr * kDwTileO; idx += blockDim.x) {
+          const int q = idx / kDwTileO, o = o0 + idx % kDwTileO;
+          sdy[idx] = (s_on[q] && o < No) ? pr.dY[(rc + q) * No + o] : 0.f;
+        }
+        __syncthreads();
+        if (k <= K) {
+          for (int q = 0; q < nr; ++q) {
+            if (!s_on[q]) continue;
+            const float x = k < K ? pr.X[(rc + q) * K + k] : 1.f;
+            MGB_UNROLL
+            for (int o = 0; o < kDwTileO; ++o) acc[o] = fmaf(sdy[q * kDwTileO + o], x, acc[o]);
+          }
+        }
+      }
+      if (k <= K) {
+        MGB_UNROLL
+        for (int o = 0; o < kDwTileO; ++o) {
+          if (o0 + o < No && acc[o] != 0.f) {
+            if (k < K) atomicAdd(grad + pr.dW + (long long)(o0 + o) * K + k, acc[o]);
+            else atomicAdd(grad + pr.db + o0 + o, acc[o]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-canvas policy head.  Shared-memory scratch carved out by PolicySmem.
+// ------------------------------------------------------------------------------------------------------------
+struct PolicySmem {
+  float* fl;      // [N] focus logits -> probabilities p' (normalised twice like Categorical(probs=...))
+  float* flog;    // [N] clamped log-probabilities
+  float* finv;    // [lat]
+  float* he;      // [Wd]
+  float* el;      // [Z] element logits -> probabilities
+  float* elog;    // [Z]
+  float2* ecov;   // [25][CPE]
+  float* einv;    // [latE]
+  float* hd;      // [Wd]
+  float* yd;      // [2G]
+  float2* cat;    // [totM]
+  float2* cond;   // [25][CPE]
+  float2* alm;    // [25] normalised sum over channels
+  float* vf;      // [Wd]
+  float* hv;      // [Wd]
+  float* red;     // [64] reduction scratch
+  float* misc;    // [32]
+};
+__host__ __device__ inline int policy_smem_floats(const CovDesc& d) {
+  return 2 * d.N + d.lat + d.Wd + 2 * d.Z + 2 * kM * d.CPE + d.latE + d.Wd + 2 * d.G + 2 * d.totM + 2 * kM * d.CPE + 2 * kM +
+         2 * d.Wd + 64 + 32 + 16;
+}
+__device__ __forceinline__ PolicySmem policy_smem_carve(const CovDesc& d, float* base) {
+  PolicySmem s;
+  float* p = base;
+  s.cat = reinterpret_cast<float2*>(p); p += 2 * d.totM;
+  s.ecov = reinterpret_cast<float2*>(p); p += 2 * kM * d.CPE;
+  s.cond = reinterpret_cast<float2*>(p); p += 2 * kM * d.CPE;
+  s.alm = reinterpret_cast<float2*>(p); p += 2 * kM;
+  s.fl = p; p += d.N;
+  s.flog = p; p += d.N;
+  s.finv = p; p += d.lat;
+  s.he = p; p += d.Wd;
+  s.el = p; p += d.Z;
+  s.elog = p; p += d.Z;
+  s.einv = p; p += d.latE;
+  s.hd = p; p += d.Wd;
+  s.yd = p; p += 2 * d.G;
+  s.vf = p; p += d.Wd;
+  s.hv = p; p += d.Wd;
+  s.red = p; p += 64;
+  s.misc = p;
+  return s;
+}
+
+// masked softmax + Categorical(probs=...) arithmetic on a short vector held in shared memory (single thread; the
+// vectors have <= 40 entries).  logits -> probs p' in place, clamped log-probs in `logp`.  Returns entropy.
+//   q = exp(z - max) / (sum + 1e-12) * mask   (torch_scatter scatter_softmax + modules.py:27)
+//   p' = q / sum(q) ;  L = log(clamp(p', eps, 1 - eps)) ; entropy = -sum p' L
+struct SoftmaxAux { float mx, s1, s2; };
+__device__ inline float categorical_fwd(float* z, float* logp, const bool* mask, int n, SoftmaxAux* aux) {
+  float mx = -3.4028234663852886e38f;
+  for (int i = 0; i < n; ++i) if (mask[i]) mx = fmaxf(mx, z[i]);
+  float s1 = 0.f;
+  for (int i = 0; i < n; ++i) { z[i] = mask[i] ? expf(z[i] - mx) : 0.f; s1 += z[i]; }
+  s1 += 1e-12f;
+  float s2 = 0.f;
+  for (int i = 0; i < n; ++i) { z[i] = z[i] / s1; s2 += z[i]; }
+  float ent = 0.f;
+  for (int i = 0; i < n; ++i) {
+    z[i] = z[i] / s2;
+    logp[i] = logf(fminf(fmaxf(z[i], kF32Eps), 1.f - kF32Eps));
+    ent -= z[i] * logp[i];
+  }
+  if (aux) { aux->mx = mx; aux->s1 = s1; aux->s2 = s2; }
+  return ent;
+}
+// Backward of categorical_fwd: given g_logp (cotangent of L[pick]) and g_ent, p' and L as produced above,
+// writes dz (cotangent of the raw logits) into dz[].
+__device__ inline void categorical_bwd(const float* p, const float* logp, const bool* mask, int n, int pick, float g_logp,
+                                       float g_ent, const SoftmaxAux& aux, float* dz) {
+  // dL/dp'_i
+  float dotq = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const bool pass = p[i] >= kF32Eps && p[i] <= 1.f - kF32Eps;  // clamp passes gradient inside [min, max]
+    float dL = (i == pick ? g_logp : 0.f) - g_ent * p[i];         // through L_i
+    float dp = (pass ? dL / p[i] : 0.f) - g_ent * logp[i];        // + direct -g_ent * L_i
+    dz[i] = dp;
+  }
+  // p' = q / s2  ->  dq_i = (dp_i - sum_j dp_j p'_j) / s2
+  for (int i = 0; i < n; ++i) dotq += dz[i] * p[i];
+  for (int i = 0; i < n; ++i) dz[i] = (dz[i] - dotq) / aux.s2;
+  // q = e / s1 * mask, s1 = sum e + 1e-12 -> de_i = mask_i dq_i / s1 - sum_j (mask_j dq_j q_j) / s1 ; e = exp(z - mx)
+  float dots = 0.f;
+  for (int i = 0; i < n; ++i) {
+    if (!mask[i]) dz[i] = 0.f;
+    dots += dz[i] * (p[i] * aux.s2);  // q_i = p'_i * s2
+  }
+  for (int i = 0; i < n; ++i) {
+    const float q = p[i] * aux.s2, e = q * aux.s1;
+    dz[i] = mask[i] ? (dz[i] / aux.s1 - dots / aux.s1) * e : 0.f;
+  }
+}
+
+// y[o] = b[o] + sum_k Wt[k][o] x[k]  for o < n_out (threads over o); optional relu.  x in shared memory.
+__device__ __forceinline__ void gemv_t(const float* __restrict__ Wt, const float* __restrict__ bias, const float* x, int K,
+                                       int n_out, bool relu, float* y) {
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    float acc = bias[o];
+    for (int k = 0; k < K; ++k) acc = fmaf(Wt[(long long)k * n_out + o], x[k], acc);
+    y[o] = relu ? fmaxf(acc, 0.f) : acc;
+  }
+}
+
+struct PolicyScalars {
+  int n, focus, element;
+  bool focus_valid;
+  float dist;
+  float ent_f, ent_e, logp_f, logp_e, logp_d, logp_o, v;
+  float k_raw, inv_sqrt_k, log_z, lse_max, lse_sum;  // spherical
+  float2 s_o;                                          // s(orientation)
+  SoftmaxAux aux_f, aux_e;
+};
+
+// s(x) = sum_lm a_lm Y_lm(x)
+__device__ __forceinline__ float2 sph_sum(const float2* a, const float2* y) {
+  float2 s = make_float2(0.f, 0.f);
+  MGB_UNROLL
+  for (int q = 0; q < kM; ++q) cfma(s, a[q], y[q]);
+  return s;
+}
+
+// Mixer cat vector (covariant/modules.py:180-190): ag = d * ecov ; sq = CG(ag x ag) ; cat_l = [ag | sq | ecov]
+__device__ __forceinline__ void mixer_build_cat(const CovDesc& d, const float2* ecov, float dist, float2* scratch_ag, float2* cat) {
+  const int CPE = d.CPE;
+  for (int idx = threadIdx.x; idx < kM * CPE; idx += blockDim.x) {
+    const int lm = idx / CPE, c = idx % CPE, l = ell_of_lm(lm);
+    const float2 e = ecov[idx];
+    const float2 ag = make_float2(dist * e.x, dist * e.y);
+    scratch_ag[idx] = ag;
+    const int base = d.offM[l] + (lm - l * l) * d.catM[l];
+    cat[base + c] = ag;
+    cat[base + d.inM_block[l] * CPE + c] = e;
+  }
+  __syncthreads();
+  int sqb[kNL] = {1, 1, 1, 1, 1};
+  cg_gather<true>(d.mix_sq, CPE, scratch_ag, d.catM, d.offM, sqb, cat, 1.f);
+  __syncthreads();
+}
+
+// Everything the reference's step() does after the Cormorant body, for canvas b.  Leaves intermediates in `s`.
+__device__ inline void policy_forward(const CovDesc& d, const float* __restrict__ P, const float* __restrict__ Wt, int b,
+                                      const int* __restrict__ n_atoms, const float* __restrict__ bags,
+                                      const float* __restrict__ actions, const float* __restrict__ A_last,
+                                      const float* __restrict__ inv, const float* __restrict__ flogit,
+                                      const float* __restrict__ trans, PolicySmem& s, PolicyScalars& ps) {
+  const int N = d.N, Z = d.Z, CPE = d.CPE, Wd = d.Wd, G = d.G, tau = d.Cout;
+  const int n = n_atoms[b];
+  const float* act = actions + (long long)b * 6;
+  ps.n = n;
+  ps.focus = (int)rintf(act[0]);
+  ps.element = (int)rintf(act[1]);
+  ps.dist = act[2];
+  ps.focus_valid = ps.focus < n;
+  const int nact = n > 1 ? n : 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s.fl[i] = i < nact ? flogit[(long long)b * N + i] : 0.f;
+  for (int k = threadIdx.x; k < d.lat; k += blockDim.x) s.finv[k] = inv[((long long)b * N + ps.focus) * d.lat + k];
+  for (int idx = threadIdx.x; idx < kM * CPE; idx += blockDim.x) {
+    const int lm = idx / CPE, c = idx % CPE;
+    float2 v = make_float2(0.f, 0.f);
+    if (ps.focus_valid)
+      v = reinterpret_cast<const float2*>(A_last)[(((long long)b * N + ps.focus) * kM + lm) * tau + ps.element * CPE + c];
+    s.ecov[idx] = v;
+  }
+  for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += trans[((long long)b * N + i) * Wd + h];
+    s.vf[h] = acc;
+  }
+  __syncthreads();
+  // --- focus (agent.py:223-240)
+  if (threadIdx.x == 0) {
+    bool mask[64];
+    for (int i = 0; i < N; ++i) mask[i] = i < nact;
+    ps.ent_f = categorical_fwd(s.fl, s.flog, mask, N, &ps.aux_f);
+    s.misc[0] = ps.ent_f; s.misc[1] = ps.aux_f.mx; s.misc[2] = ps.aux_f.s1; s.misc[3] = ps.aux_f.s2;
+  }
+  // --- element (agent.py:243-259)
+  gemv_t(Wt + d.element.W0t, P + d.element.b0, s.finv, d.lat, Wd, true, s.he);
+  atomic_scalars_row(s.ecov, CPE, CPE, s.einv, threadIdx.x, blockDim.x);
+  __syncthreads();
+  gemv_t(Wt + d.element.W1t, P + d.element.b1, s.he, Wd, Z, false, s.el);
+  // --- distance (agent.py:263-276)
+  gemv_t(Wt + d.dist.W0t, P + d.dist.b0, s.einv, d.latE, Wd, true, s.hd);
+  // --- value (agent.py:313-316)
+  gemv_t(Wt + d.value.W0t, P + d.value.b0, s.vf, Wd, Wd, true, s.hv);
+  __syncthreads();
+  gemv_t(Wt + d.dist.W1t, P + d.dist.b1, s.hd, Wd, 2 * G, false, s.yd);
+  if (threadIdx.x == 0) {
+    bool mask[MGB_MAX_SPECIES];
+    for (int z = 0; z < Z; ++z) mask[z] = bags[(long long)b * Z + z] > 0.f;
+    ps.ent_e = categorical_fwd(s.el, s.elog, mask, Z, &ps.aux_e);
+    s.misc[4] = ps.ent_e; s.misc[5] = ps.aux_e.mx; s.misc[6] = ps.aux_e.s1; s.misc[7] = ps.aux_e.s2;
+  }
+  {  // v = b1 + W1 hv  (block reduction)
+    float part = 0.f;
+    for (int h = threadIdx.x; h < Wd; h += blockDim.x) part += P[d.value.W1 + h] * s.hv[h];
+    ps.v = block_sum(part, s.red) + P[d.value.b1];
+  }
+  __syncthreads();
+  ps.ent_f = s.misc[0]; ps.aux_f.mx = s.misc[1]; ps.aux_f.s1 = s.misc[2]; ps.aux_f.s2 = s.misc[3];
+  ps.ent_e = s.misc[4]; ps.aux_e.mx = s.misc[5]; ps.aux_e.s1 = s.misc[6]; ps.aux_e.s2 = s.misc[7];
+  ps.logp_f = s.flog[ps.focus];
+  ps.logp_e = s.elog[ps.element];
+  {  // GMM log-prob (gmm.py:8-18): every thread computes the same few numbers
+    float lse_g = -3.0e38f;
+    for (int k = 0; k < G; ++k) lse_g = fmaxf(lse_g, s.yd[k]);
+    float sg = 0.f;
+    for (int k = 0; k < G; ++k) sg += expf(s.yd[k] - lse_g);
+    lse_g += logf(sg);
+    const float hw = 0.5f * (d.dmax - d.dmin), ctr = 0.5f * (d.dmin + d.dmax);
+    float t[8], tm = -3.0e38f;
+    for (int k = 0; k < G; ++k) {
+      const float mu = tanhf(s.yd[G + k]) * hw + ctr;
+      const float sd = fmaxf(expf(P[d.p_logstd + k]), 1e-6f);
+      const float df = ps.dist - mu;
+      t[k] = -(df * df) / (2.f * sd * sd) - logf(sd) - kLogSqrt2Pi + (s.yd[k] - lse_g);
+      tm = fmaxf(tm, t[k]);
+    }
+    float st = 0.f;
+    for (int k = 0; k < G; ++k) st += expf(t[k] - tm);
+    ps.logp_d = tm + logf(st);
+  }
+  // --- condition on distance + spherical distribution (agent.py:279-292)
+  mixer_build_cat(d, s.ecov, ps.dist, s.cond /* scratch for ag */, s.cat);
+  mix_rows<4, 3>(d.units_hidden, d.n_units_hidden, d.catM, d.offM, d.offWM, CPE,
+                 reinterpret_cast<const float2*>(P + d.p_mixW), s.cat, s.cond);
+  __syncthreads();
+  if (threadIdx.x < kM) {
+    float2 a = make_float2(0.f, 0.f);
+    for (int c = 0; c < CPE; ++c) { a.x += s.cond[threadIdx.x * CPE + c].x; a.y += s.cond[threadIdx.x * CPE + c].y; }
+    s.alm[threadIdx.x] = a;
+  }
+  __syncthreads();
+  float k_raw = 0.f;
+  for (int q = 0; q < kM; ++q) k_raw += s.alm[q].x * s.alm[q].x + s.alm[q].y * s.alm[q].y;
+  ps.k_raw = k_raw;
+  ps.inv_sqrt_k = 1.f / sqrtf(fmaxf(k_raw, 1e-10f));
+  __syncthreads();
+  if (threadIdx.x < kM) {
+    s.alm[threadIdx.x].x *= ps.inv_sqrt_k;
+    s.alm[threadIdx.x].y *= ps.inv_sqrt_k;
+  }
+  __syncthreads();
+  float2 a_loc[kM];
+  MGB_UNROLL
+  for (int q = 0; q < kM; ++q) a_loc[q] = s.alm[q];
+  {
+    float ox = act[3], oy = act[4], oz = act[5];
+    const float nr = sqrtf(ox * ox + oy * oy + oz * oz);
+    if (nr > 0.f) { ox /= nr; oy /= nr; oz /= nr; } else { ox = oy = oz = 0.f; }
+    float2 y[kM];
+    sph_harm_l4(ox, oy, oz, false, false, y);
+    ps.s_o = sph_sum(a_loc, y);
+  }
+  const float so2 = ps.s_o.x * ps.s_o.x + ps.s_o.y * ps.s_o.y;
+  if (d.has_beta) {
+    // log Z = log 4 pi + logsumexp_g(-beta |s(x_g)|^2 + log w_g)   (spherical_dists.py:208-215)
+    float mx = -3.0e38f;
+    for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
+      const float2 sg = sph_sum(a_loc, reinterpret_cast<const float2*>(d.leb_y) + (long long)g * kM);
+      mx = fmaxf(mx, -d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g]);
+    }
+    mx = block_max(mx, s.red);
+    float sum = 0.f;
+    for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
+      const float2 sg = sph_sum(a_loc, reinterpret_cast<const float2*>(d.leb_y) + (long long)g * kM);
+      sum += expf(-d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g] - mx);
+    }
+    sum = block_sum(sum, s.red);
+    ps.lse_max = mx;
+    ps.lse_sum = sum;
+    ps.log_z = kLog4Pi + mx + logf(sum);
+    ps.logp_o = -d.beta * so2 - ps.log_z;
+  } else {
+    ps.log_z = 0.f;
+    const float p = (n == 0) ? (1.f / kFourPi) : so2;   // SO3Distribution.prob with the `empty` override
+    ps.logp_o = logf(fmaxf(p, 1e-10f));
+  }
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
+             const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
+             const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
+             const float* __restrict__ trans, mgb_cov_outputs out) {
+  const CovDesc& d = *dp;
+  MGB_DYN_SMEM(float, sm);
+  PolicySmem s = policy_smem_carve(d, sm);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    PolicyScalars ps;
+    __syncthreads();
+    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps);
+    if (threadIdx.x == 0) {
+      out.logp[b] = ((ps.logp_f + ps.logp_e) + ps.logp_d) + ps.logp_o;
+      out.ent[b] = ps.ent_f + ps.ent_e;
+      out.v[b] = ps.v;
+      if (out.logp_parts) {
+        out.logp_parts[b * 4 + 0] = ps.logp_f; out.logp_parts[b * 4 + 1] = ps.logp_e;
+        out.logp_parts[b * 4 + 2] = ps.logp_d; out.logp_parts[b * 4 + 3] = ps.logp_o;
+      }
+      if (out.log_z) out.log_z[b] = ps.log_z;
+    }
+    if (out.focus_probs) for (int i = threadIdx.x; i < d.N; i += blockDim.x) out.focus_probs[(long long)b * d.N + i] = s.fl[i];
+    if (out.element_probs) for (int z = threadIdx.x; z < d.Z; z += blockDim.x) out.element_probs[(long long)b * d.Z + z] = s.el[z];
+    if (out.coefficients)
+      for (int idx = threadIdx.x; idx < kM * d.CPE; idx += blockDim.x) {
+        reinterpret_cast<float2*>(out.coefficients)[(long long)b * kM * d.CPE + idx] =
+            make_float2(s.cond[idx].x * ps.inv_sqrt_k, s.cond[idx].y * ps.inv_sqrt_k);
+      }
+    if (out.gmm && threadIdx.x == 0) {
+      const int G = d.G;
+      float lse = -3.0e38f;
+      for (int k = 0; k < G; ++k) lse = fmaxf(lse, s.yd[k]);
+      float sg = 0.f;
+      for (int k = 0; k < G; ++k) sg += expf(s.yd[k] - lse);
+      lse += logf(sg);
+      for (int k = 0; k < G; ++k) {
+        out.gmm[((long long)b * 3 + 0) * G + k] = s.yd[k] - lse;
+        out.gmm[((long long)b * 3 + 1) * G + k] = tanhf(s.yd[G + k]) * 0.5f * (d.dmax - d.dmin) + 0.5f * (d.dmin + d.dmax);
+        out.gmm[((long long)b * 3 + 2) * G + k] = fmaxf(expf(P[d.p_logstd + k]), 1e-6f);
+      }
+    }
+  }
+}
+
+}  // namespace mgb

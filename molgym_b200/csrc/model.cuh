@@ -1,0 +1,158 @@
+// model.cuh — descriptors shared by host and device code + the host-side plan builder.
+//
+// Reference structure being described (paths relative to the reference tree):
+//   molgym/agents/covariant/agent.py:59-143   (module inventory of CovariantAC)
+//   molgym/agents/covariant/modules.py:11-135 (Cormorant stack configuration), :138-190 (CormorantMixer)
+// and the cormorant package semantics restated in oracle/thirdparty/cormorant (CG product path ordering,
+// cat orderings, radial basis).
+#pragma once
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mgb {
+
+constexpr int kMaxLevels = MGB_MAX_LEVELS;
+constexpr int kMaxMixUnits = 32;
+
+// A unit of the channel-mixing contraction: rows (l, m0 .. m0+nm-1) handled by one warp pass.
+struct MixUnit {
+  int l, m0, nm;
+};
+
+struct MlpDesc {
+  int in, hidden, out;
+  long long W0, b0, W1, b1;      // float offsets into the flat parameter buffer (reference layout [out,in])
+  long long W0t, W1t;            // float offsets into the transposed-weights scratch ([in,out])
+};
+
+struct CovDesc {
+  int N, Z, K;                   // canvas size, species, number of CG levels
+  int C, CPE, Cout;              // hidden channels, channels per element, last-level channels (Z*CPE)
+  int G, Wd;                     // gaussians, MLP width
+  int lat, latE;                 // invariant feature sizes (48Z and 48 for the defaults)
+  int S_in;                      // input scalar features per atom: Z*3 + Z
+  int zs[MGB_MAX_SPECIES];
+  float charge_scale, bag_scale;
+  float cut_rad, cut_width;      // soft cutoff (agent.py:66-69)
+  float dmin, dmax;
+  int has_beta;
+  float beta;
+  long long p_inW, p_inb;        // InputLinear
+  LevelDesc lv[kMaxLevels];
+  // mixer (CormorantMixer): cat = [ag(CPE) | sq blocks | in(CPE)]
+  int catM[kNL], offM[kNL], totM, offWM[kNL], totWM, inM_block[kNL];
+  long long p_mixW;
+  CgTable mix_sq;
+  MlpDesc focus, element, dist, trans, value;
+  long long p_logstd;
+  long long n_params;
+  long long n_wt;                // floats of transposed-weight scratch
+  long long wt_edge[kMaxLevels]; // float offset of transposed edge weights [l][k][c'][2] in the scratch
+  int n_grid;                    // Lebedev points
+  const float* leb_y;            // [n_grid][25][2]  Y_lm(x_g), 'qm' norm, no conjugation
+  const float* leb_logw;         // [n_grid]
+  int n_units_hidden, n_units_out;
+  MixUnit units_hidden[kMaxMixUnits], units_out[kMaxMixUnits];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------------
+inline double factorial_d(int n) {
+  double r = 1.0;
+  for (int i = 2; i <= n; ++i) r *= i;
+  return r;
+}
+
+// <j1 m1 j2 m2 | j m>, Racah's formula (same convention as oracle/thirdparty/cormorant/cg_lib.py::clebsch).
+inline double clebsch_gordan(int j1, int m1, int j2, int m2, int j, int m) {
+  if (m1 + m2 != m || j < std::abs(j1 - j2) || j > j1 + j2) return 0.0;
+  if (std::abs(m1) > j1 || std::abs(m2) > j2 || std::abs(m) > j) return 0.0;
+  auto f = factorial_d;
+  double pref = (2 * j + 1) * f(j + j1 - j2) * f(j - j1 + j2) * f(j1 + j2 - j) / f(j1 + j2 + j + 1);
+  pref *= f(j + m) * f(j - m) * f(j1 - m1) * f(j1 + m1) * f(j2 - m2) * f(j2 + m2);
+  double tot = 0.0;
+  for (int k = 0; k <= j1 + j2 - j; ++k) {
+    int a[6] = {k, j1 + j2 - j - k, j1 - m1 - k, j2 + m2 - k, j - j2 + m1 + k, j - j1 - m2 + k};
+    bool ok = true;
+    double den = 1.0;
+    for (int x : a) {
+      if (x < 0) { ok = false; break; }
+      den *= f(x);
+    }
+    if (!ok) continue;
+    tot += ((k & 1) ? -1.0 : 1.0) / den;
+  }
+  return tot * std::sqrt(pref);
+}
+
+struct HostCgTable {
+  int n_out = 0, n_pair = 0, nlm2 = 0;
+  int n_blocks[kNL] = {0, 0, 0, 0, 0};  // number of channel blocks (paths) ending in each l
+  std::vector<int> out_l, out_m, out_block, term_start, term_lm1, term_lm2;
+  std::vector<float> term_coef;
+  std::vector<int> pair_start, pair_out;
+  std::vector<float> pair_coef;
+};
+
+// CG product table for rep1 with ells 0..n1-1 and rep2 with ells 0..n2-1, truncated at kL, paths enumerated
+// l1 outer / l2 inner and outputs of one l concatenated in that order (cg_lib.py::cg_product).
+inline HostCgTable build_cg_table(int n1, int n2) {
+  HostCgTable t;
+  const int nlm1 = n1 * n1, nlm2 = n2 * n2;
+  t.nlm2 = nlm2;
+  t.n_pair = nlm1 * nlm2;
+  std::vector<std::vector<std::pair<int, float>>> by_pair(t.n_pair);
+  t.term_start.push_back(0);
+  for (int l1 = 0; l1 < n1; ++l1)
+    for (int l2 = 0; l2 < n2; ++l2)
+      for (int l = std::abs(l1 - l2); l <= std::min(l1 + l2, kL); ++l) {
+        const int block = t.n_blocks[l]++;
+        for (int m = -l; m <= l; ++m) {
+          const int o = t.n_out++;
+          t.out_l.push_back(l);
+          t.out_m.push_back(m + l);
+          t.out_block.push_back(block);
+          for (int m1 = -l1; m1 <= l1; ++m1) {
+            const int m2 = m - m1;
+            if (std::abs(m2) > l2) continue;
+            const double cg = clebsch_gordan(l1, m1, l2, m2, l, m);
+            if (cg == 0.0) continue;
+            const int a = lm_index(l1, m1), b = lm_index(l2, m2);
+            t.term_lm1.push_back(a);
+            t.term_lm2.push_back(b);
+            t.term_coef.push_back((float)cg);
+            by_pair[a * nlm2 + b].push_back({o, (float)cg});
+          }
+          t.term_start.push_back((int)t.term_lm1.size());
+        }
+      }
+  t.pair_start.push_back(0);
+  for (auto& v : by_pair) {
+    for (auto& pr : v) {
+      t.pair_out.push_back(pr.first);
+      t.pair_coef.push_back(pr.second);
+    }
+    t.pair_start.push_back((int)t.pair_out.size());
+  }
+  return t;
+}
+
+// Greedy split of the 25 (l, m) rows into warp units of <= 3 consecutive m of the same l.
+inline int build_mix_units(MixUnit* units, int max_nm) {
+  int n = 0;
+  for (int l = kL; l >= 0; --l) {  // heavy rows first
+    int m = 0;
+    while (m < 2 * l + 1) {
+      int nm = std::min(max_nm, 2 * l + 1 - m);
+      units[n++] = MixUnit{l, m, nm};
+      m += nm;
+    }
+  }
+  return n;
+}
+
+}  // namespace mgb

@@ -1,0 +1,189 @@
+// plan.cuh — host-side plan: descriptors, Clebsch-Gordan tables, parameter layout, workspace carving.
+#pragma once
+#include <cstdarg>
+#include <memory>
+
+#include "heads.cuh"
+
+struct mgb_cov_plan {
+  mgb_cov_config cfg;
+  mgb::CovDesc desc;                 // host copy (device pointers inside)
+  mgb::CovDesc* d_desc = nullptr;    // device copy
+  void* d_tables = nullptr;          // one allocation holding every table
+  std::vector<mgb::TransposeSeg> segs;
+  mgb::TransposeSeg* d_segs = nullptr;
+  std::vector<long long> p_offsets, p_numels;
+  int forward_batch = -1;            // batch of the last forward on this plan's workspace (backward must match)
+};
+
+namespace mgb {
+
+inline thread_local char g_err[512] = "";
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define MGB_CUDA_OK(expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) return mgb::fail(MGB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+// Bump allocator over one host staging buffer mirrored to the device.
+struct TableArena {
+  std::vector<unsigned char> host;
+  size_t add(const void* p, size_t bytes) {
+    size_t off = (host.size() + 15) & ~size_t(15);
+    host.resize(off + bytes);
+    std::memcpy(host.data() + off, p, bytes);
+    return off;
+  }
+};
+struct PendingTable {
+  CgTable* dst;
+  size_t o_out_l, o_out_m, o_out_block, o_term_start, o_lm1, o_lm2, o_coef, o_pstart, o_pout, o_pcoef;
+};
+inline PendingTable stage_table(TableArena& a, const HostCgTable& h, CgTable* dst) {
+  dst->n_out = h.n_out; dst->n_pair = h.n_pair; dst->nlm2 = h.nlm2;
+  PendingTable p;
+  p.dst = dst;
+  auto vi = [&](const std::vector<int>& v) { return a.add(v.data(), v.size() * sizeof(int)); };
+  auto vf = [&](const std::vector<float>& v) { return a.add(v.data(), v.size() * sizeof(float)); };
+  p.o_out_l = vi(h.out_l); p.o_out_m = vi(h.out_m); p.o_out_block = vi(h.out_block); p.o_term_start = vi(h.term_start);
+  p.o_lm1 = vi(h.term_lm1); p.o_lm2 = vi(h.term_lm2); p.o_coef = vf(h.term_coef);
+  p.o_pstart = vi(h.pair_start); p.o_pout = vi(h.pair_out); p.o_pcoef = vf(h.pair_coef);
+  return p;
+}
+inline void resolve_table(const PendingTable& p, const unsigned char* base) {
+  CgTable* t = p.dst;
+  t->out_l = (const int*)(base + p.o_out_l); t->out_m = (const int*)(base + p.o_out_m);
+  t->out_block = (const int*)(base + p.o_out_block); t->term_start = (const int*)(base + p.o_term_start);
+  t->term_lm1 = (const int*)(base + p.o_lm1); t->term_lm2 = (const int*)(base + p.o_lm2);
+  t->term_coef = (const float*)(base + p.o_coef); t->pair_start = (const int*)(base + p.o_pstart);
+  t->pair_out = (const int*)(base + p.o_pout); t->pair_coef = (const float*)(base + p.o_pcoef);
+}
+
+// Complex spherical harmonics on the host in double (same closed forms as sph_harm_l4), 'qm' norm, no conjugation,
+// unit-vector argument: used for the Lebedev table.
+inline void host_sph_harm(double x, double y, double z, double* out /* [25][2] */) {
+  const double r2 = x * x + y * y + z * z, z2 = z * z;
+  double e[5][2] = {{1, 0}, {x, y}, {x * x - y * y, 2 * x * y}, {0, 0}, {0, 0}};
+  e[3][0] = e[2][0] * x - e[2][1] * y; e[3][1] = e[2][0] * y + e[2][1] * x;
+  e[4][0] = e[2][0] * e[2][0] - e[2][1] * e[2][1]; e[4][1] = 2 * e[2][0] * e[2][1];
+  double dlm[5][5] = {};
+  dlm[0][0] = 1;
+  dlm[1][0] = z; dlm[1][1] = 1;
+  dlm[2][0] = 0.5 * (3 * z2 - r2); dlm[2][1] = 3 * z; dlm[2][2] = 3;
+  dlm[3][0] = 0.5 * z * (5 * z2 - 3 * r2); dlm[3][1] = 0.5 * (15 * z2 - 3 * r2); dlm[3][2] = 15 * z; dlm[3][3] = 15;
+  dlm[4][0] = 0.125 * (35 * z2 * z2 - 30 * z2 * r2 + 3 * r2 * r2); dlm[4][1] = 0.5 * z * (35 * z2 - 15 * r2);
+  dlm[4][2] = 0.5 * (105 * z2 - 15 * r2); dlm[4][3] = 105 * z; dlm[4][4] = 105;
+  const double pi = 3.14159265358979323846;
+  for (int l = 0; l <= 4; ++l)
+    for (int m = 0; m <= l; ++m) {
+      const double nrm = std::sqrt((2 * l + 1) / (4 * pi) * factorial_d(l - m) / factorial_d(l + m));
+      const double a = nrm * dlm[l][m];
+      const double sg = (m & 1) ? -1.0 : 1.0;
+      out[(l * l + l + m) * 2 + 0] = sg * a * e[m][0];
+      out[(l * l + l + m) * 2 + 1] = sg * a * e[m][1];
+      if (m > 0) {
+        out[(l * l + l - m) * 2 + 0] = a * e[m][0];
+        out[(l * l + l - m) * 2 + 1] = -a * e[m][1];
+      }
+    }
+}
+
+inline void fill_mlp(MlpDesc& m, int in, int hidden, int out, long long& p, long long& wt) {
+  m.in = in; m.hidden = hidden; m.out = out;
+  m.W0 = p; p += (long long)hidden * in;
+  m.b0 = p; p += hidden;
+  m.W1 = p; p += (long long)out * hidden;
+  m.b1 = p; p += out;
+  m.W0t = wt; wt += (long long)hidden * in;
+  m.W1t = wt; wt += (long long)out * hidden;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Workspace carving (device pointers).  Everything a forward leaves for its backward lives here.
+// ------------------------------------------------------------------------------------------------------------
+struct CovWs {
+  int* n_atoms;
+  float* Wt;                      // transposed weights scratch
+  float* X;                       // [B,N,S_in]
+  float* A[kMaxLevels + 1];       // A[0] [B,N,1,C,2]; A[k] [B,N,25,C_k,2]
+  float* E[kMaxLevels];           // [B,N,N,5,C,2]
+  float* cat[kMaxLevels];         // [B,N,totA_k,2]
+  float* inv;                     // [B,N,lat]
+  float* hf, *flogit, *ht0, *trans;       // rows
+  // backward
+  float* finv, *he, *einv, *hd, *vf, *hv;  // per canvas activations saved by policy_bwd for the weight gradients
+  float* dhe, *dye, *dhd, *dyd, *dhv, *dyv, *dvf;
+  float* dflogit, *dhf, *dht0, *dtrans, *dinv;
+  float* dA[2];                   // ping-pong, each [B,N,25,Cmax,2]
+  float* dE[2];                   // ping-pong, each [B,N,N,5,C,2]
+  float* dD;                      // [B,N,N,5C,2]
+  double* loss_acc;               // [16]
+  DwProblem* dw_probs;            // [16]
+  size_t bytes;
+};
+
+inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
+  CovWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((unsigned char*)base + off) : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  const size_t BN = (size_t)B * d.N, BNN = BN * d.N;
+  const int C = d.C;
+  int cmax = std::max(C, d.Cout);
+  w.n_atoms = (int*)take(sizeof(int) * B);
+  w.Wt = (float*)take(sizeof(float) * d.n_wt);
+  w.X = (float*)take(sizeof(float) * BN * d.S_in);
+  w.A[0] = (float*)take(sizeof(float) * BN * C * 2);
+  for (int k = 0; k < d.K; ++k) {
+    w.A[k + 1] = (float*)take(sizeof(float) * BN * kM * d.lv[k].Cout * 2);
+    w.E[k] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+    w.cat[k] = (float*)take(sizeof(float) * BN * d.lv[k].totA * 2);
+  }
+  w.inv = (float*)take(sizeof(float) * BN * d.lat);
+  w.hf = (float*)take(sizeof(float) * BN * d.Wd);
+  w.flogit = (float*)take(sizeof(float) * BN);
+  w.ht0 = (float*)take(sizeof(float) * BN * d.Wd);
+  w.trans = (float*)take(sizeof(float) * BN * d.Wd);
+  w.finv = (float*)take(sizeof(float) * B * d.lat);
+  w.he = (float*)take(sizeof(float) * B * d.Wd);
+  w.einv = (float*)take(sizeof(float) * B * d.latE);
+  w.hd = (float*)take(sizeof(float) * B * d.Wd);
+  w.vf = (float*)take(sizeof(float) * B * d.Wd);
+  w.hv = (float*)take(sizeof(float) * B * d.Wd);
+  w.dhe = (float*)take(sizeof(float) * B * d.Wd);
+  w.dye = (float*)take(sizeof(float) * B * d.Z);
+  w.dhd = (float*)take(sizeof(float) * B * d.Wd);
+  w.dyd = (float*)take(sizeof(float) * B * 2 * d.G);
+  w.dhv = (float*)take(sizeof(float) * B * d.Wd);
+  w.dyv = (float*)take(sizeof(float) * B);
+  w.dvf = (float*)take(sizeof(float) * B * d.Wd);
+  w.dflogit = (float*)take(sizeof(float) * BN);
+  w.dhf = (float*)take(sizeof(float) * BN * d.Wd);
+  w.dht0 = (float*)take(sizeof(float) * BN * d.Wd);
+  w.dtrans = (float*)take(sizeof(float) * BN * d.Wd);
+  w.dinv = (float*)take(sizeof(float) * BN * d.lat);
+  for (int q = 0; q < 2; ++q) w.dA[q] = (float*)take(sizeof(float) * BN * kM * cmax * 2);
+  for (int q = 0; q < 2; ++q) w.dE[q] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.loss_acc = (double*)take(sizeof(double) * 16);
+  w.dw_probs = (DwProblem*)take(sizeof(DwProblem) * 16);
+  w.bytes = off;
+  return w;
+}
+
+inline int pick_co(int cout) {
+  for (int co : {10, 8, 6, 5, 4}) if (cout % co == 0) return co;
+  return 4;
+}
+
+}  // namespace mgb

@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE — drive the C ABI of the kernel emulator build (tests/cusim/_build/) with numpy arrays.
+
+The same .cu sources as the product, compiled by g++ against cusim.h: lets the CPU-only container check kernel logic
+(indexing, barriers, reductions, hand-written backward) against the oracle before GPU time is spent.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from molgym_b200 import _cabi, build  # noqa: E402
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = build.build_cusim()
+        _LIB = _cabi.bind(ctypes.CDLL(path))
+        assert _LIB.mgb_is_cuda_build() == 0
+    return _LIB
+
+
+def lebedev():
+    from scipy.integrate import lebedev_rule
+    pts, w = lebedev_rule(71)
+    return np.ascontiguousarray(pts.T, dtype=np.float64), np.ascontiguousarray(w / (4 * np.pi), dtype=np.float64)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class CusimCov:
+    def __init__(self, zs, canvas_size, **kw):
+        self.L = lib()
+        self.cfg = _cabi.make_config(zs, canvas_size, **kw)
+        xyz, w = lebedev()
+        plan = ctypes.c_void_p()
+        _cabi.check(self.L, self.L.mgb_cov_plan_create(ctypes.byref(self.cfg), xyz.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                       w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(w),
+                                                       ctypes.byref(plan)))
+        self.plan = plan
+        n = self.L.mgb_cov_param_count(plan)
+        off = (ctypes.c_int64 * n)()
+        num = (ctypes.c_int64 * n)()
+        tot = ctypes.c_int64()
+        _cabi.check(self.L, self.L.mgb_cov_param_layout(plan, off, num, ctypes.byref(tot)))
+        self.offsets, self.numels, self.total = list(off), list(num), tot.value
+        self.names = _cabi.param_names(self.cfg.num_cg_levels)
+        assert len(self.names) == n, (len(self.names), n)
+        self.N, self.Z = canvas_size, len(zs)
+        self.CPE, self.G = self.cfg.num_channels_per_element, self.cfg.num_gaussians
+        self.ws = None
+
+    def __del__(self):
+        try:
+            self.L.mgb_cov_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+    def flatten(self, state_dict):
+        flat = np.zeros(self.total, dtype=np.float32)
+        for name, o, n in zip(self.names, self.offsets, self.numels):
+            v = np.asarray(state_dict[name].detach().cpu().numpy() if hasattr(state_dict[name], 'detach') else state_dict[name],
+                           dtype=np.float32).ravel()
+            assert v.size == n, (name, v.size, n)
+            flat[o:o + n] = v
+        return flat
+
+    def unflatten(self, flat, shapes):
+        return {name: flat[o:o + n].reshape(shapes[name]) for name, o, n in zip(self.names, self.offsets, self.numels)}
+
+    def forward(self, pos, charges, bags, actions, params):
+        B = len(pos)
+        self.B = B
+        self.inputs = [np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(charges, np.int32),
+                       np.ascontiguousarray(bags, np.float32), np.ascontiguousarray(actions, np.float32),
+                       np.ascontiguousarray(params, np.float32)]
+        nbytes = self.L.mgb_cov_workspace_bytes(self.plan, B)
+        self.ws = np.zeros(nbytes // 4 + 64, dtype=np.float32)
+        self.ws_bytes = nbytes
+        N, Z = self.N, self.Z
+        o = dict(logp=np.zeros(B, np.float32), ent=np.zeros(B, np.float32), v=np.zeros(B, np.float32),
+                 logp_parts=np.zeros((B, 4), np.float32), focus_probs=np.zeros((B, N), np.float32),
+                 element_probs=np.zeros((B, Z), np.float32), gmm=np.zeros((B, 3, self.G), np.float32),
+                 coefficients=np.zeros((B, 25, self.CPE, 2), np.float32), log_z=np.zeros(B, np.float32),
+                 covariats=np.zeros((B, N, 25, Z * self.CPE, 2), np.float32))
+        outs = _cabi.CovOutputs(**{k: ptr(v) for k, v in o.items()})
+        _cabi.check(self.L, self.L.mgb_cov_forward(self.plan, B, *[ptr(a) for a in self.inputs], ptr(self.ws), nbytes,
+                                                   ctypes.byref(outs), None))
+        return o
+
+    def backward(self, g_logp, g_ent, g_v, accumulate_into=None):
+        grad = np.zeros(self.total, np.float32) if accumulate_into is None else accumulate_into
+        g = [np.ascontiguousarray(x, np.float32) for x in (g_logp, g_ent, g_v)]
+        _cabi.check(self.L, self.L.mgb_cov_backward(self.plan, self.B, *[ptr(a) for a in self.inputs], ptr(self.ws),
+                                                    self.ws_bytes, ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(grad),
+                                                    0 if accumulate_into is None else 1, None))
+        return grad
