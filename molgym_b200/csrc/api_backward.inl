@@ -1,1 +1,157 @@
-// api_backward.inl — backward launch sequence + PPO loss (part of api.cu).
+// api_backward.inl — backward launch sequence + PPO loss + host packer (part of api.cu).
+
+namespace mgb {
+struct DwProblemList {
+  DwProblem p[12];
+  int n;
+};
+__global__ void k_store_dw_problems(DwProblemList list, DwProblem* __restrict__ dst) {
+  if ((int)threadIdx.x < list.n) dst[threadIdx.x] = list.p[threadIdx.x];
+}
+}  // namespace mgb
+
+template <int NLM2>
+static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
+                           int accumulate_dE, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const LevelDesc& L = d.lv[level];
+  const size_t smem = sizeof(float) * atom_bwd_smem_floats(L);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms, w.A[level], w.E[level],
+             w.dA[(level + 1) & 1], w.dA[level & 1], w.dE[level & 1], accumulate_dE);
+  MGB_LAUNCH_OK("k_atom_bwd");
+  return MGB_OK;
+}
+
+extern "C" {
+
+int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32_t* charges, const float* bags,
+                     const float* actions, const float* P, void* workspace, size_t workspace_bytes, const float* g_logp,
+                     const float* g_ent, const float* g_v, float* grad, int32_t accumulate, void* stream) {
+  if (!plan || !pos || !charges || !bags || !actions || !P || !workspace || !g_logp || !g_ent || !g_v || !grad)
+    return fail(MGB_ERR_INVALID, "null argument");
+  if (plan->forward_batch != B) return fail(MGB_ERR_STATE, "backward(batch=%d) without a matching forward (last forward batch %d)", B, plan->forward_batch);
+  const CovDesc& d = plan->desc;
+  const CovWs w = carve_workspace(d, B, workspace);
+  if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d.N, K = d.K;
+  const size_t BN = (size_t)B * N;
+  const int cmax = std::max(d.C, d.Cout);
+  if (!accumulate) MGB_CUDA_OK(cudaMemsetAsync(grad, 0, sizeof(float) * d.n_params, st));
+  MGB_CUDA_OK(cudaMemsetAsync(w.dinv, 0, sizeof(float) * BN * d.lat, st));
+  MGB_CUDA_OK(cudaMemsetAsync(w.dA[K & 1], 0, sizeof(float) * BN * kM * cmax * 2, st));
+  {
+    PolicyBwdOut o{w.finv, w.he, w.einv, w.hd, w.vf, w.hv, w.dhe, w.dye, w.dhd, w.dyd, w.dhv, w.dyv, w.dvf, w.dflogit, w.dinv, w.dA[K & 1]};
+    const size_t sm = sizeof(float) * (policy_smem_floats(d) + policy_bwd_extra_floats(d));
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int grid = std::min(B, 148 * 2);
+    MGB_LAUNCH(k_policy_bwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
+               w.trans, g_logp, g_ent, g_v, o, grad);
+    MGB_LAUNCH_OK("k_policy_bwd");
+  }
+  {
+    const long long rows = (long long)BN;
+    const size_t sm = sizeof(float) * kRowTile * d.Wd * 3;
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    MGB_LAUNCH(k_rows_mlp_bwd, (unsigned)((rows + kRowTile - 1) / kRowTile), kHeadThreads, sm, st, plan->d_desc, P, w.n_atoms, rows,
+               w.hf, w.dflogit, w.dhf, w.ht0, w.dvf, w.dtrans, w.dht0, w.dinv);
+    MGB_LAUNCH_OK("k_rows_mlp_bwd");
+  }
+  MGB_LAUNCH(k_scalars_bwd, B * N, 64, 0, st, plan->d_desc, w.n_atoms, w.A[K], w.dinv, w.dA[K & 1]);
+  MGB_LAUNCH_OK("k_scalars_bwd");
+  for (int k = K - 1; k >= 0; --k) {
+    const LevelDesc& L = d.lv[k];
+    MGB_CUDA_OK(cudaMemsetAsync(w.dA[k & 1], 0, sizeof(float) * BN * kM * cmax * 2, st));
+    const int acc_dE = (k < K - 1) ? 1 : 0;
+    int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, st);
+    if (rc != MGB_OK) return rc;
+    {
+      const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 7) / 8, 148 * 2));
+      dim3 grid(chunks, kNL);
+      MGB_LAUNCH(k_mix_dw, grid, kMixDwThreads, sizeof(float2) * 9 * L.Cout, st, plan->d_desc, k, B, w.n_atoms, w.cat[k],
+                 w.dA[(k + 1) & 1], grad);
+      MGB_LAUNCH_OK("k_mix_dw");
+    }
+    {
+      const int per_warp = L.sumCatE + 16 + kNL * L.C;
+      const size_t esm = sizeof(float2) * (L.nlm_in * L.C + kEdgeBwdWarps * per_warp);
+      const int grid = (int)std::min<size_t>(BN, 148 * 2);
+      if (k == 0) {
+        MGB_LAUNCH(k_edge_bwd<1>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.A[k],
+                   (const float*)nullptr, w.dE[k & 1], (float*)nullptr, w.dD, grad);
+        MGB_LAUNCH_OK("k_edge_bwd");
+        MGB_LAUNCH(k_dot_bwd<1>, B * N, 64, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
+      } else {
+        MGB_LAUNCH(k_edge_bwd<kNL>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.A[k], w.E[k - 1],
+                   w.dE[k & 1], w.dE[(k - 1) & 1], w.dD, grad);
+        MGB_LAUNCH_OK("k_edge_bwd");
+        MGB_LAUNCH(k_dot_bwd<kNL>, B * N, 256, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
+      }
+      MGB_LAUNCH_OK("k_dot_bwd");
+    }
+  }
+  {
+    DwProblemList list;
+    int q = 0;
+    const long long rows = (long long)BN;
+    auto add = [&](const float* X, const float* dY, long long r, int Kin, int No, int mode, long long dW, long long db) {
+      list.p[q++] = DwProblem{X, dY, r, Kin, No, mode, dW, db};
+    };
+    add(w.inv, w.dhf, rows, d.lat, d.Wd, kRowsActive, d.focus.W0, d.focus.b0);
+    add(w.hf, w.dflogit, rows, d.Wd, 1, kRowsActive, d.focus.W1, d.focus.b1);
+    add(w.inv, w.dht0, rows, d.lat, d.Wd, kRowsValid, d.trans.W0, d.trans.b0);
+    add(w.ht0, w.dtrans, rows, d.Wd, d.Wd, kRowsValid, d.trans.W1, d.trans.b1);
+    add(w.finv, w.dhe, B, d.lat, d.Wd, kRowsAll, d.element.W0, d.element.b0);
+    add(w.he, w.dye, B, d.Wd, d.Z, kRowsAll, d.element.W1, d.element.b1);
+    add(w.einv, w.dhd, B, d.latE, d.Wd, kRowsAll, d.dist.W0, d.dist.b0);
+    add(w.hd, w.dyd, B, d.Wd, 2 * d.G, kRowsAll, d.dist.W1, d.dist.b1);
+    add(w.vf, w.dhv, B, d.Wd, d.Wd, kRowsAll, d.value.W0, d.value.b0);
+    add(w.hv, w.dyv, B, d.Wd, 1, kRowsAll, d.value.W1, d.value.b1);
+    add(w.X, w.dA[0], rows, d.S_in, 2 * d.C, kRowsValid, d.p_inW, d.p_inb);
+    list.n = q;
+    MGB_LAUNCH(k_store_dw_problems, 1, 32, 0, st, list, w.dw_probs);
+    MGB_LAUNCH_OK("k_store_dw_problems");
+    const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 31) / 32, 64));
+    dim3 grid(chunks, q);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, sizeof(float) * kDwRowChunk * kDwTileO, st, w.dw_probs, w.n_atoms, N, grad);
+    MGB_LAUNCH_OK("k_dw_grouped");
+  }
+  return MGB_OK;
+}
+
+int mgb_ppo_loss(int32_t B, const float* logp, const float* ent, const float* v, const float* old_logp, const double* adv,
+                 const double* ret, double clip_ratio, double vf_coef, double entropy_coef, double inv_global_batch,
+                 double* info, float* g_logp, float* g_ent, float* g_v, void* stream) {
+  if (!logp || !ent || !v || !old_logp || !adv || !ret || !info) return fail(MGB_ERR_INVALID, "null argument");
+  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
+  if ((g_logp || g_ent || g_v) && !(g_logp && g_ent && g_v)) return fail(MGB_ERR_INVALID, "gradient outputs must be all set or all NULL");
+  MGB_LAUNCH(k_ppo_loss, 1, 256, 0, (cudaStream_t)stream, B, logp, ent, v, old_logp, adv, ret, clip_ratio, vf_coef, entropy_coef,
+             inv_global_batch, info, g_logp, g_ent, g_v);
+  MGB_LAUNCH_OK("k_ppo_loss");
+  return MGB_OK;
+}
+
+int mgb_pack_observations(const mgb_cov_config* cfg, int32_t B, const int32_t* labels, const double* xyz, float* positions,
+                          int32_t* charges) {
+  if (!cfg || !labels || !xyz || !positions || !charges) return fail(MGB_ERR_INVALID, "null argument");
+  const int N = cfg->canvas_size, Z = cfg->num_species;
+  for (int b = 0; b < B; ++b) {
+    int k = 0;
+    for (int i = 0; i < N; ++i) {
+      const int lab = labels[(size_t)b * N + i];
+      if (lab < 0 || lab >= Z) return fail(MGB_ERR_INVALID, "canvas %d item %d: label %d outside [0, %d)", b, i, lab, Z);
+      if (cfg->zs[lab] == 0) continue;
+      charges[(size_t)b * N + k] = cfg->zs[lab];
+      for (int a = 0; a < 3; ++a) positions[((size_t)b * N + k) * 3 + a] = (float)xyz[((size_t)b * N + i) * 3 + a];
+      ++k;
+    }
+    for (; k < N; ++k) {
+      charges[(size_t)b * N + k] = 0;
+      for (int a = 0; a < 3; ++a) positions[((size_t)b * N + k) * 3 + a] = 0.f;
+    }
+  }
+  return MGB_OK;
+}
+
+}  // extern "C"

@@ -1,4 +1,800 @@
-// cov_backward.cuh — backward kernels (filled in below).
+// cov_backward.cuh — hand-written backward of the covariant actor-critic (the reference relies on torch autograd
+// through molgym/agents/covariant/agent.py:209-334; nothing here has a counterpart file in the reference).
+//
+// Complex tensors are stored as (re, im) pairs and cotangents likewise; for a holomorphic product z = a * b the
+// cotangents are  da += conj(b) * dz,  db += conj(a) * dz.
 #pragma once
 #include "heads.cuh"
-namespace mgb {}
+
+namespace mgb {
+
+#ifdef MGB_CUSIM
+__device__ inline void atomic_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+#else
+__device__ __forceinline__ void atomic_add2(float2* p, float2 v) { atomicAdd(p, v); }  // red.global.add.v2.f32 (sm_90+)
+#endif
+__device__ __forceinline__ void smem_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+
+// cotangent of atomic_scalars_row: d a[lm][t] += ...   (a: [25][stride] complex, dinv: [(L+2)*tau*2])
+__device__ __forceinline__ float2 scalars_bwd_elem(const float2* __restrict__ a, int tau, int stride, const float* __restrict__ dinv,
+                                                   int lm, int t) {
+  const int l = ell_of_lm(lm), m = lm - l * l - l;
+  const float2 p = a[lm * stride + t], q = a[lm_index(l, -m) * stride + t];
+  const float sg = (m & 1) ? -1.f : 1.f;
+  const float dprod = dinv[((1 + l) * tau + t) * 2 + 0], dnorm = dinv[((1 + l) * tau + t) * 2 + 1];
+  float2 g = make_float2(2.f * sg * q.x * dprod + 2.f * p.x * dnorm, -2.f * sg * q.y * dprod + 2.f * p.y * dnorm);
+  if (lm == 0) { g.x += dinv[t * 2 + 0]; g.y += dinv[t * 2 + 1]; }
+  return g;
+}
+
+__global__ void k_scalars_bwd(const CovDesc* __restrict__ dp, const int* __restrict__ n_atoms, const float* __restrict__ A,
+                              const float* __restrict__ dinv, float* __restrict__ dA) {
+  const CovDesc& d = *dp;
+  const int N = d.N, tau = d.Cout;
+  const int b = blockIdx.x / N, i = blockIdx.x % N;
+  if (i >= n_atoms[b]) return;
+  const float2* a = reinterpret_cast<const float2*>(A) + (long long)blockIdx.x * kM * tau;
+  float2* da = reinterpret_cast<float2*>(dA) + (long long)blockIdx.x * kM * tau;
+  const float* di = dinv + (long long)blockIdx.x * d.lat;
+  for (int idx = threadIdx.x; idx < kM * tau; idx += blockDim.x) {
+    const float2 g = scalars_bwd_elem(a, tau, tau, di, idx / tau, idx % tau);
+    da[idx].x += g.x;
+    da[idx].y += g.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-canvas policy head backward.  Persistent CTAs: mixer-weight and log-std cotangents are accumulated on chip
+// over the canvases a CTA visits and flushed once.
+// ------------------------------------------------------------------------------------------------------------
+struct PolicyBwdOut {
+  float* finv; float* he; float* einv; float* hd; float* vf; float* hv;   // activations for the weight gradients
+  float* dhe; float* dye; float* dhd; float* dyd; float* dhv; float* dyv;
+  float* dvf; float* dflogit; float* dinv; float* dA_last;
+};
+
+// y[k] = sum_h W[h][k] x[h]  (reference layout [rows=h][cols=k], lanes over k)
+__device__ __forceinline__ void gemv_n(const float* __restrict__ W, const float* x, int rows, int cols, float* y) {
+  for (int k = threadIdx.x; k < cols; k += blockDim.x) {
+    float acc = 0.f;
+    for (int h = 0; h < rows; ++h) acc = fmaf(W[(long long)h * cols + k], x[h], acc);
+    y[k] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
+             const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
+             const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
+             const float* __restrict__ trans, const float* __restrict__ g_logp, const float* __restrict__ g_ent,
+             const float* __restrict__ g_v, PolicyBwdOut o, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  MGB_DYN_SMEM(float, sm);
+  PolicySmem s = policy_smem_carve(d, sm);
+  const int Wd = d.Wd, Z = d.Z, G = d.G, CPE = d.CPE, N = d.N;
+  float* extra = sm + policy_smem_floats(d);
+  float* s_dh = extra;                                                // [Wd] scratch
+  float* s_dx = s_dh + Wd;                                            // [max(lat, Wd)]
+  float2* s_dcat = reinterpret_cast<float2*>(s_dx + (d.lat > Wd ? d.lat : Wd));   // [totM]
+  float2* s_dWM = s_dcat + d.totM;                                    // [totWM]  accumulated over canvases
+  float2* s_decov = s_dWM + d.totWM;                                  // [25][CPE]
+  float2* s_ag = s_decov + kM * CPE;                                  // [25][CPE]
+  float2* s_da = s_ag + kM * CPE;                                     // [25]
+  float* s_small = reinterpret_cast<float*>(s_da + kM);               // [64]
+  for (int idx = threadIdx.x; idx < d.totWM; idx += blockDim.x) s_dWM[idx] = make_float2(0.f, 0.f);
+  float acc_logstd[8];
+  for (int k = 0; k < 8; ++k) acc_logstd[k] = 0.f;
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    PolicyScalars ps;
+    __syncthreads();
+    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps);
+    const float gl = g_logp[b], ge = g_ent[b], gv = g_v[b];
+    const int nact = ps.n > 1 ? ps.n : 1;
+    // ---- value head
+    for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+      const float dh = s.hv[h] > 0.f ? P[d.value.W1 + h] * gv : 0.f;
+      s_dh[h] = dh;
+      o.dhv[(long long)b * Wd + h] = dh;
+      o.hv[(long long)b * Wd + h] = s.hv[h];
+      o.vf[(long long)b * Wd + h] = s.vf[h];
+    }
+    if (threadIdx.x == 0) o.dyv[b] = gv;
+    __syncthreads();
+    gemv_n(P + d.value.W0, s_dh, Wd, Wd, s_dx);
+    __syncthreads();
+    for (int k = threadIdx.x; k < Wd; k += blockDim.x) o.dvf[(long long)b * Wd + k] = s_dx[k];
+    // ---- focus + element categoricals
+    if (threadIdx.x == 0) {
+      bool mask[64];
+      float dz[64];
+      for (int i = 0; i < N; ++i) mask[i] = i < nact;
+      categorical_bwd(s.fl, s.flog, mask, N, ps.focus, gl, ge, ps.aux_f, dz);
+      for (int i = 0; i < N; ++i) o.dflogit[(long long)b * N + i] = dz[i];
+      bool emask[MGB_MAX_SPECIES];
+      for (int z = 0; z < Z; ++z) emask[z] = bags[(long long)b * Z + z] > 0.f;
+      categorical_bwd(s.el, s.elog, emask, Z, ps.element, gl, ge, ps.aux_e, s_small);
+      for (int z = 0; z < Z; ++z) o.dye[(long long)b * Z + z] = s_small[z];
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+      float acc = 0.f;
+      for (int z = 0; z < Z; ++z) acc = fmaf(P[d.element.W1 + (long long)z * Wd + h], s_small[z], acc);
+      const float dh = s.he[h] > 0.f ? acc : 0.f;
+      s_dh[h] = dh;
+      o.dhe[(long long)b * Wd + h] = dh;
+      o.he[(long long)b * Wd + h] = s.he[h];
+    }
+    for (int k = threadIdx.x; k < d.lat; k += blockDim.x) o.finv[(long long)b * d.lat + k] = s.finv[k];
+    __syncthreads();
+    gemv_n(P + d.element.W0, s_dh, Wd, d.lat, s_dx);
+    __syncthreads();
+    for (int k = threadIdx.x; k < d.lat; k += blockDim.x) o.dinv[((long long)b * N + ps.focus) * d.lat + k] += s_dx[k];
+    __syncthreads();
+    // ---- distance (GMM) head
+    if (threadIdx.x == 0) {
+      float lse_g = -3.0e38f;
+      for (int k = 0; k < G; ++k) lse_g = fmaxf(lse_g, s.yd[k]);
+      float sg = 0.f;
+      for (int k = 0; k < G; ++k) sg += expf(s.yd[k] - lse_g);
+      lse_g += logf(sg);
+      const float hw = 0.5f * (d.dmax - d.dmin), ctr = 0.5f * (d.dmin + d.dmax);
+      float t[8], tm = -3.0e38f, mu[8], sd[8], th[8], raw_sd[8];
+      for (int k = 0; k < G; ++k) {
+        th[k] = tanhf(s.yd[G + k]);
+        mu[k] = th[k] * hw + ctr;
+        raw_sd[k] = expf(P[d.p_logstd + k]);
+        sd[k] = fmaxf(raw_sd[k], 1e-6f);
+        const float df = ps.dist - mu[k];
+        t[k] = -(df * df) / (2.f * sd[k] * sd[k]) - logf(sd[k]) - kLogSqrt2Pi + (s.yd[k] - lse_g);
+        tm = fmaxf(tm, t[k]);
+      }
+      float st = 0.f;
+      for (int k = 0; k < G; ++k) st += expf(t[k] - tm);
+      float wsum = 0.f, w[8];
+      for (int k = 0; k < G; ++k) { w[k] = expf(t[k] - tm) / st * gl; wsum += w[k]; }
+      for (int k = 0; k < G; ++k) {
+        const float df = ps.dist - mu[k];
+        const float dlogit = w[k] - expf(s.yd[k] - lse_g) * wsum;
+        const float dmu = w[k] * df / (sd[k] * sd[k]);
+        const float dsd = w[k] * (df * df / (sd[k] * sd[k] * sd[k]) - 1.f / sd[k]);
+        s_small[16 + k] = dlogit;
+        s_small[16 + G + k] = dmu * hw * (1.f - th[k] * th[k]);
+        s_small[40 + k] = raw_sd[k] >= 1e-6f ? dsd * raw_sd[k] : 0.f;
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < G) acc_logstd[threadIdx.x] += s_small[40 + threadIdx.x];  // thread k owns log-std k
+    for (int q = threadIdx.x; q < 2 * G; q += blockDim.x) o.dyd[(long long)b * 2 * G + q] = s_small[16 + q];
+    for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+      float acc = 0.f;
+      for (int q = 0; q < 2 * G; ++q) acc = fmaf(P[d.dist.W1 + (long long)q * Wd + h], s_small[16 + q], acc);
+      const float dh = s.hd[h] > 0.f ? acc : 0.f;
+      s_dh[h] = dh;
+      o.dhd[(long long)b * Wd + h] = dh;
+      o.hd[(long long)b * Wd + h] = s.hd[h];
+    }
+    for (int k = threadIdx.x; k < d.latE; k += blockDim.x) o.einv[(long long)b * d.latE + k] = s.einv[k];
+    __syncthreads();
+    gemv_n(P + d.dist.W0, s_dh, Wd, d.latE, s_dx);   // s_dx[0..latE) = d einv
+    // ---- orientation: cotangent of the normalised coefficients a~_lm
+    {
+      float2 da[kM];
+      MGB_UNROLL
+      for (int q = 0; q < kM; ++q) da[q] = make_float2(0.f, 0.f);
+      float2 a_loc[kM];
+      MGB_UNROLL
+      for (int q = 0; q < kM; ++q) a_loc[q] = s.alm[q];
+      if (d.has_beta) {
+        // -g * dlogZ/da~ : softmax-weighted over the Lebedev grid
+        for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
+          const float2* y = reinterpret_cast<const float2*>(d.leb_y) + (long long)g * kM;
+          const float2 sg = sph_sum(a_loc, y);
+          const float wgt = expf(-d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g] - ps.lse_max) / ps.lse_sum;
+          const float cf = -gl * wgt * (-2.f * d.beta);
+          const float2 z = make_float2(cf * sg.x, cf * sg.y);
+          MGB_UNROLL
+          for (int q = 0; q < kM; ++q) cfmacl(da[q], y[q], z);   // conj(Y) * z
+        }
+      }
+      // block-reduce the 50 numbers
+      for (int q = 0; q < kM; ++q) {
+        const float rx = block_sum(da[q].x, s.red), ry = block_sum(da[q].y, s.red);
+        if (threadIdx.x == 0) s_da[q] = make_float2(rx, ry);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float ox = actions[(long long)b * 6 + 3], oy = actions[(long long)b * 6 + 4], oz = actions[(long long)b * 6 + 5];
+        const float nr = sqrtf(ox * ox + oy * oy + oz * oz);
+        if (nr > 0.f) { ox /= nr; oy /= nr; oz /= nr; } else { ox = oy = oz = 0.f; }
+        float2 y[kM];
+        sph_harm_l4(ox, oy, oz, false, false, y);
+        float cf;
+        if (d.has_beta) {
+          cf = gl * (-2.f * d.beta);
+        } else {
+          const float so2 = ps.s_o.x * ps.s_o.x + ps.s_o.y * ps.s_o.y;
+          cf = (ps.n == 0 || so2 < 1e-10f) ? 0.f : gl * 2.f / so2;
+        }
+        const float2 z = make_float2(cf * ps.s_o.x, cf * ps.s_o.y);
+        // through a~ = a / sqrt(max(k, 1e-10))
+        float dot = 0.f;
+        for (int q = 0; q < kM; ++q) {
+          cfmacl(s_da[q], y[q], z);
+          dot += s_da[q].x * a_loc[q].x + s_da[q].y * a_loc[q].y;   // sum d a~ . a~
+        }
+        // a_raw = a~ / inv_sqrt_k ; dk = -0.5 k^-3/2 sum(da~ . a_raw) = -0.5 inv^2 * dot(da~, a~)
+        const float dk = ps.k_raw >= 1e-10f ? -0.5f * ps.inv_sqrt_k * ps.inv_sqrt_k * dot : 0.f;
+        for (int q = 0; q < kM; ++q) {
+          const float2 araw = make_float2(a_loc[q].x / ps.inv_sqrt_k, a_loc[q].y / ps.inv_sqrt_k);
+          s_da[q] = make_float2(s_da[q].x * ps.inv_sqrt_k + 2.f * araw.x * dk, s_da[q].y * ps.inv_sqrt_k + 2.f * araw.y * dk);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- mixer backward: cond[lm][c'] = sum_k W_l[c'][k] cat_l[m][k], d cond[lm][c'] = s_da[lm] for every c'
+    for (int l = 0; l < kNL; ++l) {
+      const int Kc = d.catM[l];
+      const float2* Wl = reinterpret_cast<const float2*>(P + d.p_mixW) + d.offWM[l];
+      for (int k = threadIdx.x; k < Kc; k += blockDim.x) {
+        float2 wsum = make_float2(0.f, 0.f);
+        for (int c = 0; c < CPE; ++c) { wsum.x += Wl[c * Kc + k].x; wsum.y += Wl[c * Kc + k].y; }
+        float2 dw = make_float2(0.f, 0.f);
+        for (int m = 0; m < 2 * l + 1; ++m) {
+          const float2 g = s_da[l * l + m];
+          const float2 x = s.cat[d.offM[l] + m * Kc + k];
+          float2 dc = make_float2(0.f, 0.f);
+          cfmacl(dc, wsum, g);            // conj(sum_c' W) * g
+          s_dcat[d.offM[l] + m * Kc + k] = dc;
+          cfmacl(dw, x, g);               // conj(cat) * g
+        }
+        for (int c = 0; c < CPE; ++c) { s_dWM[d.offWM[l] + c * Kc + k].x += dw.x; s_dWM[d.offWM[l] + c * Kc + k].y += dw.y; }
+      }
+    }
+    // ag = dist * ecov (recomputed)
+    for (int idx = threadIdx.x; idx < kM * CPE; idx += blockDim.x)
+      s_ag[idx] = make_float2(ps.dist * s.ecov[idx].x, ps.dist * s.ecov[idx].y);
+    __syncthreads();
+    // d ecov = d in + dist * (d ag_block + square-backward) + invariants backward
+    for (int idx = threadIdx.x; idx < kM * CPE; idx += blockDim.x) {
+      const int x = idx / CPE, c = idx % CPE, l = ell_of_lm(x);
+      const int base = d.offM[l] + (x - l * l) * d.catM[l];
+      float2 dag = s_dcat[base + c];
+      const CgTable& t = d.mix_sq;
+      for (int y = 0; y < kM; ++y) {
+        float2 g = make_float2(0.f, 0.f);
+        for (int q = t.pair_start[x * kM + y]; q < t.pair_start[x * kM + y + 1]; ++q) {
+          const int oo = t.pair_out[q], lo = t.out_l[oo];
+          const float2 dc = s_dcat[d.offM[lo] + t.out_m[oo] * d.catM[lo] + (1 + t.out_block[oo]) * CPE + c];
+          g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
+        }
+        for (int q = t.pair_start[y * kM + x]; q < t.pair_start[y * kM + x + 1]; ++q) {
+          const int oo = t.pair_out[q], lo = t.out_l[oo];
+          const float2 dc = s_dcat[d.offM[lo] + t.out_m[oo] * d.catM[lo] + (1 + t.out_block[oo]) * CPE + c];
+          g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
+        }
+        cfmacl(dag, s_ag[y * CPE + c], g);   // conj(ag_y) * g
+      }
+      float2 de = s_dcat[base + d.inM_block[l] * CPE + c];
+      de.x += ps.dist * dag.x; de.y += ps.dist * dag.y;
+      const float2 gs = scalars_bwd_elem(s.ecov, CPE, CPE, s_dx, x, c);
+      de.x += gs.x; de.y += gs.y;
+      if (ps.focus_valid) {
+        float2* dst = reinterpret_cast<float2*>(o.dA_last) + (((long long)b * N + ps.focus) * kM + x) * d.Cout + ps.element * CPE + c;
+        dst->x += de.x; dst->y += de.y;
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < d.totWM; idx += blockDim.x) {
+    const float2 v = s_dWM[idx];
+    if (v.x != 0.f) atomicAdd(grad + d.p_mixW + 2ll * idx, v.x);
+    if (v.y != 0.f) atomicAdd(grad + d.p_mixW + 2ll * idx + 1, v.y);
+  }
+  if ((int)threadIdx.x < G && acc_logstd[threadIdx.x] != 0.f) atomicAdd(grad + d.p_logstd + threadIdx.x, acc_logstd[threadIdx.x]);
+}
+__host__ __device__ inline int policy_bwd_extra_floats(const CovDesc& d) {
+  return d.Wd + (d.lat > d.Wd ? d.lat : d.Wd) + 2 * d.totM + 2 * d.totWM + 2 * kM * d.CPE * 2 + 2 * kM + 64 + 16;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Atom level backward for atom i (see k_atom_fwd).  Inputs: dOut = d A_{k+1}[b,i].  Produces
+//   dE_k[b,i,j,:,:] for all j (assigned, or added when the next level's edge network already wrote its share),
+//   dA_k[b,j] += ... for all j (global atomics; dA_k zero-initialised), including the own-atom terms.
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L) {
+  const int nlm2 = L.nlm_in;
+  const int stage = kJChunk * (kM + kNL * L.C + nlm2 * L.C + kM * L.C + kNL * L.C) * 2;
+  return L.totA * 2 + kM * L.Cout * 2 + stage + nlm2 * L.C * 2;
+}
+
+// dcat[l][m][k] = sum_c' conj(W_l[c'][k]) dOut[lm][c']   (warp units, lanes over k)
+__device__ __forceinline__ void mix_rows_bwd(const MixUnit* __restrict__ units, int n_units, const int* catA, const int* offA,
+                                             const int* offW, int Cout, const float2* __restrict__ W,
+                                             const float2* __restrict__ sdOut, float2* __restrict__ sDcat) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int u = warp; u < n_units; u += nwarps) {
+    const MixUnit un = units[u];
+    const int K = catA[un.l];
+    const float2* Wl = W + offW[un.l];
+    const int lm0 = un.l * un.l + un.m0;
+    for (int k = lane; k < K; k += 32) {
+      float2 acc[3];
+      acc[0] = acc[1] = acc[2] = make_float2(0.f, 0.f);
+      for (int c = 0; c < Cout; ++c) {
+        const float2 w = Wl[c * K + k];
+        MGB_UNROLL
+        for (int q = 0; q < 3; ++q)
+          if (q < un.nm) cfmacl(acc[q], w, sdOut[(lm0 + q) * Cout + c]);
+      }
+      for (int q = 0; q < un.nm; ++q) sDcat[offA[un.l] + (un.m0 + q) * K + k] = acc[q];
+    }
+  }
+}
+
+template <int NLM2>
+__global__ void __launch_bounds__(kAtomThreads)
+k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ P, const float* __restrict__ pos,
+           const int* __restrict__ n_atoms, const float* __restrict__ A_in, const float* __restrict__ E,
+           const float* __restrict__ dA_out, float* __restrict__ dA_in, float* __restrict__ dE, int accumulate_dE) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, Cout = L.Cout;
+  const int b = blockIdx.x / N, i = blockIdx.x % N;
+  const int n = n_atoms[b];
+  if (i >= n) return;
+  MGB_DYN_SMEM(float2, smem);
+  float2* sDcat = smem;                         // [totA]
+  float2* sdOut = sDcat + L.totA;               // [25][Cout]
+  float2* sY = sdOut + kM * Cout;               // [JC][25]
+  float2* sE = sY + kJChunk * kM;               // [JC][5][C]
+  float2* sAj = sE + kJChunk * kNL * C;         // [JC][NLM2][C]
+  float2* sU = sAj + kJChunk * NLM2 * C;        // [JC][25][C]   E * Y
+  float2* sdE = sU + kJChunk * kM * C;          // [JC][5][C]
+  float2* sAi = sdE + kJChunk * kNL * C;        // [NLM2][C]
+  const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
+  const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
+  float2* dE_i = reinterpret_cast<float2*>(dE) + ((long long)b * N + i) * N * kNL * C;
+  float2* dAb = reinterpret_cast<float2*>(dA_in) + (long long)b * N * NLM2 * C;
+  const float* pos_b = pos + (long long)b * N * 3;
+  for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
+  {
+    const float2* src = reinterpret_cast<const float2*>(dA_out) + ((long long)b * N + i) * kM * Cout;
+    for (int idx = threadIdx.x; idx < kM * Cout; idx += blockDim.x) sdOut[idx] = src[idx];
+  }
+  __syncthreads();
+  mix_rows_bwd(d.units_hidden, d.n_units_hidden, L.catA, L.offA, L.offWA, Cout, reinterpret_cast<const float2*>(P + L.p_atomW),
+               sdOut, sDcat);
+  __syncthreads();
+
+  const bool owner = (int)threadIdx.x < kM * C;
+  const int x = owner ? threadIdx.x / C : 0, c = owner ? threadIdx.x % C : 0;
+  const int l1 = ell_of_lm(x);
+  const bool col_owner = owner && x < NLM2;
+  float2 dTrow[NLM2];   // dT[x][y], y < NLM2
+  float2 dTcol[kM];     // dT[y][x], y < 25   (col owners only)
+  if (owner) {
+    const CgTable& t = L.ag;
+    MGB_UNROLL
+    for (int y = 0; y < NLM2; ++y) {
+      float2 g = make_float2(0.f, 0.f);
+      for (int q = t.pair_start[x * NLM2 + y]; q < t.pair_start[x * NLM2 + y + 1]; ++q) {
+        const int oo = t.pair_out[q], lo = t.out_l[oo];
+        const float2 dc = sDcat[L.offA[lo] + t.out_m[oo] * L.catA[lo] + t.out_block[oo] * C + c];
+        g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
+      }
+      dTrow[y] = g;
+    }
+    MGB_UNROLL
+    for (int y = 0; y < kM; ++y) {
+      float2 g = make_float2(0.f, 0.f);
+      if (col_owner) {
+        for (int q = t.pair_start[y * NLM2 + x]; q < t.pair_start[y * NLM2 + x + 1]; ++q) {
+          const int oo = t.pair_out[q], lo = t.out_l[oo];
+          const float2 dc = sDcat[L.offA[lo] + t.out_m[oo] * L.catA[lo] + t.out_block[oo] * C + c];
+          g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
+        }
+      }
+      dTcol[y] = g;
+    }
+    // own-atom terms: pass-through block and CG square
+    if (col_owner) {
+      const int base = L.offA[l1] + (x - l1 * l1) * L.catA[l1];
+      float2 dai = sDcat[base + L.in_block[l1] * C + c];
+      const CgTable& ts = L.sq;
+      for (int y = 0; y < NLM2; ++y) {
+        float2 g = make_float2(0.f, 0.f);
+        for (int q = ts.pair_start[x * NLM2 + y]; q < ts.pair_start[x * NLM2 + y + 1]; ++q) {
+          const int oo = ts.pair_out[q], lo = ts.out_l[oo];
+          const float2 dc = sDcat[L.offA[lo] + ts.out_m[oo] * L.catA[lo] + (L.sq_block[lo] + ts.out_block[oo]) * C + c];
+          g.x = fmaf(ts.pair_coef[q], dc.x, g.x); g.y = fmaf(ts.pair_coef[q], dc.y, g.y);
+        }
+        for (int q = ts.pair_start[y * NLM2 + x]; q < ts.pair_start[y * NLM2 + x + 1]; ++q) {
+          const int oo = ts.pair_out[q], lo = ts.out_l[oo];
+          const float2 dc = sDcat[L.offA[lo] + ts.out_m[oo] * L.catA[lo] + (L.sq_block[lo] + ts.out_block[oo]) * C + c];
+          g.x = fmaf(ts.pair_coef[q], dc.x, g.x); g.y = fmaf(ts.pair_coef[q], dc.y, g.y);
+        }
+        cfmacl(dai, sAi[y * C + c], g);
+      }
+      atomic_add2(dAb + (long long)i * NLM2 * C + x * C + c, dai);
+    }
+  }
+  // neighbour loop
+  for (int j0 = 0; j0 < n; j0 += kJChunk) {
+    const int nj = min(kJChunk, n - j0);
+    __syncthreads();
+    stage_neighbours<NLM2>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
+    for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) sdE[idx] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nj * kM * C; idx += blockDim.x) {
+      const int jj = idx / (kM * C), r = idx % (kM * C), lm = r / C, cc = r % C;
+      sU[idx] = cmul(sE[(jj * kNL + ell_of_lm(lm)) * C + cc], sY[jj * kM + lm]);
+    }
+    __syncthreads();
+    if (owner) {
+      for (int jj = 0; jj < nj; ++jj) {
+        // row part: dE_ij[l1, c] += conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
+        float2 w = make_float2(0.f, 0.f);
+        const float2* a = sAj + jj * NLM2 * C + c;
+        MGB_UNROLL
+        for (int y = 0; y < NLM2; ++y) cfmacl(w, a[y * C], dTrow[y]);
+        float2 de = make_float2(0.f, 0.f);
+        cfmacl(de, sY[jj * kM + x], w);
+        smem_add2(sdE + (jj * kNL + l1) * C + c, de);
+        // column part: dA_j[x, c] += sum_y conj(E_ij[l(y), c] Y[y]) dT[y][x]
+        if (col_owner) {
+          float2 v = make_float2(0.f, 0.f);
+          const float2* u = sU + jj * kM * C + c;
+          MGB_UNROLL
+          for (int y = 0; y < kM; ++y) cfmacl(v, u[y * C], dTcol[y]);
+          atomic_add2(dAb + (long long)(j0 + jj) * NLM2 * C + x * C + c, v);
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) {
+      float2 v = sdE[idx];
+      float2* dst = dE_i + (long long)j0 * kNL * C + idx;
+      if (accumulate_dE) { v.x += dst->x; v.y += dst->y; }
+      *dst = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Atom-mix weight gradient: dW_l[c'][k] += sum_{atoms, m} conj(cat[a][l][m][k]) dOut[a][lm][c'].
+// grid = (atom chunks, 5 ells); lanes over k straight out of HBM (the forward saved cat), register tile over c'.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMixDwThreads = 128;
+constexpr int kMixDwSlots = 3;   // catA_l <= 3 * 128
+constexpr int kMixDwCO = 10;
+
+__global__ void __launch_bounds__(kMixDwThreads)
+k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ n_atoms, const float* __restrict__ cat,
+         const float* __restrict__ dA_out, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, Cout = L.Cout, l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1;
+  const long long rows = (long long)B * N;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x, r1 = (r0 + per < rows) ? r0 + per : rows;
+  MGB_DYN_SMEM(float2, sd);   // [9][Cout]
+  for (int c0 = 0; c0 < Cout; c0 += kMixDwCO) {
+    float2 acc[kMixDwSlots][kMixDwCO];
+    MGB_UNROLL
+    for (int s = 0; s < kMixDwSlots; ++s)
+      MGB_UNROLL
+      for (int c = 0; c < kMixDwCO; ++c) acc[s][c] = make_float2(0.f, 0.f);
+    for (long long r = r0; r < r1; ++r) {
+      const int b = (int)(r / N), i = (int)(r % N);
+      if (i >= n_atoms[b]) continue;
+      __syncthreads();
+      const float2* src = reinterpret_cast<const float2*>(dA_out) + (r * kM + l * l) * Cout;
+      for (int idx = threadIdx.x; idx < nm * Cout; idx += blockDim.x) sd[idx] = src[idx];
+      __syncthreads();
+      const float2* cr = reinterpret_cast<const float2*>(cat) + r * L.totA + L.offA[l];
+      for (int m = 0; m < nm; ++m) {
+        float2 xv[kMixDwSlots];
+        MGB_UNROLL
+        for (int s = 0; s < kMixDwSlots; ++s) {
+          const int k = threadIdx.x + s * kMixDwThreads;
+          xv[s] = k < K ? cr[m * K + k] : make_float2(0.f, 0.f);
+        }
+        MGB_UNROLL
+        for (int c = 0; c < kMixDwCO; ++c) {
+          if (c0 + c < Cout) {
+            const float2 g = sd[m * Cout + c0 + c];
+            MGB_UNROLL
+            for (int s = 0; s < kMixDwSlots; ++s) cfmacl(acc[s][c], xv[s], g);
+          }
+        }
+      }
+    }
+    MGB_UNROLL
+    for (int s = 0; s < kMixDwSlots; ++s) {
+      const int k = threadIdx.x + s * kMixDwThreads;
+      if (k < K) {
+        MGB_UNROLL
+        for (int c = 0; c < kMixDwCO; ++c) {
+          if (c0 + c < Cout) {
+            float* dst = grad + L.p_atomW + 2ll * (L.offWA[l] + (long long)(c0 + c) * K + k);
+            if (acc[s][c].x != 0.f) atomicAdd(dst, acc[s][c].x);
+            if (acc[s][c].y != 0.f) atomicAdd(dst + 1, acc[s][c].y);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Edge level backward.  Persistent CTAs over (b, i) rows; each round handles one pair per warp.  Weight cotangents
+// (edge mix, radial linears, scales/phases) are accumulated in registers and flushed once per CTA.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kEdgeBwdThreads = 192;
+constexpr int kEdgeBwdWarps = kEdgeBwdThreads / 32;
+constexpr int kEdgeSlots = 2;        // sum_l catE[l] <= 2 * 192
+constexpr int kEdgeMaxC = 10;
+constexpr int kRadSlots = (kNL * 2 * kEdgeMaxC * kRadFeat + kEdgeBwdThreads - 1) / kEdgeBwdThreads;   // 17
+
+template <int NLIN>
+__global__ void __launch_bounds__(kEdgeBwdThreads)
+k_edge_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
+           const float* __restrict__ pos, const int* __restrict__ n_atoms, const float* __restrict__ A_in,
+           const float* __restrict__ E_prev, const float* __restrict__ dE, float* __restrict__ dE_prev,
+           float* __restrict__ dD, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, C2 = 2 * C;
+  constexpr int NLM = NLIN * NLIN;
+  MGB_DYN_SMEM(float2, smem);
+  float2* sAi = smem;                                                  // [NLM][C]
+  const int per_warp = L.sumCatE + 16 + kNL * C;                       // catbuf + f + dpre
+  float2* wbase = sAi + NLM * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* catbuf = wbase + warp * per_warp;
+  float* f = reinterpret_cast<float*>(catbuf + L.sumCatE);
+  float2* dpre = catbuf + L.sumCatE + 16;
+  __shared__ int s_j[kEdgeBwdWarps];
+
+  // slot ownership for the edge-mix weights: slot -> (l, k)
+  int sl_l[kEdgeSlots], sl_k[kEdgeSlots], sl_off[kEdgeSlots];
+  float2 we[kEdgeSlots][kEdgeMaxC], dwe[kEdgeSlots][kEdgeMaxC];
+  MGB_UNROLL
+  for (int s = 0; s < kEdgeSlots; ++s) {
+    int e = threadIdx.x + s * kEdgeBwdThreads;
+    sl_l[s] = -1; sl_k[s] = 0; sl_off[s] = 0;
+    int off = 0;
+    for (int l = 0; l < kNL; ++l) {
+      if (sl_l[s] < 0 && e < L.catE[l]) { sl_l[s] = l; sl_k[s] = e; sl_off[s] = off; }
+      if (sl_l[s] < 0) e -= L.catE[l];
+      off += L.catE[l];
+    }
+    MGB_UNROLL
+    for (int c = 0; c < kEdgeMaxC; ++c) {
+      dwe[s][c] = make_float2(0.f, 0.f);
+      we[s][c] = (sl_l[s] >= 0 && c < C)
+                     ? reinterpret_cast<const float2*>(P + L.p_edgeW)[L.offE[sl_l[s]] + c * L.catE[sl_l[s]] + sl_k[s]]
+                     : make_float2(0.f, 0.f);
+    }
+  }
+  float drw[kRadSlots];
+  MGB_UNROLL
+  for (int s = 0; s < kRadSlots; ++s) drw[s] = 0.f;
+  float drb = 0.f;             // thread e < 5*2C owns radial bias e
+  float dsc = 0.f, dph = 0.f;  // lane t accumulates its share of scale/phase cotangents
+  const int n_rad = kNL * C2 * kRadFeat;
+  const float* Wt_rad = Wt + d.wt_edge[level] + 2ll * L.totE;
+
+  for (int item = blockIdx.x; item < B * N; item += gridDim.x) {
+    const int b = item / N, i = item % N;
+    const int n = n_atoms[b];
+    if (i >= n) continue;
+    const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM * C;
+    const float* pos_b = pos + (long long)b * N * 3;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NLM * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM * C + idx];
+    __syncthreads();
+    for (int jg = 0; jg < n; jg += kEdgeBwdWarps) {
+      const int j = jg + warp;
+      const bool act = j < n;
+      PairGeom g = PairGeom();
+      if (act) {
+        g = pair_geom(pos_b, i, j, d.cut_rad, d.cut_width);
+        const long long pair = ((long long)b * N + i) * N + j;
+        const float2* Eprev_ij = L.has_prev ? reinterpret_cast<const float2*>(E_prev) + pair * kNL * C : nullptr;
+        edge_build_cat<NLIN>(L, P, Wt_rad, g, sAi, Ab + (long long)j * NLM * C, Eprev_ij, catbuf, f, lane);
+        const float2* dE_ij = reinterpret_cast<const float2*>(dE) + pair * kNL * C;
+        for (int idx = lane; idx < kNL * C; idx += 32) dpre[idx] = make_float2(dE_ij[idx].x * g.s, dE_ij[idx].y * g.s);
+      }
+      if (lane == 0) s_j[warp] = act ? j : -1;
+      __syncthreads();
+      // phase 2: all threads, slot ownership; in place catbuf -> dcat
+      MGB_UNROLL
+      for (int s = 0; s < kEdgeSlots; ++s) {
+        if (sl_l[s] < 0) continue;
+        for (int w = 0; w < kEdgeBwdWarps; ++w) {
+          if (s_j[w] < 0) continue;
+          float2* cb = wbase + w * per_warp;
+          const float2* dp_w = cb + L.sumCatE + 16 + sl_l[s] * C;
+          const float2 xk = cb[sl_off[s] + sl_k[s]];
+          float2 dc = make_float2(0.f, 0.f);
+          MGB_UNROLL
+          for (int c = 0; c < kEdgeMaxC; ++c) {
+            if (c < C) {
+              const float2 gq = dp_w[c];
+              cfmacl(dwe[s][c], xk, gq);
+              cfmacl(dc, we[s][c], gq);
+            }
+          }
+          cb[sl_off[s] + sl_k[s]] = dc;
+        }
+      }
+      __syncthreads();
+      // phase 3a: all threads: radial weight / bias cotangents from dR (radial part of dcat) and f
+      for (int w = 0; w < kEdgeBwdWarps; ++w) {
+        if (s_j[w] < 0) continue;
+        const float2* cb = wbase + w * per_warp;
+        const float* fw = reinterpret_cast<const float*>(cb + L.sumCatE);
+        MGB_UNROLL
+        for (int s = 0; s < kRadSlots; ++s) {
+          const int e = threadIdx.x + s * kEdgeBwdThreads;
+          if (e < n_rad) {
+            const int l = e / (C2 * kRadFeat), r = e % (C2 * kRadFeat), oo = r / kRadFeat, t = r % kRadFeat;
+            int off = 0;
+            for (int q = 0; q < l; ++q) off += L.catE[q];
+            const float dR = reinterpret_cast<const float*>(cb + off + L.catE[l] - C)[oo];
+            drw[s] = fmaf(dR, fw[t], drw[s]);
+          }
+        }
+        if ((int)threadIdx.x < kNL * C2) {
+          const int l = threadIdx.x / C2, oo = threadIdx.x % C2;
+          int off = 0;
+          for (int q = 0; q < l; ++q) off += L.catE[q];
+          drb += reinterpret_cast<const float*>(cb + off + L.catE[l] - C)[oo];
+        }
+      }
+      // phase 3b: per warp: previous-edge and dot cotangents out, scale/phase cotangents
+      if (act) {
+        const long long pair = ((long long)b * N + i) * N + j;
+        int off_l[kNL];
+        {
+          int o = 0;
+          for (int l = 0; l < kNL; ++l) { off_l[l] = o; o += L.catE[l]; }
+        }
+        if (L.has_prev) {
+          float2* dst = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C;
+          for (int idx = lane; idx < kNL * C; idx += 32) dst[idx] = catbuf[off_l[idx / C] + idx % C];
+        }
+        {
+          float2* dst = reinterpret_cast<float2*>(dD) + pair * kNL * C;
+          const int kdot = L.has_prev ? C : 0;
+          for (int idx = lane; idx < NLIN * C; idx += 32) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int l = 0; l < NLIN; ++l) { acc.x += catbuf[off_l[l] + kdot + idx].x; acc.y += catbuf[off_l[l] + kdot + idx].y; }
+            dst[idx] = acc;
+          }
+        }
+        // df[t] = sum_{l,o} W_l[o][t] dR_l[o]   (lane = t)
+        float df = 0.f;
+        for (int l = 0; l < kNL; ++l) {
+          const float* dR = reinterpret_cast<const float*>(catbuf + off_l[l] + L.catE[l] - C);
+          const float* w = Wt_rad + ((long long)l * kRadFeat + lane) * C2;
+          for (int oo = 0; oo < C2; ++oo) df = fmaf(w[oo], dR[oo], df);
+        }
+        float dval;
+        rad_feature(lane, g, P + L.p_scales, P + L.p_phases, &dval);
+        dph = fmaf(df, dval, dph);
+        dsc = fmaf(df, dval * kTwoPi * g.r, dsc);
+      }
+      __syncthreads();
+    }
+  }
+  // flush
+  MGB_UNROLL
+  for (int s = 0; s < kEdgeSlots; ++s) {
+    if (sl_l[s] < 0) continue;
+    MGB_UNROLL
+    for (int c = 0; c < kEdgeMaxC; ++c) {
+      if (c < C) {
+        float* dst = grad + L.p_edgeW + 2ll * (L.offE[sl_l[s]] + c * L.catE[sl_l[s]] + sl_k[s]);
+        if (dwe[s][c].x != 0.f) atomicAdd(dst, dwe[s][c].x);
+        if (dwe[s][c].y != 0.f) atomicAdd(dst + 1, dwe[s][c].y);
+      }
+    }
+  }
+  MGB_UNROLL
+  for (int s = 0; s < kRadSlots; ++s) {
+    const int e = threadIdx.x + s * kEdgeBwdThreads;
+    if (e < n_rad && drw[s] != 0.f) atomicAdd(grad + L.p_radW + e, drw[s]);
+  }
+  if ((int)threadIdx.x < kNL * C2 && drb != 0.f) atomicAdd(grad + L.p_radb + threadIdx.x, drb);
+  {
+    // lanes t = trig*4 + p share a (scale, phase): reduce over p inside the warp
+    dsc += __shfl_xor_sync(0xffffffffu, dsc, 1); dsc += __shfl_xor_sync(0xffffffffu, dsc, 2);
+    dph += __shfl_xor_sync(0xffffffffu, dph, 1); dph += __shfl_xor_sync(0xffffffffu, dph, 2);
+    if ((lane & 3) == 0) {
+      if (dsc != 0.f) atomicAdd(grad + L.p_scales + (lane >> 2), dsc);
+      if (dph != 0.f) atomicAdd(grad + L.p_phases + (lane >> 2), dph);
+    }
+  }
+}
+
+// dA_k[b,i,l',m,c] += sum_j (dD_ij + dD_ji)[l',c] (-1)^m conj(A_j[l',-m,c])
+template <int NLIN>
+__global__ void k_dot_bwd(const CovDesc* __restrict__ dp, int level, const int* __restrict__ n_atoms, const float* __restrict__ A_in,
+                          const float* __restrict__ dD, float* __restrict__ dA_in) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C;
+  constexpr int NLM = NLIN * NLIN;
+  const int b = blockIdx.x / N, i = blockIdx.x % N;
+  const int n = n_atoms[b];
+  if (i >= n) return;
+  const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM * C;
+  const float2* dDb = reinterpret_cast<const float2*>(dD) + (long long)b * N * N * kNL * C;
+  float2* dst = reinterpret_cast<float2*>(dA_in) + ((long long)b * N + i) * NLM * C;
+  for (int idx = threadIdx.x; idx < NLM * C; idx += blockDim.x) {
+    const int lm = idx / C, c = idx % C, l = ell_of_lm(lm), m = lm - l * l - l;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+      const float2 g1 = dDb[((long long)i * N + j) * kNL * C + l * C + c], g2 = dDb[((long long)j * N + i) * kNL * C + l * C + c];
+      const float2 g = make_float2(g1.x + g2.x, g1.y + g2.y);
+      cfmacl(acc, Ab[(long long)j * NLM * C + lm_index(l, -m) * C + c], g);
+    }
+    const float sg = (m & 1) ? -1.f : 1.f;
+    dst[idx].x += sg * acc.x;
+    dst[idx].y += sg * acc.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PPO-clip loss (molgym/ppo.py:28-52) and its cotangents, float64 like the reference (adv / ret are float64).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_ppo_loss(int B, const float* __restrict__ logp, const float* __restrict__ ent, const float* __restrict__ v,
+                           const float* __restrict__ old_logp, const double* __restrict__ adv, const double* __restrict__ ret,
+                           double clip, double vf_coef, double ent_coef, double invB, double* __restrict__ info,
+                           float* __restrict__ g_logp, float* __restrict__ g_ent, float* __restrict__ g_v) {
+  __shared__ double red[6][32];
+  double acc[6] = {0, 0, 0, 0, 0, 0};   // policy, entropy, vf, kl, clipfrac, unused
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float ratio_f = expf(logp[b] - old_logp[b]);
+    const double ratio = ratio_f, a = adv[b];
+    const double lo = 1.0 - clip, hi = 1.0 + clip;
+    const float ratio_c = fminf(fmaxf(ratio_f, (float)lo), (float)hi);   // clamp happens in float32 (ppo.py:35)
+    const double o1 = ratio * a, o2 = (double)ratio_c * a;
+    const bool in_range = ratio_f >= (float)lo && ratio_f <= (float)hi;
+    acc[0] -= (o1 < o2 ? o1 : o2);
+    acc[1] -= ent_coef * (double)ent[b];
+    const double dv = (double)v[b] - ret[b];
+    acc[2] += vf_coef * dv * dv;
+    acc[3] += (double)(old_logp[b] - logp[b]);
+    acc[4] += (ratio_f < (float)lo || ratio_f > (float)hi) ? 1.0 : 0.0;
+    if (g_logp) {
+      double dr;
+      if (o1 < o2) dr = a;
+      else if (o1 == o2) dr = 0.5 * a + (in_range ? 0.5 * a : 0.0);
+      else dr = in_range ? a : 0.0;
+      g_logp[b] = (float)(-invB * dr * ratio);
+      g_ent[b] = (float)(-ent_coef * invB);
+      g_v[b] = (float)(vf_coef * 2.0 * dv * invB);
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int q = 0; q < 5; ++q) {
+    double x = acc[q];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[q][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[5] = {0, 0, 0, 0, 0};
+    for (int q = 0; q < 5; ++q)
+      for (int k = 0; k < nw; ++k) tot[q] += red[q][k];
+    info[1] = tot[0] * invB; info[2] = tot[1] * invB; info[3] = tot[2] * invB;
+    info[0] = info[1] + info[2] + info[3];
+    info[4] = tot[3] * invB; info[5] = tot[4] * invB; info[6] = 0; info[7] = 0;
+  }
+}
+
+}  // namespace mgb
