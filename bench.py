@@ -1,0 +1,372 @@
+"""bench.py — PPO-minibatch forward+backward throughput of the covariant agent (canvases / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one minibatch of synthetic canvases: forward (Cormorant body + heads) ->
+PPO-clip loss -> backward -> (N > 1) gradient all-reduce.  Weak scaling: every rank processes its own minibatch of the
+workload's size; `value` = canvases processed by all ranks / max-over-ranks device time.
+
+  value : inputs resident in HBM, direct C-ABI calls (mgb_cov_forward, mgb_ppo_loss, mgb_cov_backward), CUDA events.
+  e2e   : the reference-facing call — CovariantAC.step(list of observation tuples, actions) driven by the restated
+          ppo.compute_loss, loss.backward(), and a device->host read of the loss info — host packing and H2D copies inside.
+  roofline / cpu_baseline : see DESIGN.md.
+"""
+import argparse
+import ctypes
+import dataclasses
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CLIP, VF, ENT = 0.2, 0.5, 0.01   # arg_parser.py:84-86
+METRIC = 'ppo_minibatch_fwd_bwd_canvases_per_sec'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--workload', default='C2')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=None, help='override the minibatch size (per rank)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-kernel', default='k_atom_bwd')
+    return ap.parse_args()
+
+
+def workload(name, batch=None):
+    from molgym_b200 import synth
+    cfg = synth.CONFIGS[name]
+    if batch:
+        cfg = dataclasses.replace(cfg, mini_batch_size=batch)
+    return cfg
+
+
+def config_json(cfg, world):
+    return {'workload': f'{cfg.name}: canvas_size={cfg.canvas_size} zs={cfg.zs} mini_batch_size={cfg.mini_batch_size} per rank, '
+                        f'occupancies 0..K-1 uniform (synthetic PPO buffer)',
+            'global_batch': cfg.mini_batch_size * world, 'canvas_size': cfg.canvas_size,
+            'hyper': {'network_width': cfg.network_width, 'maxl': cfg.maxl, 'num_cg_levels': cfg.num_cg_levels,
+                      'num_channels_hidden': cfg.num_channels_hidden, 'num_channels_per_element': cfg.num_channels_per_element,
+                      'num_gaussians': cfg.num_gaussians, 'beta': cfg.beta},
+            'parallelism': f'dp{world}', 'l2': 'flushed between timed steps (256 MiB write)'}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (CPU restatement of the reference) driven by the restated ppo loss, all host threads
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step_fn(cfg, sample):
+    import torch
+    from molgym_b200 import synth
+    from oracle.molgym_oracle import CovariantOracle, ppo_loss
+    torch.manual_seed(0)
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=sample)
+    act = synth.make_actions(cfg, obs, n)
+    with torch.no_grad():
+        logp0 = oracle.step(obs, act)['logp'].numpy()
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0)
+    chunk = 128   # the reference-style formulation materialises B*N^2*(2.5k floats): chunk + accumulate (ppo.py:122-131)
+
+    def step():
+        oracle.zero_grad()
+        for lo in range(0, sample, chunk):
+            hi = min(sample, lo + chunk)
+            out = oracle.step(obs[lo:hi], act[lo:hi])
+            loss, _ = ppo_loss(out['logp'], out['ent'], out['v'], old_logp[lo:hi], adv[lo:hi], ret[lo:hi], CLIP, VF, ENT)
+            (loss * ((hi - lo) / sample)).backward()
+    return step
+
+
+def run_cpu(cfg, steps, warmup, budget_s=25.0):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = min(cfg.mini_batch_size, 140)
+    step = cpu_step_fn(cfg, sample)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    warmup = max(0, min(warmup, int(budget_s / 4 / max(first, 1e-3))))
+    for _ in range(warmup):
+        step()
+    steps = max(1, min(steps, int(budget_s / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=sample / dt, ms_per_step=dt * 1e3, steps=steps, warmup=warmup, cores=cores,
+                sample=f'{sample} canvases of {cfg.name} per step, {steps} steps, oracle fwd+loss+bwd in float32, '
+                       f'torch.set_num_threads({cores})')
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling (pynvml) during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x10: 'sync_boost',
+               0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != 'gpu_idle':
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# algorithmic work model (DESIGN.md "Work model")
+# ----------------------------------------------------------------------------------------------------------------
+def atom_bwd_bytes(cfg, n_atoms):
+    """Algorithmic HBM bytes of ONE launch of the dominant kernel (k_atom_bwd, levels >= 1) over a minibatch:
+    per valid atom i: dA_out[25,Cout] read + per neighbour j: A_j[25,C] read, E_ij[5,C] read, dE_ij[5,C] write,
+    dA_j[25,C] read-modify-write."""
+    C = cfg.num_channels_hidden
+    tot = 0
+    for n in n_atoms:
+        n = int(n)
+        per_pair = 25 * C * 8 + 5 * C * 8 + 5 * C * 8 + 2 * 25 * C * 8
+        tot += n * (25 * C * 8 + n * per_pair)
+    return tot
+
+
+def atom_bwd_flops(cfg, n_atoms):
+    """FLOPs of one k_atom_bwd launch (level with 25 input components): per pair 2 x 625 complex MAC per channel (8 flop
+    each) + per atom the transposed mix (sum_l catA_l (2l+1) Cout complex MAC) + CG scatter (~4 x 1439 x C x 2 x 2)."""
+    C = cfg.num_channels_hidden
+    cat = [C * x for x in (11, 25, 33, 35, 31)]
+    mix = sum(c * (2 * l + 1) for l, c in enumerate(cat)) * C * 8
+    cg = 4 * 1439 * C * 4
+    return sum(int(n) * (int(n) * 2 * 625 * C * 8 + mix + cg) for n in n_atoms)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from molgym_b200 import _cabi, _lib, parallel, ppo, synth
+    from molgym_b200.agents.covariant.agent import CovariantAC
+    from molgym_b200.spaces import ActionSpace, ObservationSpace
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    lib = _lib.load()
+    cfg = workload(args.workload, args.batch)
+    B = cfg.mini_batch_size
+
+    torch.manual_seed(0)
+    agent = CovariantAC(ObservationSpace(cfg.canvas_size, cfg.zs), ActionSpace(cfg.zs), device=dev, **cfg.agent_kwargs())
+    if world > 1:
+        parallel.shard_agent(agent)
+    obs, n_atoms = synth.make_observations(cfg, batch=B, seed=cfg.seed + 17 * rank, start_index=rank)
+    act = synth.make_actions(cfg, obs, n_atoms, seed=cfg.seed + 17 * rank)
+    with torch.no_grad():
+        logp0 = agent.step(obs, act)['logp'].cpu().numpy()
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0, seed=cfg.seed + 17 * rank)
+    data = dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret)
+
+    # ---- device-resident inputs for the `value` measurement
+    parsed = agent.parse_observations(obs)
+    pos, charges, bags = parsed['positions'], parsed['charges'], parsed['bags']
+    act_d = torch.as_tensor(act, dtype=torch.float32, device=dev)
+    old_d = torch.as_tensor(old_logp, device=dev)
+    adv_d = torch.as_tensor(adv, device=dev)
+    ret_d = torch.as_tensor(ret, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    logp, ent, v = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
+    g_logp, g_ent, g_v = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
+    info = torch.zeros(8, dtype=torch.float64, device=dev)
+    grad = torch.zeros_like(agent._flat)
+    ws = torch.empty(lib.mgb_cov_workspace_bytes(agent._plan, B), dtype=torch.uint8, device=dev)
+    outs = _cabi.CovOutputs()
+    outs.logp, outs.ent, outs.v = logp.data_ptr(), ent.data_ptr(), v.data_ptr()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    inv_global = 1.0 / (B * world)
+
+    def device_step():
+        _cabi.check(lib, lib.mgb_cov_forward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(), act_d.data_ptr(),
+                                             agent._flat.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(outs), stream))
+        _cabi.check(lib, lib.mgb_ppo_loss(B, logp.data_ptr(), ent.data_ptr(), v.data_ptr(), old_d.data_ptr(), adv_d.data_ptr(),
+                                          ret_d.data_ptr(), CLIP, VF, ENT, inv_global, info.data_ptr(), g_logp.data_ptr(),
+                                          g_ent.data_ptr(), g_v.data_ptr(), stream))
+        _cabi.check(lib, lib.mgb_cov_backward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(), act_d.data_ptr(),
+                                              agent._flat.data_ptr(), ws.data_ptr(), ws.numel(), g_logp.data_ptr(),
+                                              g_ent.data_ptr(), g_v.data_ptr(), grad.data_ptr(), 0, stream))
+        if world > 1:
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+
+    def e2e_step():
+        agent.zero_grad()
+        loss, info_d = ppo.compute_loss(agent, data, CLIP, VF, ENT)
+        (loss / world).backward()
+        return info_d
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        if sampler:
+            sampler.start()
+        wall0 = time.perf_counter()
+        for s in range(steps):
+            flush_buf.zero_()              # evict L2 between timed steps (outside the event pair)
+            starts[s].record()
+            fn()
+            stops[s].record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, wall, clocks
+
+    # ---- value (device-resident) with the dominant kernel timed live
+    launches0 = lib.mgb_launch_count()
+    lib.mgb_profile_kernel(args.profile_kernel.encode())
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize(dev)
+    tot = ctypes.c_double()
+    cnt = ctypes.c_int64()
+    lib.mgb_profile_read(ctypes.byref(tot), ctypes.byref(cnt))   # drop warm-up timings
+    launches_before = lib.mgb_launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    total_ms, wall, clocks = timed(device_step, args.steps, 0, sampler)
+    launches = lib.mgb_launch_count() - launches_before
+    lib.mgb_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.mgb_profile_kernel(None)
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- e2e through the public API (host observations, packing, H2D, torch loss, D2H of the loss info)
+    e2e_steps = max(10, args.steps // 4)
+    e2e_ms, e2e_wall, _ = timed(e2e_step, e2e_steps, max(3, args.warmup // 4))
+    # the e2e step has host work outside the event pairs' GPU time only if the GPU idles; events bracket the call, so
+    # host time shows up as the gap between start.record() and the first kernel: elapsed_time includes it.
+    e2e_value = B * world / (e2e_ms / e2e_steps * 1e-3)
+    h2d = pos.numel() * 4 + charges.numel() * 4 + bags.numel() * 4 + act_d.numel() * 4 + old_d.numel() * 4 + adv_d.numel() * 8 + ret_d.numel() * 8
+    d2h = 6 * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    n_timed = max(int(cnt.value), 1)
+    k_ms = tot.value / n_timed
+    launches_per_step_of_kernel = n_timed / args.steps
+    # levels with 25 input components dominate: use their per-launch algorithmic work
+    alg_bytes = atom_bwd_bytes(cfg, n_atoms)
+    alg_flops = atom_bwd_flops(cfg, n_atoms)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'canvases/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': config_json(cfg, world), 'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'canvases/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'kernel': args.profile_kernel, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': achieved / hbm_peak, 'traffic': None,
+                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s',
+                     'kernel_ms_per_launch': k_ms, 'kernel_launches_per_step': launches_per_step_of_kernel,
+                     'kernel_share_of_step': (tot.value / args.steps) / ms_per_step if ms_per_step > 0 else None,
+                     'algorithmic_bytes_per_launch': alg_bytes, 'algorithmic_flops_per_launch': alg_flops,
+                     'fp32_achieved_tflops': alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
+                     'note': 'kernel is FP32-FMA/latency bound at this size (arithmetic intensity >> ridge); see DESIGN.md'},
+        'wall_ms_per_step': wall / args.steps * 1e3,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cpu = run_cpu(cfg, steps=5, warmup=1, budget_s=20.0)
+        line['cpu_baseline'] = {'value': cpu['value'], 'unit': 'canvases/s', 'cores': cpu['cores'], 'kind': 'port', 'sample': cpu['sample']}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path: here the oracle port (the reference's third-party dependencies are
+    not installable and /root/reference does not travel to the GPU box), all host threads, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank != 0:
+        return
+    cfg = workload(args.workload, args.batch)
+    cpu = run_cpu(cfg, steps=args.steps, warmup=args.warmup, budget_s=60.0)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cpu['value'], 'unit': 'canvases/s', 'n_gpus': world, 'steps': cpu['steps'],
+            'warmup': cpu['warmup'], 'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config_json(cfg, world),
+            'cpu_baseline': {'value': cpu['value'], 'unit': 'canvases/s', 'cores': cpu['cores'], 'kind': 'port', 'sample': cpu['sample']},
+            'e2e': {'value': cpu['value'], 'unit': 'canvases/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -33,7 +33,7 @@ typedef enum {
   MGB_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
   MGB_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed */
   MGB_ERR_WORKSPACE = -3, /* workspace too small */
-  MGB_ERR_STATE = -4      /* backward called without a matching forward */
+  MGB_ERR_STATE = -4      /* reserved */
 } mgb_status;
 
 /* Hyper-parameters of the covariant agent — same meaning as the CovariantAC constructor (agent.py:21-35). */
@@ -98,10 +98,18 @@ typedef struct {
 
 /* Forward in evaluate mode.  d_positions[B,N,3] f32, d_charges[B,N] i32 (0 = padding, real atoms first),
  * d_bags[B,Z] f32, d_actions[B,6] f32 = focus, element, distance, ox, oy, oz (agent.py:230,249,271,288).
- * Saves what backward needs inside the workspace. */
+ * Saves what backward needs inside the workspace: the backward (or mgb_cov_policy) call must be handed the same
+ * workspace, untouched, together with the same inputs and parameters. */
 int mgb_cov_forward(mgb_cov_plan* plan, int32_t batch, const float* d_positions, const int32_t* d_charges,
                     const float* d_bags, const float* d_actions, const float* d_params, void* d_workspace,
                     size_t workspace_bytes, const mgb_cov_outputs* out, void* stream);
+
+/* Policy heads only, on the workspace a previous mgb_cov_forward of the same batch filled (the Cormorant body is not
+ * recomputed).  Used by rollout mode (agent.py:229-292), where the element head needs the sampled focus, the distance
+ * head the sampled element and the orientation head the sampled distance: the caller re-evaluates the heads after
+ * each sub-action is drawn.  Same outputs as mgb_cov_forward except `covariats`. */
+int mgb_cov_policy(mgb_cov_plan* plan, int32_t batch, const float* d_bags, const float* d_actions, const float* d_params,
+                   void* d_workspace, size_t workspace_bytes, const mgb_cov_outputs* out, void* stream);
 
 /* Backward of the same call: cotangents d_g_logp/d_g_ent/d_g_v [B] -> d_grad_params (flat, same layout as params).
  * accumulate != 0 adds into d_grad_params, else it is overwritten. */
@@ -118,6 +126,15 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t batch, const float* d_positions
 int mgb_ppo_loss(int32_t batch, const float* d_logp, const float* d_ent, const float* d_v, const float* d_old_logp,
                  const double* d_adv, const double* d_ret, double clip_ratio, double vf_coef, double entropy_coef,
                  double inv_global_batch, double* d_info, float* d_g_logp, float* d_g_ent, float* d_g_v, void* stream);
+
+/* Launch accounting and per-kernel timing, for bench.py (no counterpart in the reference).
+ * mgb_launch_count: kernels launched by this library in this process so far.
+ * mgb_profile_kernel(substr): from now on bracket every launch whose kernel name contains `substr` with CUDA events on
+ *   the launching stream (NULL or "" switches it off).  mgb_profile_read: synchronise those events, return the summed
+ *   duration in milliseconds and the number of launches timed, and reset. */
+int64_t mgb_launch_count(void);
+int mgb_profile_kernel(const char* substr);
+int mgb_profile_read(double* total_ms, int64_t* launches);
 
 /* Host-side observation packer (no device work).  labels[B,N] are indices into zs, xyz[B,N,3] float64 canvas
  * coordinates, as found in ObservationType tuples.  Null-symbol items are dropped and the rest compacted to the

@@ -34,7 +34,8 @@ class CovOutputs(ctypes.Structure):
 
 EXPORTS = ('mgb_last_error', 'mgb_version', 'mgb_is_cuda_build', 'mgb_cov_plan_create', 'mgb_cov_plan_destroy',
            'mgb_cov_param_count', 'mgb_cov_param_layout', 'mgb_cov_cat_sizes', 'mgb_cov_workspace_bytes',
-           'mgb_cov_forward', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations')
+           'mgb_cov_forward', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_launch_count',
+           'mgb_profile_kernel', 'mgb_profile_read')
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
@@ -57,6 +58,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.mgb_cov_forward.restype = ctypes.c_int
     lib.mgb_cov_forward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                     POINTER(CovOutputs), c_void_p]
+    lib.mgb_cov_policy.restype = ctypes.c_int
+    lib.mgb_cov_policy.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(CovOutputs), c_void_p]
     if hasattr(lib, 'mgb_cov_backward'):
         lib.mgb_cov_backward.restype = ctypes.c_int
         lib.mgb_cov_backward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -68,6 +71,12 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     if hasattr(lib, 'mgb_pack_observations'):
         lib.mgb_pack_observations.restype = ctypes.c_int
         lib.mgb_pack_observations.argtypes = [POINTER(CovConfig), c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.mgb_launch_count.restype = c_int64
+    lib.mgb_launch_count.argtypes = []
+    lib.mgb_profile_kernel.restype = ctypes.c_int
+    lib.mgb_profile_kernel.argtypes = [c_char_p]
+    lib.mgb_profile_read.restype = ctypes.c_int
+    lib.mgb_profile_read.argtypes = [POINTER(c_double), POINTER(c_int64)]
     return lib
 
 

@@ -1,0 +1,427 @@
+"""CovariantAC — the reference's covariant actor-critic (molgym/agents/covariant/agent.py:20-334) behind the same
+constructor and `step(observations, actions)` contract, computed by the hand-written sm_100a kernels of
+molgym_b200/csrc through the C ABI in include/molgym_b200.h.
+
+What stays Python: parameter ownership (ordinary nn.Parameters named exactly like the reference's, so state_dicts,
+optimizers, clipping and whole-module pickles interchange), observation packing, autograd glue, and rollout-mode
+sampling.  There is no CPU fallback: without the CUDA library / a CUDA device construction fails.
+"""
+import ctypes
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from molgym_b200 import _cabi, _lib
+from molgym_b200.agents.base import AbstractActorCritic
+from molgym_b200.agents.covariant import sampling
+from molgym_b200.agents.covariant.packing import pack_observations
+
+_LEBEDEV = None
+
+
+def _lebedev_071():
+    """quadpy.u3._lebedev.lebedev_071() (spherical_dists.py:209): 1730 points, weights summing to 1."""
+    global _LEBEDEV
+    if _LEBEDEV is None:
+        from scipy.integrate import lebedev_rule
+        pts, w = lebedev_rule(71)
+        _LEBEDEV = (np.ascontiguousarray(pts.T, dtype=np.float64), np.ascontiguousarray(w / (4 * np.pi), dtype=np.float64))
+    return _LEBEDEV
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _register(root: nn.Module, dotted: str, param: nn.Parameter):
+    parts = dotted.split('.')
+    node = root
+    for part in parts[:-1]:
+        if part not in node._modules:
+            node.add_module(part, _Node())
+        node = node._modules[part]
+    node.register_parameter(parts[-1], param)
+
+
+class _CovEvaluate(torch.autograd.Function):
+    """logp, ent, v = f(parameters; canvases, actions).  Parameter gradients are written by the CUDA backward straight into
+    the agent's flat gradient buffer, of which every `p.grad` is a view; autograd only routes the three cotangents."""
+
+    @staticmethod
+    def forward(ctx, anchor, agent, pos, charges, bags, actions):
+        outs, ws = agent._forward_raw(pos, charges, bags, actions, want_extras=True)
+        ctx.agent = agent
+        ctx.saved = (pos, charges, bags, actions, ws)
+        ctx.mark_non_differentiable(*outs[3:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_logp, g_ent, g_v, *unused):
+        agent = ctx.agent
+        pos, charges, bags, actions, ws = ctx.saved
+        B = pos.shape[0]
+
+        def prep(g):
+            if g is None:
+                return torch.zeros(B, dtype=torch.float32, device=pos.device)
+            return g.to(torch.float32).contiguous()
+
+        agent._backward_raw(pos, charges, bags, actions, ws, prep(g_logp), prep(g_ent), prep(g_v))
+        return (None, ) * 6
+
+
+class CovariantAC(AbstractActorCritic):
+    def __init__(
+        self,
+        observation_space,
+        action_space,
+        min_max_distance: Tuple[float, float],
+        network_width: int,
+        maxl: int,
+        num_cg_levels: int,
+        num_channels_hidden: int,
+        num_channels_per_element: int,
+        num_gaussians: int,
+        bag_scale: int,
+        beta: Optional[float] = None,
+        device=None,
+    ):
+        super().__init__(observation_space, action_space)
+        self.device = _lib.require_cuda_device(device)
+        self.dtype = torch.float
+        self.zs = list(self.observation_space.zs)
+        self.min_distance, self.max_distance = min_max_distance
+        assert self.min_distance < self.max_distance
+        self.beta = beta
+        self.max_sh = maxl
+        self.num_cg_levels = num_cg_levels
+        self.num_channels_hidden = num_channels_hidden
+        self.num_channels_per_element = num_channels_per_element
+        self.num_gaussians = num_gaussians
+        self.num_channels_out = len(self.zs) * num_channels_per_element
+        self.network_width = network_width
+        self.bag_scale = bag_scale
+        self.canvas_size = self.observation_space.canvas_space.size
+        self.data_parallel = False   # set by molgym_b200.parallel.shard_agent
+        self._init_native()
+        self._init_parameters()
+
+    # ------------------------------------------------------------------------------------------------------
+    # native plan + parameter storage
+    # ------------------------------------------------------------------------------------------------------
+    def _config_kwargs(self):
+        return dict(min_max_distance=(self.min_distance, self.max_distance), network_width=self.network_width, maxl=self.max_sh,
+                    num_cg_levels=self.num_cg_levels, num_channels_hidden=self.num_channels_hidden,
+                    num_channels_per_element=self.num_channels_per_element, num_gaussians=self.num_gaussians,
+                    bag_scale=self.bag_scale, beta=self.beta)
+
+    def _init_native(self):
+        lib = _lib.load()
+        self._cfg = _cabi.make_config(self.zs, self.canvas_size, **self._config_kwargs())
+        xyz, w = _lebedev_071()
+        plan = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib, lib.mgb_cov_plan_create(ctypes.byref(self._cfg), xyz.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                     w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(w), ctypes.byref(plan)))
+        self._plan = plan
+        n = lib.mgb_cov_param_count(plan)
+        off = (ctypes.c_int64 * n)()
+        num = (ctypes.c_int64 * n)()
+        tot = ctypes.c_int64()
+        _cabi.check(lib, lib.mgb_cov_param_layout(plan, off, num, ctypes.byref(tot)))
+        cats = (ctypes.c_int32 * (self.num_cg_levels * 10 + 5))()
+        _cabi.check(lib, lib.mgb_cov_cat_sizes(plan, cats))
+        self._p_offsets, self._p_numels, self._p_total = list(off), list(num), tot.value
+        self._p_names = _cabi.param_names(self.num_cg_levels, self.max_sh)
+        assert len(self._p_names) == n
+        self._cat_sizes = list(cats)
+        self._ws_cache: Dict[int, torch.Tensor] = {}
+
+    def _param_shapes(self) -> Dict[str, tuple]:
+        C, Z, cpe, W, G = self.num_channels_hidden, len(self.zs), self.num_channels_per_element, self.network_width, self.num_gaussians
+        nl = self.max_sh + 1
+        lat, late = (self.max_sh + 2) * Z * cpe * 2, (self.max_sh + 2) * cpe * 2
+        shapes = {'cg_model.input_func_atom.lin.weight': (2 * C, 4 * Z), 'cg_model.input_func_atom.lin.bias': (2 * C, )}
+        for k in range(self.num_cg_levels):
+            rad = f'cg_model.rad_funcs.rad_funcs.{k}'
+            shapes[f'{rad}.scales'] = (1, 1, 1, 8)
+            shapes[f'{rad}.phases'] = (1, 1, 1, 8)
+            cout = C if k < self.num_cg_levels - 1 else Z * cpe
+            for l in range(nl):
+                shapes[f'{rad}.linear.{l}.weight'] = (2 * C, 32)
+                shapes[f'{rad}.linear.{l}.bias'] = (2 * C, )
+                shapes[f'cg_model.cormorant_cg.edge_levels.{k}.cat_mix.mix_reps.weights.{l}'] = (C, self._cat_sizes[(k * nl + l) * 2], 2)
+                shapes[f'cg_model.cormorant_cg.atom_levels.{k}.cat_mix.mix_reps.weights.{l}'] = (cout, self._cat_sizes[(k * nl + l) * 2 + 1], 2)
+        for l in range(nl):
+            shapes[f'cg_mix.cat_mix.mix_reps.weights.{l}'] = (cpe, self._cat_sizes[self.num_cg_levels * nl * 2 + l], 2)
+        for head, (i, o) in dict(phi_focus=(lat, 1), phi_element=(lat, Z), phi_d=(late, 2 * G), phi_trans=(lat, W), phi_v=(W, 1)).items():
+            shapes[f'{head}.layers.0.weight'] = (W, i)
+            shapes[f'{head}.layers.0.bias'] = (W, )
+            shapes[f'{head}.layers.1.weight'] = (o, W)
+            shapes[f'{head}.layers.1.bias'] = (o, )
+        shapes['distance_log_stds'] = (G, )
+        return shapes
+
+    def _initial_values(self) -> Dict[str, torch.Tensor]:
+        """Same distributions as the reference's constructors, drawn in the reference's construction order
+        (covariant/modules.py:59-95 -> cormorant RadialFilters / InputLinear / CormorantCG 'rand' weights with level_gain 10,
+        modules.py:30-50 orthogonal MLPs, agent.py:131-133 log-stds)."""
+        C, Z, cpe = self.num_channels_hidden, len(self.zs), self.num_channels_per_element
+        shapes = self._param_shapes()
+        vals: Dict[str, torch.Tensor] = {}
+        nl = self.max_sh + 1
+
+        def linear(name, out_f, in_f):
+            lin = nn.Linear(in_f, out_f)
+            vals[f'{name}.weight'], vals[f'{name}.bias'] = lin.weight.data, lin.bias.data
+
+        def rand_mix(name, gain=10.0):
+            shape = shapes[name]
+            vals[name] = (gain / max(shape)) * (2 * torch.rand(shape) - 1)
+
+        for k in range(self.num_cg_levels):
+            rad = f'cg_model.rad_funcs.rad_funcs.{k}'
+            scales = torch.cat([torch.arange(4), torch.arange(4)]).view(1, 1, 1, -1).to(torch.float)
+            phases = torch.cat([torch.zeros(4), math.pi / 2 * torch.ones(4)]).view(1, 1, 1, -1)
+            phases[0, 0, 0, 0] = math.pi / 2
+            vals[f'{rad}.scales'], vals[f'{rad}.phases'] = scales, phases
+            for l in range(nl):
+                linear(f'{rad}.linear.{l}', 2 * C, 32)
+        linear('cg_model.input_func_atom.lin', 2 * C, 4 * Z)
+        for k in range(self.num_cg_levels):
+            for l in range(nl):
+                rand_mix(f'cg_model.cormorant_cg.edge_levels.{k}.cat_mix.mix_reps.weights.{l}', gain=1.0)
+            for l in range(nl):
+                rand_mix(f'cg_model.cormorant_cg.atom_levels.{k}.cat_mix.mix_reps.weights.{l}')
+        for l in range(nl):
+            rand_mix(f'cg_mix.cat_mix.mix_reps.weights.{l}')
+        for head in ('phi_focus', 'phi_element', 'phi_d'):
+            self._init_mlp(vals, shapes, head)
+        vals['distance_log_stds'] = torch.log(torch.tensor([0.1] * self.num_gaussians, dtype=torch.float))
+        for head in ('phi_trans', 'phi_v'):
+            self._init_mlp(vals, shapes, head)
+        return vals
+
+    @staticmethod
+    def _init_mlp(vals, shapes, head):
+        for layer in (0, 1):
+            out_f, in_f = shapes[f'{head}.layers.{layer}.weight']
+            lin = nn.Linear(in_f, out_f)
+            nn.init.orthogonal_(lin.weight.data)
+            nn.init.constant_(lin.bias.data, 0)
+            vals[f'{head}.layers.{layer}.weight'], vals[f'{head}.layers.{layer}.bias'] = lin.weight.data, lin.bias.data
+
+    def _init_parameters(self):
+        shapes = self._param_shapes()
+        vals = self._initial_values()
+        self._flat = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
+        self._flat_grad = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
+        self._grad_scratch = None
+        # registration order follows the reference's named_parameters(): log-stds first (agent.py:131), then module tree
+        order = ['distance_log_stds'] + [n for n in self._p_names if n != 'distance_log_stds']
+        index = {n: i for i, n in enumerate(self._p_names)}
+        self._views, self._grad_views = {}, {}
+        host = torch.zeros(self._p_total, dtype=torch.float32)
+        for name in self._p_names:
+            i = index[name]
+            o, n = self._p_offsets[i], self._p_numels[i]
+            assert int(np.prod(shapes[name])) == n, (name, shapes[name], n)
+            host[o:o + n] = vals[name].reshape(-1).to(torch.float32)
+        self._flat.copy_(host)
+        for name in order:
+            i = index[name]
+            o, n = self._p_offsets[i], self._p_numels[i]
+            p = nn.Parameter(self._flat[o:o + n].view(shapes[name]), requires_grad=True)
+            _register(self, name, p)
+            self._views[name] = p
+            self._grad_views[name] = self._flat_grad[o:o + n].view(shapes[name])
+        self._param_list = [self._views[n] for n in self._p_names]
+
+    # ------------------------------------------------------------------------------------------------------
+    # keep nn.Parameters aliased to the flat buffers (load_state_dict / optimizers keep the aliasing; .to(), pickling,
+    # or user code that rebinds .data do not)
+    # ------------------------------------------------------------------------------------------------------
+    def _params_aliased(self) -> bool:
+        base = self._flat.data_ptr()
+        first, last = self._param_list[0], self._param_list[-1]
+        return (first.data_ptr() == base + 4 * self._p_offsets[0] and last.data_ptr() == base + 4 * self._p_offsets[-1]
+                and first.device == self._flat.device)
+
+    def _realias(self):
+        with torch.no_grad():
+            for name, p, o, n in zip(self._p_names, self._param_list, self._p_offsets, self._p_numels):
+                view = self._flat[o:o + n].view(p.shape)
+                if p.data_ptr() != view.data_ptr():
+                    view.copy_(p.data.to(self._flat.device))
+                    p.data = view
+
+    def _attach_grads(self):
+        """Make every p.grad a view of the flat gradient buffer; returns True if existing values must be kept."""
+        first = self._param_list[0]
+        if first.grad is not None and first.grad.data_ptr() == self._flat_grad.data_ptr() + 4 * self._p_offsets[0]:
+            return True
+        if all(p.grad is None for p in self._param_list):
+            self._flat_grad.zero_()
+            keep = False
+        else:   # somebody assigned their own gradient tensors: fold them in
+            self._flat_grad.zero_()
+            for name, p in zip(self._p_names, self._param_list):
+                if p.grad is not None:
+                    self._grad_views[name].add_(p.grad)
+            keep = True
+        for name, p in zip(self._p_names, self._param_list):
+            p.grad = self._grad_views[name]
+        return keep
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in ('_plan', '_cfg', '_ws_cache', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.device = _lib.require_cuda_device(self.device)
+        self._init_native()
+        named = dict(self.named_parameters())
+        self._flat = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
+        self._flat_grad = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
+        self._grad_scratch = None
+        self._views = {n: named[n] for n in self._p_names}
+        self._param_list = [self._views[n] for n in self._p_names]
+        self._grad_views = {n: self._flat_grad[o:o + k].view(self._views[n].shape)
+                            for n, o, k in zip(self._p_names, self._p_offsets, self._p_numels)}
+        self._realias()
+
+    def __del__(self):
+        try:
+            _lib.load().mgb_cov_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------
+    # raw forward / backward through the C ABI
+    # ------------------------------------------------------------------------------------------------------
+    def _workspace(self, B: int, fresh: bool) -> torch.Tensor:
+        lib = _lib.load()
+        nbytes = lib.mgb_cov_workspace_bytes(self._plan, B)
+        if fresh:
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ws = self._ws_cache.get(B)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_cache = {B: ws}
+        return ws
+
+    def _forward_raw(self, pos, charges, bags, actions, want_extras=True, policy_only_ws=None):
+        lib = _lib.load()
+        if not self._params_aliased():
+            self._realias()
+        B, N, Z = pos.shape[0], self.canvas_size, len(self.zs)
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        logp, ent, v = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
+        extras = ()
+        o = _cabi.CovOutputs()
+        o.logp, o.ent, o.v = logp.data_ptr(), ent.data_ptr(), v.data_ptr()
+        if want_extras:
+            parts = torch.empty(B, 4, **f32)
+            fprobs, eprobs = torch.empty(B, N, **f32), torch.empty(B, Z, **f32)
+            gmm = torch.empty(B, 3, self.num_gaussians, **f32)
+            coeff = torch.empty(B, 25, self.num_channels_per_element, 2, **f32)
+            log_z = torch.empty(B, **f32)
+            o.logp_parts, o.focus_probs, o.element_probs = parts.data_ptr(), fprobs.data_ptr(), eprobs.data_ptr()
+            o.gmm, o.coefficients, o.log_z = gmm.data_ptr(), coeff.data_ptr(), log_z.data_ptr()
+            extras = (parts, fprobs, eprobs, gmm, coeff, log_z)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            if policy_only_ws is not None:
+                ws = policy_only_ws
+                _cabi.check(lib, lib.mgb_cov_policy(self._plan, B, bags.data_ptr(), actions.data_ptr(), self._flat.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), ctypes.byref(o), stream))
+            else:
+                ws = self._workspace(B, fresh=torch.is_grad_enabled())
+                _cabi.check(lib, lib.mgb_cov_forward(self._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
+                                                     actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     ctypes.byref(o), stream))
+        return (logp, ent, v) + extras, ws
+
+    def _backward_raw(self, pos, charges, bags, actions, ws, g_logp, g_ent, g_v):
+        lib = _lib.load()
+        dev = self.device
+        B = pos.shape[0]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        keep = self._attach_grads()
+        sharded = self.data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1
+        with torch.cuda.device(dev):
+            if sharded:
+                if self._grad_scratch is None:
+                    self._grad_scratch = torch.empty_like(self._flat_grad)
+                target, accumulate = self._grad_scratch, 0
+            else:
+                target, accumulate = self._flat_grad, 1 if keep else 0
+            _cabi.check(lib, lib.mgb_cov_backward(self._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
+                                                  actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), target.data_ptr(),
+                                                  accumulate, stream))
+            if sharded:
+                # the one exchange step of the path: sum of the flat gradient over ranks (NCCL over NVLink)
+                torch.distributed.all_reduce(self._grad_scratch, op=torch.distributed.ReduceOp.SUM)
+                if keep:
+                    self._flat_grad.add_(self._grad_scratch)
+                else:
+                    self._flat_grad.copy_(self._grad_scratch)
+
+    # ------------------------------------------------------------------------------------------------------
+    # the reference surface
+    # ------------------------------------------------------------------------------------------------------
+    def to_action_space(self, action, observation):
+        """agent.py:147-163."""
+        action = np.asarray(action.detach().cpu().numpy() if torch.is_tensor(action) else action)
+        assert action.shape == (6, )
+        focus = int(round(action[0].item()))
+        element_index = int(round(action[1].item()))
+        d, so3 = action[2], action[-3:]
+        null = self.zs.index(0)
+        atoms = [item for item in observation[0] if item[0] != null]
+        if len(atoms):
+            position = tuple(np.asarray(atoms[focus][1], dtype=np.float64) + d * so3)
+        else:
+            position = (0.0, 0.0, 0.0)
+        return element_index, position
+
+    def parse_observations(self, observations: List) -> Dict[str, torch.Tensor]:
+        """agent.py:165-197 — device tensors for a list of observations (one packed H2D copy per tensor)."""
+        pos, charges, bags = pack_observations(observations, self.zs, self.canvas_size)
+        dev = self.device
+        data = dict(positions=torch.from_numpy(pos).to(dev, non_blocking=True), charges=torch.from_numpy(charges).to(dev, non_blocking=True),
+                    bags=torch.from_numpy(bags).to(dev, non_blocking=True))
+        return data
+
+    def step(self, observations: List, actions: Optional[np.ndarray] = None) -> dict:
+        data = self.parse_observations(observations)
+        pos, charges, bags = data['positions'], data['charges'], data['bags']
+        response: Dict[str, Any] = {}
+        if actions is not None:
+            act = torch.as_tensor(actions, dtype=torch.float, device=self.device).contiguous()
+            assert act.shape == (len(observations), 6)
+            outs = self._evaluate(pos, charges, bags, act)
+        else:
+            act, outs = sampling.rollout(self, pos, charges, bags, training=self.training)
+            response['actions'] = [self.to_action_space(a, o) for a, o in zip(act.detach().cpu().numpy(), observations)]
+        logp, ent, v, parts, fprobs, eprobs, gmm, coeff, log_z = outs
+        response.update({
+            'a': act, 'logp': logp, 'ent': ent, 'v': v,
+            'dists': sampling.LazyDists(self, fprobs, eprobs, gmm, coeff, log_z, charges),
+        })
+        return response
+
+    def _evaluate(self, pos, charges, bags, act):
+        if torch.is_grad_enabled():
+            return _CovEvaluate.apply(self._param_list[-1], self, pos, charges, bags, act)
+        outs, _ = self._forward_raw(pos, charges, bags, act, want_extras=True)
+        return outs

@@ -58,8 +58,28 @@ def build_cusim(force=False):
     return CUSIM_LIB
 
 
+def packer_path():
+    import sysconfig
+    return os.path.join(LIB_DIR, '_mgb_packer' + sysconfig.get_config_var('EXT_SUFFIX'))
+
+
+def build_packer(force=False):
+    """CPython extension that flattens observation tuples (host side of the packing path)."""
+    import sysconfig
+    out = packer_path()
+    src = os.path.join(CSRC, 'packer.c')
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = ['gcc', '-O2', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'], src, '-o', out]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == '__main__':
     if '--cusim' in sys.argv:
         print(build_cusim(force=True))
+    elif '--packer' in sys.argv:
+        print(build_packer(force=True))
     else:
         print(build_cuda(force=True, verbose='-v' in sys.argv))

@@ -36,6 +36,18 @@ static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const flo
   return MGB_OK;
 }
 
+static int launch_policy_fwd(const mgb_cov_plan* plan, int B, const float* bags, const float* actions, const float* P,
+                             const CovWs& w, const mgb_cov_outputs* out, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const size_t sm = sizeof(float) * policy_smem_floats(d);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int grid = std::min(B, 148 * 4);
+  MGB_LAUNCH(k_policy_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
+             w.flogit, w.trans, *out);
+  MGB_LAUNCH_OK("k_policy_fwd");
+  return MGB_OK;
+}
+
 extern "C" {
 
 const char* mgb_last_error(void) { return g_err; }
@@ -250,6 +262,8 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   MGB_LAUNCH_OK("k_prep_params");
   MGB_LAUNCH(k_input_fwd, B, 128, sizeof(float) * N * d.S_in, st, plan->d_desc, P, charges, bags, w.n_atoms, w.X, w.A[0]);
   MGB_LAUNCH_OK("k_input_fwd");
+  if (out->covariats)   // padded atoms carry zero representations in the reference; the level kernels skip them
+    MGB_CUDA_OK(cudaMemsetAsync(w.A[d.K], 0, sizeof(float) * (size_t)B * N * kM * d.Cout * 2, st));
   for (int k = 0; k < d.K; ++k) {
     const LevelDesc& L = d.lv[k];
     const size_t esm = sizeof(float2) * (L.nlm_in * L.C + (kEdgeThreads / 32) * (L.sumCatE + 16));
@@ -273,17 +287,22 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
     MGB_LAUNCH_OK("k_rows_mlp_fwd");
   }
   {
-    const size_t sm = sizeof(float) * policy_smem_floats(d);
-    MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const int grid = std::min(B, 148 * 4);
-    MGB_LAUNCH(k_policy_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
-               w.flogit, w.trans, *out);
-    MGB_LAUNCH_OK("k_policy_fwd");
+    int rc = launch_policy_fwd(plan, B, bags, actions, P, w, out, st);
+    if (rc != MGB_OK) return rc;
   }
   if (out->covariats)
     MGB_CUDA_OK(cudaMemcpyAsync(out->covariats, w.A[d.K], sizeof(float) * (size_t)B * N * kM * d.Cout * 2, cudaMemcpyDeviceToDevice, st));
-  plan->forward_batch = B;
   return MGB_OK;
+}
+
+int mgb_cov_policy(mgb_cov_plan* plan, int32_t B, const float* bags, const float* actions, const float* P, void* workspace,
+                   size_t workspace_bytes, const mgb_cov_outputs* out, void* stream) {
+  if (!plan || !bags || !actions || !P || !workspace || !out) return fail(MGB_ERR_INVALID, "null argument");
+  if (!out->logp || !out->ent || !out->v) return fail(MGB_ERR_INVALID, "logp/ent/v outputs are required");
+  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
+  const CovWs w = carve_workspace(plan->desc, B, workspace);
+  if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  return launch_policy_fwd(plan, B, bags, actions, P, w, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -30,7 +30,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
                      const float* g_ent, const float* g_v, float* grad, int32_t accumulate, void* stream) {
   if (!plan || !pos || !charges || !bags || !actions || !P || !workspace || !g_logp || !g_ent || !g_v || !grad)
     return fail(MGB_ERR_INVALID, "null argument");
-  if (plan->forward_batch != B) return fail(MGB_ERR_STATE, "backward(batch=%d) without a matching forward (last forward batch %d)", B, plan->forward_batch);
+  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
   const CovDesc& d = plan->desc;
   const CovWs w = carve_workspace(d, B, workspace);
   if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
@@ -129,6 +129,37 @@ int mgb_ppo_loss(int32_t B, const float* logp, const float* ent, const float* v,
   MGB_LAUNCH(k_ppo_loss, 1, 256, 0, (cudaStream_t)stream, B, logp, ent, v, old_logp, adv, ret, clip_ratio, vf_coef, entropy_coef,
              inv_global_batch, info, g_logp, g_ent, g_v);
   MGB_LAUNCH_OK("k_ppo_loss");
+  return MGB_OK;
+}
+
+int64_t mgb_launch_count(void) { return g_prof.launches; }
+
+int mgb_profile_kernel(const char* substr) {
+#ifndef MGB_CUSIM
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.active = substr && substr[0];
+  std::snprintf(g_prof.pattern, sizeof(g_prof.pattern), "%s", substr ? substr : "");
+#endif
+  return MGB_OK;
+}
+
+int mgb_profile_read(double* total_ms, int64_t* launches) {
+  double tot = 0.0;
+  int64_t n = 0;
+#ifndef MGB_CUSIM
+  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
+    MGB_CUDA_OK(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float ms = 0.f;
+    MGB_CUDA_OK(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+#endif
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
   return MGB_OK;
 }
 

@@ -13,7 +13,6 @@ struct mgb_cov_plan {
   std::vector<mgb::TransposeSeg> segs;
   mgb::TransposeSeg* d_segs = nullptr;
   std::vector<long long> p_offsets, p_numels;
-  int forward_batch = -1;            // batch of the last forward on this plan's workspace (backward must match)
 };
 
 namespace mgb {

@@ -10,7 +10,37 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
-#define MGB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#include <vector>
+namespace mgb {
+// Launch accounting + optional per-kernel timing (CUDA events recorded on the launching stream around every launch whose
+// stringified name contains the selected substring); read back through mgb_launch_count / mgb_profile_read.
+struct Profiler {
+  long long launches = 0;
+  char pattern[64] = "";
+  bool active = false, hit = false;
+  std::vector<cudaEvent_t> ev;   // start/stop pairs not yet read
+};
+inline Profiler g_prof;
+inline void prof_begin(const char* name, cudaStream_t st) {
+  ++g_prof.launches;
+  g_prof.hit = g_prof.active && std::strstr(name, g_prof.pattern) != nullptr;
+  if (g_prof.hit) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    g_prof.ev.push_back(a); g_prof.ev.push_back(b);
+  }
+}
+inline void prof_end(cudaStream_t st) {
+  if (g_prof.hit) cudaEventRecord(g_prof.ev.back(), st);
+}
+}  // namespace mgb
+#define MGB_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+  do {                                                                \
+    mgb::prof_begin(#kernel, (stream));                               \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);       \
+    mgb::prof_end((stream));                                          \
+  } while (0)
 #define MGB_DYN_SMEM(type, name)                                        \
   extern __shared__ __align__(16) unsigned char _mgb_dyn_smem[];        \
   type* name = reinterpret_cast<type*>(_mgb_dyn_smem)

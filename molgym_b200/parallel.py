@@ -1,0 +1,73 @@
+"""Data-parallel sharding of the PPO minibatch: one process per GPU, canvases are independent
+through forward and backward, the only exchange is one sum-all-reduce of the flat parameter gradient (NCCL over
+NVLink) issued by CovariantAC's backward when `agent.data_parallel` is set.
+
+Two ways to use it, both keeping the reference's ppo.py arithmetic:
+  * `shard_agent(agent)` + every rank calls compute_loss on ITS OWN slice and divides the loss by the world size
+    (each rank's `mean()` is over its slice; with equal slices the summed gradients equal the global-mean gradient);
+  * `global_step(agent, observations, actions)`: every rank holds the whole minibatch, evaluates only its slice and
+    all-gathers logp / ent / v, so the loss, approx_kl and the early-stop branch (ppo.py:138-140) are identical on
+    every rank."""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of n canvases into `world` shards whose sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_agent(agent, broadcast: bool = True):
+    """Mark the agent data-parallel and make every rank start from rank 0's parameters."""
+    agent.data_parallel = True
+    if broadcast and dist.is_initialized() and dist.get_world_size() > 1:
+        agent._realias()
+        dist.broadcast(agent._flat, src=0)
+    return agent
+
+
+class _GatherShards(torch.autograd.Function):
+    """all-gather of per-shard [n_r] vectors into the global [n] vector; backward hands each rank its slice."""
+
+    @staticmethod
+    def forward(ctx, local: torch.Tensor, n: int):
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ctx.bounds = shard_bounds(n, rank, world)
+        width = (n + world - 1) // world
+        padded = local.new_zeros(width)
+        padded[:local.numel()] = local
+        gathered = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(gathered, padded)
+        parts = []
+        for r in range(world):
+            lo, hi = shard_bounds(n, r, world)
+            parts.append(gathered[r][:hi - lo])
+        return torch.cat(parts)
+
+    @staticmethod
+    def backward(ctx, grad):
+        lo, hi = ctx.bounds
+        return grad[lo:hi].contiguous(), None
+
+
+def gather_shards(local: torch.Tensor, n: int) -> torch.Tensor:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    return _GatherShards.apply(local, n)
+
+
+def global_step(agent, observations: List, actions) -> dict:
+    """step() on the whole minibatch with the work sharded over ranks; returns global logp / ent / v."""
+    n = len(observations)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_bounds(n, rank, world)
+    pred = agent.step(observations[lo:hi], actions[lo:hi])
+    out = dict(pred)
+    for k in ('logp', 'ent', 'v'):
+        out[k] = gather_shards(pred[k], n)
+    return out

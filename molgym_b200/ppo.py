@@ -1,0 +1,52 @@
+"""Host-side mirror of the PPO minibatch step that calls the hot path (reference: molgym/ppo.py:18-63 compute_loss,
+:66-89 batch generation, :99-160 train).  The reference's own ppo.py runs unchanged on top of molgym_b200's agents; this
+restatement exists so the benchmark and the tests can drive the same arithmetic on machines where the reference tree
+is not present (the GPU box)."""
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+
+def compute_loss(ac, data: dict, clip_ratio: float, vf_coef: float, entropy_coef: float, device=None) -> Tuple[torch.Tensor, Dict[str, float]]:
+    """ppo.py:18-63, same operations in the same order (adv / ret arrive as float64 numpy -> float64 loss)."""
+    pred = ac.step(data['obs'], data['act'])
+    device = device if device is not None else pred['logp'].device
+    old_logp = torch.as_tensor(data['logp'], device=device)
+    adv = torch.as_tensor(data['adv'], device=device)
+    ret = torch.as_tensor(data['ret'], device=device)
+    ratio = torch.exp(pred['logp'] - old_logp)
+    obj = ratio * adv
+    clipped_obj = ratio.clamp(1 - clip_ratio, 1 + clip_ratio) * adv
+    policy_loss = -torch.min(obj, clipped_obj).mean()
+    entropy_loss = -entropy_coef * pred['ent'].mean()
+    vf_loss = vf_coef * (pred['v'] - ret).pow(2).mean()
+    loss = policy_loss + entropy_loss + vf_loss
+    approx_kl = (old_logp - pred['logp']).mean()
+    clipped = ratio.lt(1 - clip_ratio) | ratio.gt(1 + clip_ratio)
+    clip_fraction = torch.as_tensor(clipped, dtype=torch.float32).mean()
+    stats = torch.stack([policy_loss.detach().double(), entropy_loss.detach().double(), vf_loss.detach().double(),
+                         loss.detach().double(), approx_kl.detach().double(), clip_fraction.double()]).cpu().numpy()
+    info = dict(policy_loss=float(stats[0]), entropy_loss=float(stats[1]), vf_loss=float(stats[2]), total_loss=float(stats[3]),
+                approx_kl=float(stats[4]), clip_fraction=float(stats[5]))
+    return loss, info
+
+
+def get_batch_generator(indices: np.ndarray, batch_size: int):
+    """ppo.py:66-74."""
+    assert len(indices.shape) == 1
+    indices = np.random.permutation(indices)
+    batches = indices[:len(indices) // batch_size * batch_size].reshape(-1, batch_size)
+    for batch in batches:
+        yield batch
+    r = len(indices) % batch_size
+    if r:
+        yield indices[-r:]
+
+
+def collect_data_batch(data: dict, indices: np.ndarray) -> dict:
+    """ppo.py:77-89."""
+    batch = {}
+    for k, v in data.items():
+        batch[k] = [v[i] for i in indices] if isinstance(v, list) else v[indices]
+    return batch

@@ -270,6 +270,8 @@ static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); ret
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 
 // Launch + dynamic shared memory portability macros (mirrored for CUDA in csrc/portable.h)
+namespace mgb { struct Profiler { long long launches = 0; }; inline Profiler g_prof; }
 #define MGB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ++mgb::g_prof.launches;                                  \
   cusim::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
 #define MGB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(((uintptr_t)cusim::g_block->dyn_smem + 15) & ~(uintptr_t)15)

@@ -104,3 +104,32 @@ class CusimCov:
                                                     self.ws_bytes, ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(grad),
                                                     0 if accumulate_into is None else 1, None))
         return grad
+
+
+def ppo_loss(logp, ent, v, old_logp, adv, ret, clip, vf, ent_coef, inv_b=None):
+    L = lib()
+    B = len(logp)
+    a = [np.ascontiguousarray(x, np.float32) for x in (logp, ent, v, old_logp)]
+    d = [np.ascontiguousarray(x, np.float64) for x in (adv, ret)]
+    info = np.zeros(8, np.float64)
+    g = [np.zeros(B, np.float32) for _ in range(3)]
+    _cabi.check(L, L.mgb_ppo_loss(B, *[ptr(x) for x in a], *[ptr(x) for x in d], clip, vf, ent_coef, (1.0 / B) if inv_b is None else inv_b,
+                                  ptr(info), ptr(g[0]), ptr(g[1]), ptr(g[2]), None))
+    return info, g
+
+
+def pack(zs, canvas_size, labels, xyz):
+    L = lib()
+    cfg = _cabi.CovConfig()
+    cfg.canvas_size, cfg.num_species = canvas_size, len(zs)
+    for i, z in enumerate(zs):
+        cfg.zs[i] = int(z)
+    labels = np.ascontiguousarray(labels, np.int32)
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    B = len(labels)
+    pos = np.empty((B, canvas_size, 3), np.float32)
+    charges = np.empty((B, canvas_size), np.int32)
+    rc = L.mgb_pack_observations(ctypes.byref(cfg), B, ptr(labels), ptr(xyz), ptr(pos), ptr(charges))
+    if rc != 0:
+        raise RuntimeError(L.mgb_last_error().decode())
+    return pos, charges

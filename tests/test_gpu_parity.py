@@ -1,0 +1,198 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the product path — CovariantAC.step through the C ABI and the
+sm_100a kernels — against the committed golden vectors (reference's own code), the oracle on fresh canvases, and
+size-independent properties at BASELINE.json's full minibatch sizes."""
+import dataclasses
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from molgym_b200 import synth
+from tests.util_golden import (agent_kwargs_from_config, assert_grads_close, assert_outputs_close, golden_grads,
+                               golden_observations, golden_state_dict, load_golden)
+
+pytestmark = pytest.mark.gpu
+OUT_REL = 1e-5   # abs(x - ref) <= 1e-5 * max(abs(ref), 1e-3)  (north_star: logits/value within 1e-5 relative)
+
+
+def make_agent(cfg_zs, canvas_size, **kw):
+    from molgym_b200.agents.covariant.agent import CovariantAC
+    from molgym_b200.spaces import ActionSpace, ObservationSpace
+    return CovariantAC(ObservationSpace(canvas_size, cfg_zs), ActionSpace(cfg_zs), device=torch.device('cuda:0'), **kw)
+
+
+def grads_of(agent):
+    return {n: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+            for n, p in agent.named_parameters()}
+
+
+def test_native_library_is_loaded_and_is_the_cuda_build():
+    from molgym_b200 import _lib
+    lib = _lib.load()
+    assert lib.mgb_is_cuda_build() == 1
+    maps = open('/proc/self/maps').read()
+    assert 'libmolgym_b200.so' in maps
+
+
+@pytest.mark.parametrize('name', ['covariant_sf6_beta', 'covariant_hco_nobeta_trained'])
+def test_golden_step_loss_and_gradients(name):
+    from molgym_b200 import ppo
+    g = load_golden(name)
+    cfg = g['config']
+    agent = make_agent(cfg['zs'], cfg['canvas_size'], **agent_kwargs_from_config(cfg))
+    missing = agent.load_state_dict(golden_state_dict(g))
+    assert not missing.missing_keys and not missing.unexpected_keys
+    obs = golden_observations(g)
+    pred = agent.step(obs, g['actions'])
+    for key in ('logp', 'ent', 'v'):
+        assert_outputs_close(pred[key].detach().cpu().numpy(), g[key], rel=OUT_REL, what=key)
+    assert_outputs_close(pred['dists'][0].probs.cpu().numpy(), g['focus_probs'], rel=OUT_REL, what='focus_probs')
+    assert_outputs_close(pred['dists'][1].probs.cpu().numpy(), g['element_probs'], rel=OUT_REL, what='element_probs')
+    for ell, part in enumerate(pred['dists'][3].coefficients):
+        assert_outputs_close(part.cpu().numpy(), g[f'coeff_{ell}'], rel=OUT_REL, floor=1.0, what=f'coeff_{ell}')
+    agent.zero_grad()
+    loss, info = ppo.compute_loss(agent, dict(obs=obs, act=g['actions'], logp=g['old_logp'], adv=g['adv'], ret=g['ret']), 0.2, 0.5, 0.01)
+    loss.backward()
+    assert abs(loss.item() - float(g['loss'])) <= 1e-5
+    for key in ('policy_loss', 'vf_loss', 'entropy_loss', 'approx_kl', 'clip_fraction'):
+        assert abs(info[key] - float(g['info_' + key])) <= 1e-5, key
+    assert_grads_close(grads_of(agent), golden_grads(g))
+
+
+@pytest.mark.parametrize('which,batch', [('C2', 140), ('C3', 96), ('C5', 24)])
+def test_fresh_canvases_against_oracle(which, batch):
+    from oracle.molgym_oracle import CovariantOracle, ppo_loss
+    from molgym_b200 import ppo
+    cfg = synth.CONFIGS[which]
+    torch.manual_seed(11)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle.load_state_dict({k: v.detach().cpu() for k, v in agent.state_dict().items()})
+    obs, n = synth.make_observations(cfg, batch=batch)
+    act = synth.make_actions(cfg, obs, n)
+    ref = oracle.step(obs, act)
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, ref['logp'].detach().numpy())
+    loss, info = ppo.compute_loss(agent, dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret), 0.2, 0.5, 0.01)
+    loss.backward()
+    pred = agent.step(obs, act)
+    for key in ('logp', 'ent', 'v'):
+        assert_outputs_close(pred[key].detach().cpu().numpy(), ref[key].detach().numpy(), rel=OUT_REL, what=key)
+    ref_loss, _ = ppo_loss(ref['logp'], ref['ent'], ref['v'], old_logp, adv, ret, 0.2, 0.5, 0.01)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5
+    ref_grads = {k: (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k, p in oracle.named_parameters()}
+    assert_grads_close(grads_of(agent), ref_grads)
+
+
+def test_gradients_accumulate_over_minibatches_like_autograd():
+    """ppo.train sums gradients over minibatches before one optimizer step (ppo.py:118-131)."""
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    torch.manual_seed(2)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=40)
+    act = synth.make_actions(cfg, obs, n)
+    w = torch.linspace(-1, 1, 40, device='cuda')
+
+    def objective(lo, hi):
+        p = agent.step(obs[lo:hi], act[lo:hi])
+        return (p['logp'] * w[lo:hi]).sum() + p['v'].sum() - 0.3 * p['ent'].sum()
+
+    agent.zero_grad()
+    objective(0, 40).backward()
+    whole = grads_of(agent)
+    agent.zero_grad()
+    objective(0, 25).backward()
+    objective(25, 40).backward()
+    assert_grads_close(grads_of(agent), whole, rel=2e-5)
+    # optimizer + clipping work on the parameters and update the flat buffer the kernels read
+    opt = torch.optim.Adam(agent.parameters(), lr=1e-3)
+    torch.nn.utils.clip_grad_norm_(agent.parameters(), 0.5)
+    before = agent.step(obs, act)['logp'].detach().clone()
+    opt.step()
+    after = agent.step(obs, act)['logp'].detach()
+    assert (before - after).abs().max() > 0
+
+
+def test_full_size_properties_batch_independence_and_rotation_invariance():
+    """C2 at the full minibatch (140): (1) evaluating canvases alone equals evaluating them in the batch; (2) a global
+    rotation of canvas and orientation leaves logp / ent / v unchanged (SO(3) invariance, the property the reference's
+    own agent tests pin, tests/agents/covariant/test_agent.py:43-123)."""
+    cfg = synth.CONFIGS['C2']
+    torch.manual_seed(4)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg)
+    act = synth.make_actions(cfg, obs, n)
+    with torch.no_grad():
+        full = agent.step(obs, act)
+        for lo in (0, 57, 133):
+            part = agent.step(obs[lo:lo + 7], act[lo:lo + 7])
+            for key in ('logp', 'ent', 'v'):
+                assert torch.equal(part[key], full[key][lo:lo + 7]), key
+        rng = np.random.default_rng(0)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        rot_obs = [(tuple((lab, tuple(q @ np.asarray(xyz))) for lab, xyz in canvas), bag) for canvas, bag in obs]
+        rot_act = act.copy()
+        rot_act[:, 3:6] = act[:, 3:6] @ q.T
+        rot = agent.step(rot_obs, rot_act)
+    for key in ('logp', 'ent', 'v'):
+        a, b = full[key].cpu().numpy(), rot[key].cpu().numpy()
+        assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(a).max()), (key, np.abs(a - b).max())
+
+
+def test_largest_canvas_config_runs_at_full_width_and_is_finite():
+    cfg = synth.CONFIGS['C5']
+    torch.manual_seed(1)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=256)
+    act = synth.make_actions(cfg, obs, n)
+    pred = agent.step(obs, act)
+    (pred['logp'].mean() + pred['v'].mean()).backward()
+    for key in ('logp', 'ent', 'v'):
+        assert torch.isfinite(pred[key]).all()
+    for name, p in agent.named_parameters():
+        assert torch.isfinite(p.grad).all(), name
+
+
+def test_rollout_mode_samples_valid_actions_and_consistent_logp():
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    torch.manual_seed(3)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=10)
+    for training in (True, False):
+        agent.training = training      # ppo.py:353,361 toggles the bare attribute
+        with torch.no_grad():
+            pred = agent.step(obs)
+        a = pred['a'].cpu().numpy()
+        assert a.shape == (10, 6) and len(pred['actions']) == 10
+        for row, (canvas, bag), k in zip(a, obs, n):
+            assert 0 <= round(row[0]) < max(k, 1)
+            assert bag[int(round(row[1]))] > 0
+            assert abs(np.linalg.norm(row[3:6]) - 1) < 1e-4
+        with torch.no_grad():
+            again = agent.step(obs, a)
+        assert torch.allclose(again['logp'], pred['logp'], rtol=1e-5, atol=1e-5)
+
+
+def test_whole_module_pickle_round_trip():
+    """tools/model_util.py:82-117 saves and loads the whole module object."""
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=6)
+    act = synth.make_actions(cfg, obs, n)
+    clone = pickle.loads(pickle.dumps(agent))
+    with torch.no_grad():
+        assert torch.equal(agent.step(obs, act)['logp'], clone.step(obs, act)['logp'])
+
+
+def test_bad_inputs_raise():
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=3)
+    with pytest.raises(AssertionError):
+        agent.step(obs, np.zeros((3, 5), np.float32))
+    bad = [(((-1, (0.0, 0.0, 0.0)), ) + obs[0][0][1:], obs[0][1])]
+    with pytest.raises(RuntimeError):
+        agent.step(bad, np.zeros((1, 6), np.float32))
