@@ -20,8 +20,8 @@ static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const flo
   const int co = pick_co(L.Cout);
 #define MGB_ATOM_CASE(CO)                                                                                          \
   case CO: {                                                                                                       \
-    MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_fwd<NLM2, CO, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    MGB_LAUNCH((k_atom_fwd<NLM2, CO, 3>), B * d.N, kAtomThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms,  \
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_fwd<NLM2, CO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MGB_LAUNCH((k_atom_fwd<NLM2, CO, 2>), B * d.N, kAtomThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms,  \
                w.A[level], w.E[level], w.cat[level], w.A[level + 1]);                                             \
   } break;
   switch (co) {
@@ -42,8 +42,8 @@ static int launch_policy_fwd(const mgb_cov_plan* plan, int B, const float* bags,
   const size_t sm = sizeof(float) * policy_smem_floats(d);
   MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int grid = std::min(B, 148 * 4);
-  MGB_LAUNCH(k_policy_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
-             w.flogit, w.trans, *out);
+  MGB_LAUNCH(k_policy_fwd, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
+             w.flogit, w.trans, reinterpret_cast<float2*>(w.lse), *out);
   MGB_LAUNCH_OK("k_policy_fwd");
   return MGB_OK;
 }
@@ -67,8 +67,8 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   if (cfg->num_cg_levels < 1 || cfg->num_cg_levels > kMaxLevels) return fail(MGB_ERR_INVALID, "num_cg_levels out of range");
   if (cfg->num_species < 1 || cfg->num_species > MGB_MAX_SPECIES) return fail(MGB_ERR_INVALID, "num_species out of range");
   if (cfg->canvas_size < 1 || cfg->canvas_size > 64) return fail(MGB_ERR_INVALID, "canvas_size must be in 1..64");
-  if (cfg->num_channels_hidden < 1 || cfg->num_channels_hidden * kM > kAtomThreads)
-    return fail(MGB_ERR_INVALID, "num_channels_hidden must be in 1..%d", kAtomThreads / kM);
+  if (cfg->num_channels_hidden < 1 || cfg->num_channels_hidden > 10)
+    return fail(MGB_ERR_INVALID, "num_channels_hidden must be in 1..10 in this build");
   if (cfg->num_channels_per_element < 1 || cfg->num_channels_per_element > 4)
     return fail(MGB_ERR_INVALID, "num_channels_per_element must be in 1..4");
   if (cfg->num_species * cfg->num_channels_per_element > 32) return fail(MGB_ERR_INVALID, "too many output channels");
@@ -145,6 +145,11 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     for (int l = 0; l < kNL; ++l)
       plan->segs.push_back(TransposeSeg{L.p_radW + (long long)l * C2 * kRadFeat, wt + (long long)l * C2 * kRadFeat, C2, kRadFeat, 1});
     wt += (long long)kNL * C2 * kRadFeat;
+    {
+      const int zero[kNL] = {0, 0, 0, 0, 0};
+      resolve_cg_table(ag, L.catA, L.offA, zero, C, false);
+      resolve_cg_table(sq, L.catA, L.offA, L.sq_block, C, true);
+    }
     pending.push_back(stage_table(arena, ag, &L.ag));
     pending.push_back(stage_table(arena, sq, &L.sq));
   }
@@ -159,6 +164,10 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     d.totM = ao; d.totWM = wo;
     d.p_mixW = p;
     for (int l = 0; l < kNL; ++l) param((long long)d.CPE * d.catM[l] * 2);
+    {
+      const int one[kNL] = {1, 1, 1, 1, 1};
+      resolve_cg_table(sq_full, d.catM, d.offM, one, d.CPE, true);
+    }
     pending.push_back(stage_table(arena, sq_full, &d.mix_sq));
   }
   auto mlp = [&](MlpDesc& m, int in, int hidden, int outn) {
@@ -178,8 +187,8 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   d.p_logstd = param(d.G);
   d.n_params = p;
   d.n_wt = wt;
-  d.n_units_hidden = build_mix_units(d.units_hidden, 3);
-  d.n_units_out = build_mix_units(d.units_out, 3);
+  d.n_units_hidden = build_mix_units(d.units_hidden, 2);
+  d.n_units_out = build_mix_units(d.units_out, 2);
 
   // ---- Lebedev tables
   size_t o_leb_y = 0, o_leb_w = 0;
@@ -191,7 +200,10 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
       const double nr = std::sqrt(x * x + yy * yy + z * z);
       if (nr > 0) { x /= nr; yy /= nr; z /= nr; }
       host_sph_harm(x, yy, z, y);
-      for (int q = 0; q < kM * 2; ++q) ly[(size_t)g * kM * 2 + q] = (float)y[q];
+      for (int q = 0; q < kM; ++q) {   // layout [25][n_grid] complex
+        ly[((size_t)q * n_grid + g) * 2 + 0] = (float)y[2 * q];
+        ly[((size_t)q * n_grid + g) * 2 + 1] = (float)y[2 * q + 1];
+      }
       lw[g] = (float)std::log((double)(float)leb_w[g]);   // torch.log(weights) on the float32 weights
     }
     o_leb_y = arena.add(ly.data(), ly.size() * sizeof(float));
@@ -258,19 +270,26 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = d.N;
-  MGB_LAUNCH(k_prep_params, (int)plan->segs.size(), 256, 0, st, plan->d_segs, P, w.Wt);
+  MGB_LAUNCH(k_prep_params, (int)((d.n_wt + 255) / 256), 256, 0, st, plan->d_segs, (int)plan->segs.size(), (long long)d.n_wt, P, w.Wt);
   MGB_LAUNCH_OK("k_prep_params");
   MGB_LAUNCH(k_input_fwd, B, 128, sizeof(float) * N * d.S_in, st, plan->d_desc, P, charges, bags, w.n_atoms, w.X, w.A[0]);
   MGB_LAUNCH_OK("k_input_fwd");
   if (out->covariats)   // padded atoms carry zero representations in the reference; the level kernels skip them
     MGB_CUDA_OK(cudaMemsetAsync(w.A[d.K], 0, sizeof(float) * (size_t)B * N * kM * d.Cout * 2, st));
+  MGB_LAUNCH(k_pair_offsets, 1, 1024, 0, st, B, w.n_atoms, w.pair_off);
+  MGB_LAUNCH_OK("k_pair_offsets");
+  const int pair_ctas = (int)std::min<long long>(((long long)B * N * N + 7) / 8, 148 * 8);
   for (int k = 0; k < d.K; ++k) {
     const LevelDesc& L = d.lv[k];
-    const size_t esm = sizeof(float2) * (L.nlm_in * L.C + (kEdgeThreads / 32) * (L.sumCatE + 16));
+    const size_t esm = sizeof(float2) * (kEdgeThreads / 32) * edge_warp_floats2(L, false);
     if (k == 0) {
-      MGB_LAUNCH(k_edge_fwd<1>, B * N, kEdgeThreads, esm, st, plan->d_desc, k, P, w.Wt, pos, w.n_atoms, w.A[k], (const float*)nullptr, w.E[k]);
+      MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+      MGB_LAUNCH(k_edge_fwd<1>, pair_ctas, kEdgeThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
+                 (const float*)nullptr, w.E[k]);
     } else {
-      MGB_LAUNCH(k_edge_fwd<kNL>, B * N, kEdgeThreads, esm, st, plan->d_desc, k, P, w.Wt, pos, w.n_atoms, w.A[k], w.E[k - 1], w.E[k]);
+      MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+      MGB_LAUNCH(k_edge_fwd<kNL>, pair_ctas, kEdgeThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
+                 w.E[k - 1], w.E[k]);
     }
     MGB_LAUNCH_OK("k_edge_fwd");
     int rc = k == 0 ? launch_atom_fwd<1>(plan, k, B, P, pos, w, st) : launch_atom_fwd<kM>(plan, k, B, P, pos, w, st);

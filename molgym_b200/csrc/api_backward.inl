@@ -3,10 +3,12 @@
 namespace mgb {
 struct DwProblemList {
   DwProblem p[12];
-  int n;
+  DwWork w[64];
+  int n, nw;
 };
-__global__ void k_store_dw_problems(DwProblemList list, DwProblem* __restrict__ dst) {
+__global__ void k_store_dw_problems(DwProblemList list, DwProblem* __restrict__ dst, DwWork* __restrict__ wdst) {
   if ((int)threadIdx.x < list.n) dst[threadIdx.x] = list.p[threadIdx.x];
+  if ((int)threadIdx.x < list.nw) wdst[threadIdx.x] = list.w[threadIdx.x];
 }
 }  // namespace mgb
 
@@ -16,9 +18,20 @@ static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const flo
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
   const size_t smem = sizeof(float) * atom_bwd_smem_floats(L);
-  MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms, w.A[level], w.E[level],
-             w.dA[(level + 1) & 1], w.dA[level & 1], w.dE[level & 1], accumulate_dE);
+#define MGB_ATOM_BWD_CASE(CO)                                                                                          \
+  case CO: {                                                                                                           \
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    MGB_LAUNCH((k_atom_bwd<NLM2, CO>), B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms,      \
+               w.A[level], w.E[level], w.dA[(level + 1) & 1], w.dA[level & 1], w.dE[level & 1], accumulate_dE);        \
+  } break;
+  switch (pick_co(L.Cout)) {
+    MGB_ATOM_BWD_CASE(10)
+    MGB_ATOM_BWD_CASE(8)
+    MGB_ATOM_BWD_CASE(6)
+    MGB_ATOM_BWD_CASE(5)
+    MGB_ATOM_BWD_CASE(4)
+  }
+#undef MGB_ATOM_BWD_CASE
   MGB_LAUNCH_OK("k_atom_bwd");
   return MGB_OK;
 }
@@ -46,8 +59,8 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     const size_t sm = sizeof(float) * (policy_smem_floats(d) + policy_bwd_extra_floats(d));
     MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int grid = std::min(B, 148 * 2);
-    MGB_LAUNCH(k_policy_bwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
-               w.trans, g_logp, g_ent, g_v, o, grad);
+    MGB_LAUNCH(k_policy_bwd, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
+               w.trans, d.has_beta ? reinterpret_cast<const float2*>(w.lse) : (const float2*)nullptr, g_logp, g_ent, g_v, o, grad);
     MGB_LAUNCH_OK("k_policy_bwd");
   }
   {
@@ -67,24 +80,36 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, st);
     if (rc != MGB_OK) return rc;
     {
-      const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 7) / 8, 148 * 2));
+      const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + kMixDwAtoms - 1) / kMixDwAtoms, 148 * 2));
       dim3 grid(chunks, kNL);
-      MGB_LAUNCH(k_mix_dw, grid, kMixDwThreads, sizeof(float2) * 9 * L.Cout, st, plan->d_desc, k, B, w.n_atoms, w.cat[k],
-                 w.dA[(k + 1) & 1], grad);
+      const size_t sm = sizeof(float2) * kMixDwAtoms * 9 * L.Cout;
+#define MGB_MIXDW_CASE(CO)                                                                                              \
+  case CO:                                                                                                              \
+    MGB_LAUNCH(k_mix_dw<CO>, grid, kMixDwThreads, sm, st, plan->d_desc, k, B, w.n_atoms, w.cat[k], w.dA[(k + 1) & 1], grad); \
+    break;
+      switch (pick_co(L.Cout)) {
+        MGB_MIXDW_CASE(10)
+        MGB_MIXDW_CASE(8)
+        MGB_MIXDW_CASE(6)
+        MGB_MIXDW_CASE(5)
+        MGB_MIXDW_CASE(4)
+      }
+#undef MGB_MIXDW_CASE
       MGB_LAUNCH_OK("k_mix_dw");
     }
     {
-      const int per_warp = L.sumCatE + 16 + kNL * L.C;
-      const size_t esm = sizeof(float2) * (L.nlm_in * L.C + kEdgeBwdWarps * per_warp);
-      const int grid = (int)std::min<size_t>(BN, 148 * 2);
+      const size_t esm = sizeof(float2) * kEdgeBwdWarps * edge_warp_floats2(L, true);
+      const int grid = (int)std::min<size_t>((BN * N + kEdgeBwdWarps - 1) / kEdgeBwdWarps, 148);
       if (k == 0) {
-        MGB_LAUNCH(k_edge_bwd<1>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.A[k],
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+        MGB_LAUNCH(k_edge_bwd<1>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
                    (const float*)nullptr, w.dE[k & 1], (float*)nullptr, w.dD, grad);
         MGB_LAUNCH_OK("k_edge_bwd");
         MGB_LAUNCH(k_dot_bwd<1>, B * N, 64, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
       } else {
-        MGB_LAUNCH(k_edge_bwd<kNL>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.A[k], w.E[k - 1],
-                   w.dE[k & 1], w.dE[(k - 1) & 1], w.dD, grad);
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_bwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+        MGB_LAUNCH(k_edge_bwd<kNL>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
+                   w.E[k - 1], w.dE[k & 1], w.dE[(k - 1) & 1], w.dD, grad);
         MGB_LAUNCH_OK("k_edge_bwd");
         MGB_LAUNCH(k_dot_bwd<kNL>, B * N, 256, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
       }
@@ -110,11 +135,15 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     add(w.hv, w.dyv, B, d.Wd, 1, kRowsAll, d.value.W1, d.value.b1);
     add(w.X, w.dA[0], rows, d.S_in, 2 * d.C, kRowsValid, d.p_inW, d.p_inb);
     list.n = q;
-    MGB_LAUNCH(k_store_dw_problems, 1, 32, 0, st, list, w.dw_probs);
+    int nw = 0;
+    for (int pi = 0; pi < q; ++pi)
+      for (int o0 = 0; o0 < list.p[pi].No; o0 += kDwTileO) list.w[nw++] = DwWork{pi, o0};
+    list.nw = nw;
+    MGB_LAUNCH(k_store_dw_problems, 1, 64, 0, st, list, w.dw_probs, w.dw_work);
     MGB_LAUNCH_OK("k_store_dw_problems");
-    const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 31) / 32, 64));
-    dim3 grid(chunks, q);
-    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, sizeof(float) * kDwRowChunk * kDwTileO, st, w.dw_probs, w.n_atoms, N, grad);
+    const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
+    dim3 grid(chunks, nw);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, w.dw_probs, w.dw_work, w.n_atoms, N, grad);
     MGB_LAUNCH_OK("k_dw_grouped");
   }
   return MGB_OK;

@@ -133,6 +133,10 @@ struct CgTable {
   const int* pair_start;   // [n_pair+1]   transposed table: pair = lm1*nlm2 + lm2
   const int* pair_out;     // [n_term]
   const float* pair_coef;  // [n_term]
+  // resolved against one use site (cat layout, channel count): offsets in complex units for channel 0
+  const int* out_dst;      // [n_out]  destination inside the cat vector
+  const int2* term_src;    // [n_term] (a, b): product table -> a = (lm1*nlm2+lm2)*C ; square -> a = lm1*C, b = lm2*C
+  const int2* pair_ent;    // [n_term] (destination inside the cat vector, float bits of the coefficient)
 };
 
 // One Cormorant level (edge network + atom network), everything the kernels need by value.

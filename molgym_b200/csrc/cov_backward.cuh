@@ -57,17 +57,18 @@ struct PolicyBwdOut {
 __device__ __forceinline__ void gemv_n(const float* __restrict__ W, const float* x, int rows, int cols, float* y) {
   for (int k = threadIdx.x; k < cols; k += blockDim.x) {
     float acc = 0.f;
+#pragma unroll 8
     for (int h = 0; h < rows; ++h) acc = fmaf(W[(long long)h * cols + k], x[h], acc);
     y[k] = acc;
   }
 }
 
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kPolicyThreads)
 k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
-             const float* __restrict__ trans, const float* __restrict__ g_logp, const float* __restrict__ g_ent,
-             const float* __restrict__ g_v, PolicyBwdOut o, float* __restrict__ grad) {
+             const float* __restrict__ trans, const float2* __restrict__ lse_saved, const float* __restrict__ g_logp,
+             const float* __restrict__ g_ent, const float* __restrict__ g_v, PolicyBwdOut o, float* __restrict__ grad) {
   const CovDesc& d = *dp;
   MGB_DYN_SMEM(float, sm);
   PolicySmem s = policy_smem_carve(d, sm);
@@ -88,7 +89,7 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     PolicyScalars ps;
     __syncthreads();
-    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps);
+    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps, lse_saved);
     const float gl = g_logp[b], ge = g_ent[b], gv = g_v[b];
     const int nact = ps.n > 1 ? ps.n : 1;
     // ---- value head
@@ -188,19 +189,33 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
       if (d.has_beta) {
         // -g * dlogZ/da~ : softmax-weighted over the Lebedev grid
         for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
-          const float2* y = reinterpret_cast<const float2*>(d.leb_y) + (long long)g * kM;
-          const float2 sg = sph_sum(a_loc, y);
+          const float2* y = reinterpret_cast<const float2*>(d.leb_y) + g;
+          float2 yv[kM];
+          MGB_UNROLL
+          for (int q = 0; q < kM; ++q) yv[q] = y[(long long)q * d.n_grid];
+          const float2 sg = sph_sum(a_loc, yv);
           const float wgt = expf(-d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g] - ps.lse_max) / ps.lse_sum;
           const float cf = -gl * wgt * (-2.f * d.beta);
           const float2 z = make_float2(cf * sg.x, cf * sg.y);
           MGB_UNROLL
-          for (int q = 0; q < kM; ++q) cfmacl(da[q], y[q], z);   // conj(Y) * z
+          for (int q = 0; q < kM; ++q) cfmacl(da[q], yv[q], z);   // conj(Y) * z
         }
       }
-      // block-reduce the 50 numbers
-      for (int q = 0; q < kM; ++q) {
-        const float rx = block_sum(da[q].x, s.red), ry = block_sum(da[q].y, s.red);
-        if (threadIdx.x == 0) s_da[q] = make_float2(rx, ry);
+      // block-reduce the 50 numbers: shuffles inside each warp, then one pass over the per-warp partials
+      {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        float* part = reinterpret_cast<float*>(s_dcat);   // [nwarps][50] scratch (the mixer cotangent is written later)
+        MGB_UNROLL
+        for (int q = 0; q < kM; ++q) {
+          const float rx = warp_sum(da[q].x), ry = warp_sum(da[q].y);
+          if (lane == 0) { part[warp * 2 * kM + 2 * q] = rx; part[warp * 2 * kM + 2 * q + 1] = ry; }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < 2 * kM) {
+          float acc = 0.f;
+          for (int w = 0; w < nwarps; ++w) acc += part[w * 2 * kM + threadIdx.x];
+          reinterpret_cast<float*>(s_da)[threadIdx.x] = acc;
+        }
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -301,14 +316,20 @@ __host__ __device__ inline int policy_bwd_extra_floats(const CovDesc& d) {
 // Atom level backward for atom i (see k_atom_fwd).  Inputs: dOut = d A_{k+1}[b,i].  Produces
 //   dE_k[b,i,j,:,:] for all j (assigned, or added when the next level's edge network already wrote its share),
 //   dA_k[b,j] += ... for all j (global atomics; dA_k zero-initialised), including the own-atom terms.
+// Phases: (A) dcat = W^H dOut into shared memory; (B) row pass: dT[x][.] in registers -> dE_ij; (C) column pass:
+// dT[.][x] in registers -> dA_j.  The neighbours are staged twice so that only one 25-vector of dT lives in registers.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kAtomBwdThreads = 256;
+constexpr int kJChunkBwd = 4;
+
 __host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L) {
   const int nlm2 = L.nlm_in;
-  const int stage = kJChunk * (kM + kNL * L.C + nlm2 * L.C + kM * L.C + kNL * L.C) * 2;
+  const int stage = kJChunkBwd * (kM + kNL * L.C + nlm2 * L.C + kM * L.C + kNL * L.C) * 2;
   return L.totA * 2 + kM * L.Cout * 2 + stage + nlm2 * L.C * 2;
 }
 
-// dcat[l][m][k] = sum_c' conj(W_l[c'][k]) dOut[lm][c']   (warp units, lanes over k)
+// dcat[l][m][k] = sum_c' conj(W_l[c'][k]) dOut[lm][c']   (warp units of <= 2 rows, lanes over k, dOut rows in registers)
+template <int CO>
 __device__ __forceinline__ void mix_rows_bwd(const MixUnit* __restrict__ units, int n_units, const int* catA, const int* offA,
                                              const int* offW, int Cout, const float2* __restrict__ W,
                                              const float2* __restrict__ sdOut, float2* __restrict__ sDcat) {
@@ -316,24 +337,59 @@ __device__ __forceinline__ void mix_rows_bwd(const MixUnit* __restrict__ units, 
   for (int u = warp; u < n_units; u += nwarps) {
     const MixUnit un = units[u];
     const int K = catA[un.l];
-    const float2* Wl = W + offW[un.l];
     const int lm0 = un.l * un.l + un.m0;
-    for (int k = lane; k < K; k += 32) {
-      float2 acc[3];
-      acc[0] = acc[1] = acc[2] = make_float2(0.f, 0.f);
-      for (int c = 0; c < Cout; ++c) {
-        const float2 w = Wl[c * K + k];
-        MGB_UNROLL
-        for (int q = 0; q < 3; ++q)
-          if (q < un.nm) cfmacl(acc[q], w, sdOut[(lm0 + q) * Cout + c]);
+    float2 acc0[12], acc1[12];   // up to 12 k-slots per lane (K <= 384)
+    const int nslot = (K + 31) >> 5;
+    MGB_UNROLL
+    for (int sIdx = 0; sIdx < 12; ++sIdx) { acc0[sIdx] = make_float2(0.f, 0.f); acc1[sIdx] = make_float2(0.f, 0.f); }
+    for (int c0 = 0; c0 < Cout; c0 += CO) {
+      float2 g0[CO], g1[CO];
+      MGB_UNROLL
+      for (int c = 0; c < CO; ++c) {
+        const bool on = c0 + c < Cout;
+        g0[c] = on ? sdOut[lm0 * Cout + c0 + c] : make_float2(0.f, 0.f);
+        g1[c] = (on && un.nm > 1) ? sdOut[(lm0 + 1) * Cout + c0 + c] : make_float2(0.f, 0.f);
       }
-      for (int q = 0; q < un.nm; ++q) sDcat[offA[un.l] + (un.m0 + q) * K + k] = acc[q];
+      const float2* Wl = W + offW[un.l] + (long long)c0 * K;
+      MGB_UNROLL
+      for (int sIdx = 0; sIdx < 12; ++sIdx) {
+        const int k = lane + 32 * sIdx;
+        if (sIdx < nslot && k < K) {
+          float2 w[CO];
+          MGB_UNROLL
+          for (int c = 0; c < CO; ++c) w[c] = (c0 + c < Cout) ? Wl[c * K + k] : make_float2(0.f, 0.f);
+          MGB_UNROLL
+          for (int c = 0; c < CO; ++c) { cfmacl(acc0[sIdx], w[c], g0[c]); cfmacl(acc1[sIdx], w[c], g1[c]); }
+        }
+      }
+    }
+    MGB_UNROLL
+    for (int sIdx = 0; sIdx < 12; ++sIdx) {
+      const int k = lane + 32 * sIdx;
+      if (sIdx < nslot && k < K) {
+        sDcat[offA[un.l] + un.m0 * K + k] = acc0[sIdx];
+        if (un.nm > 1) sDcat[offA[un.l] + (un.m0 + 1) * K + k] = acc1[sIdx];
+      }
     }
   }
 }
 
-template <int NLM2>
-__global__ void __launch_bounds__(kAtomThreads)
+// g = sum over the table entries of pair p: coef * dcat[dst + c]
+__device__ __forceinline__ float2 pair_scatter(const CgTable& t, int p, const float2* __restrict__ sDcat, int c) {
+  float2 g = make_float2(0.f, 0.f);
+  const int q0 = t.pair_start[p], q1 = t.pair_start[p + 1];
+  for (int q = q0; q < q1; ++q) {
+    const int2 e = t.pair_ent[q];
+    const float cf = __int_as_float(e.y);
+    const float2 dc = sDcat[e.x + c];
+    g.x = fmaf(cf, dc.x, g.x);
+    g.y = fmaf(cf, dc.y, g.y);
+  }
+  return g;
+}
+
+template <int NLM2, int CO>
+__global__ void __launch_bounds__(kAtomBwdThreads, 2)
 k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ P, const float* __restrict__ pos,
            const int* __restrict__ n_atoms, const float* __restrict__ A_in, const float* __restrict__ E,
            const float* __restrict__ dA_out, float* __restrict__ dA_in, float* __restrict__ dE, int accumulate_dE) {
@@ -347,11 +403,11 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   float2* sDcat = smem;                         // [totA]
   float2* sdOut = sDcat + L.totA;               // [25][Cout]
   float2* sY = sdOut + kM * Cout;               // [JC][25]
-  float2* sE = sY + kJChunk * kM;               // [JC][5][C]
-  float2* sAj = sE + kJChunk * kNL * C;         // [JC][NLM2][C]
-  float2* sU = sAj + kJChunk * NLM2 * C;        // [JC][25][C]   E * Y
-  float2* sdE = sU + kJChunk * kM * C;          // [JC][5][C]
-  float2* sAi = sdE + kJChunk * kNL * C;        // [NLM2][C]
+  float2* sE = sY + kJChunkBwd * kM;            // [JC][5][C]
+  float2* sAj = sE + kJChunkBwd * kNL * C;      // [JC][NLM2][C]
+  float2* sU = sAj + kJChunkBwd * NLM2 * C;     // [JC][25][C]   E * Y
+  float2* sdE = sU + kJChunkBwd * kM * C;       // [JC][5][C]
+  float2* sAi = sdE + kJChunkBwd * kNL * C;     // [NLM2][C]
   const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
   const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
   float2* dE_i = reinterpret_cast<float2*>(dE) + ((long long)b * N + i) * N * kNL * C;
@@ -363,100 +419,88 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int idx = threadIdx.x; idx < kM * Cout; idx += blockDim.x) sdOut[idx] = src[idx];
   }
   __syncthreads();
-  mix_rows_bwd(d.units_hidden, d.n_units_hidden, L.catA, L.offA, L.offWA, Cout, reinterpret_cast<const float2*>(P + L.p_atomW),
-               sdOut, sDcat);
+  mix_rows_bwd<CO>(d.units_hidden, d.n_units_hidden, L.catA, L.offA, L.offWA, Cout, reinterpret_cast<const float2*>(P + L.p_atomW),
+                   sdOut, sDcat);
   __syncthreads();
 
   const bool owner = (int)threadIdx.x < kM * C;
   const int x = owner ? threadIdx.x / C : 0, c = owner ? threadIdx.x % C : 0;
   const int l1 = ell_of_lm(x);
   const bool col_owner = owner && x < NLM2;
-  float2 dTrow[NLM2];   // dT[x][y], y < NLM2
-  float2 dTcol[kM];     // dT[y][x], y < 25   (col owners only)
-  if (owner) {
-    const CgTable& t = L.ag;
-    MGB_UNROLL
-    for (int y = 0; y < NLM2; ++y) {
-      float2 g = make_float2(0.f, 0.f);
-      for (int q = t.pair_start[x * NLM2 + y]; q < t.pair_start[x * NLM2 + y + 1]; ++q) {
-        const int oo = t.pair_out[q], lo = t.out_l[oo];
-        const float2 dc = sDcat[L.offA[lo] + t.out_m[oo] * L.catA[lo] + t.out_block[oo] * C + c];
-        g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
-      }
-      dTrow[y] = g;
+  // ---- (B) row pass
+  {
+    float2 dTrow[NLM2];   // dT[x][y], y < NLM2
+    if (owner) {
+      MGB_UNROLL
+      for (int y = 0; y < NLM2; ++y) dTrow[y] = pair_scatter(L.ag, x * NLM2 + y, sDcat, c);
     }
-    MGB_UNROLL
-    for (int y = 0; y < kM; ++y) {
-      float2 g = make_float2(0.f, 0.f);
-      if (col_owner) {
-        for (int q = t.pair_start[y * NLM2 + x]; q < t.pair_start[y * NLM2 + x + 1]; ++q) {
-          const int oo = t.pair_out[q], lo = t.out_l[oo];
-          const float2 dc = sDcat[L.offA[lo] + t.out_m[oo] * L.catA[lo] + t.out_block[oo] * C + c];
-          g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
+    for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
+      const int nj = min(kJChunkBwd, n - j0);
+      __syncthreads();
+      stage_neighbours<NLM2>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
+      for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) sdE[idx] = make_float2(0.f, 0.f);
+      __syncthreads();
+      if (owner) {
+        for (int jj = 0; jj < nj; ++jj) {
+          // dE_ij[l1, c] += conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
+          float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
+          const float2* a = sAj + jj * NLM2 * C + c;
+          MGB_UNROLL
+          for (int y = 0; y < NLM2; ++y) {
+            if (y & 1) cfmacl(w1, a[y * C], dTrow[y]); else cfmacl(w0, a[y * C], dTrow[y]);
+          }
+          w0.x += w1.x; w0.y += w1.y;
+          float2 de = make_float2(0.f, 0.f);
+          cfmacl(de, sY[jj * kM + x], w0);
+          smem_add2(sdE + (jj * kNL + l1) * C + c, de);
         }
       }
-      dTcol[y] = g;
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) {
+        float2 v = sdE[idx];
+        float2* dst = dE_i + (long long)j0 * kNL * C + idx;
+        if (accumulate_dE) { v.x += dst->x; v.y += dst->y; }
+        *dst = v;
+      }
     }
-    // own-atom terms: pass-through block and CG square
+  }
+  // ---- (C) column pass + own-atom terms
+  {
+    float2 dTcol[kM];     // dT[y][x], y < 25   (threads x < NLM2)
     if (col_owner) {
+      MGB_UNROLL
+      for (int y = 0; y < kM; ++y) dTcol[y] = pair_scatter(L.ag, y * NLM2 + x, sDcat, c);
+      // own atom: pass-through block and CG square
       const int base = L.offA[l1] + (x - l1 * l1) * L.catA[l1];
       float2 dai = sDcat[base + L.in_block[l1] * C + c];
-      const CgTable& ts = L.sq;
       for (int y = 0; y < NLM2; ++y) {
-        float2 g = make_float2(0.f, 0.f);
-        for (int q = ts.pair_start[x * NLM2 + y]; q < ts.pair_start[x * NLM2 + y + 1]; ++q) {
-          const int oo = ts.pair_out[q], lo = ts.out_l[oo];
-          const float2 dc = sDcat[L.offA[lo] + ts.out_m[oo] * L.catA[lo] + (L.sq_block[lo] + ts.out_block[oo]) * C + c];
-          g.x = fmaf(ts.pair_coef[q], dc.x, g.x); g.y = fmaf(ts.pair_coef[q], dc.y, g.y);
-        }
-        for (int q = ts.pair_start[y * NLM2 + x]; q < ts.pair_start[y * NLM2 + x + 1]; ++q) {
-          const int oo = ts.pair_out[q], lo = ts.out_l[oo];
-          const float2 dc = sDcat[L.offA[lo] + ts.out_m[oo] * L.catA[lo] + (L.sq_block[lo] + ts.out_block[oo]) * C + c];
-          g.x = fmaf(ts.pair_coef[q], dc.x, g.x); g.y = fmaf(ts.pair_coef[q], dc.y, g.y);
-        }
-        cfmacl(dai, sAi[y * C + c], g);
+        const float2 g1 = pair_scatter(L.sq, x * NLM2 + y, sDcat, c), g2 = pair_scatter(L.sq, y * NLM2 + x, sDcat, c);
+        cfmacl(dai, sAi[y * C + c], make_float2(g1.x + g2.x, g1.y + g2.y));
       }
       atomic_add2(dAb + (long long)i * NLM2 * C + x * C + c, dai);
     }
-  }
-  // neighbour loop
-  for (int j0 = 0; j0 < n; j0 += kJChunk) {
-    const int nj = min(kJChunk, n - j0);
-    __syncthreads();
-    stage_neighbours<NLM2>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
-    for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) sdE[idx] = make_float2(0.f, 0.f);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nj * kM * C; idx += blockDim.x) {
-      const int jj = idx / (kM * C), r = idx % (kM * C), lm = r / C, cc = r % C;
-      sU[idx] = cmul(sE[(jj * kNL + ell_of_lm(lm)) * C + cc], sY[jj * kM + lm]);
-    }
-    __syncthreads();
-    if (owner) {
-      for (int jj = 0; jj < nj; ++jj) {
-        // row part: dE_ij[l1, c] += conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
-        float2 w = make_float2(0.f, 0.f);
-        const float2* a = sAj + jj * NLM2 * C + c;
-        MGB_UNROLL
-        for (int y = 0; y < NLM2; ++y) cfmacl(w, a[y * C], dTrow[y]);
-        float2 de = make_float2(0.f, 0.f);
-        cfmacl(de, sY[jj * kM + x], w);
-        smem_add2(sdE + (jj * kNL + l1) * C + c, de);
-        // column part: dA_j[x, c] += sum_y conj(E_ij[l(y), c] Y[y]) dT[y][x]
-        if (col_owner) {
-          float2 v = make_float2(0.f, 0.f);
+    for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
+      const int nj = min(kJChunkBwd, n - j0);
+      __syncthreads();
+      stage_neighbours<0>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nj * kM * C; idx += blockDim.x) {
+        const int jj = idx / (kM * C), r = idx % (kM * C), lm = r / C, cc = r % C;
+        sU[idx] = cmul(sE[(jj * kNL + ell_of_lm(lm)) * C + cc], sY[jj * kM + lm]);
+      }
+      __syncthreads();
+      if (col_owner) {
+        for (int jj = 0; jj < nj; ++jj) {
+          // dA_j[x, c] += sum_y conj(E_ij[l(y), c] Y[y]) dT[y][x]
+          float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
           const float2* u = sU + jj * kM * C + c;
           MGB_UNROLL
-          for (int y = 0; y < kM; ++y) cfmacl(v, u[y * C], dTcol[y]);
-          atomic_add2(dAb + (long long)(j0 + jj) * NLM2 * C + x * C + c, v);
+          for (int y = 0; y < kM; ++y) {
+            if (y & 1) cfmacl(v1, u[y * C], dTcol[y]); else cfmacl(v0, u[y * C], dTcol[y]);
+          }
+          atomic_add2(dAb + (long long)(j0 + jj) * NLM2 * C + x * C + c, make_float2(v0.x + v1.x, v0.y + v1.y));
         }
       }
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) {
-      float2 v = sdE[idx];
-      float2* dst = dE_i + (long long)j0 * kNL * C + idx;
-      if (accumulate_dE) { v.x += dst->x; v.y += dst->y; }
-      *dst = v;
     }
   }
 }
@@ -467,8 +511,9 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMixDwThreads = 128;
 constexpr int kMixDwSlots = 3;   // catA_l <= 3 * 128
-constexpr int kMixDwCO = 10;
+constexpr int kMixDwAtoms = 8;   // atoms per CTA pass (their dOut rows are staged together)
 
+template <int CO>
 __global__ void __launch_bounds__(kMixDwThreads)
 k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ n_atoms, const float* __restrict__ cat,
          const float* __restrict__ dA_out, float* __restrict__ grad) {
@@ -478,34 +523,48 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   const long long rows = (long long)B * N;
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = per * blockIdx.x, r1 = (r0 + per < rows) ? r0 + per : rows;
-  MGB_DYN_SMEM(float2, sd);   // [9][Cout]
-  for (int c0 = 0; c0 < Cout; c0 += kMixDwCO) {
-    float2 acc[kMixDwSlots][kMixDwCO];
+  MGB_DYN_SMEM(float2, sd);   // [kMixDwAtoms][9][Cout]
+  __shared__ long long s_row[kMixDwAtoms];
+  __shared__ int s_cnt;
+  for (int c0 = 0; c0 < Cout; c0 += CO) {
+    float2 acc[kMixDwSlots][CO];
     MGB_UNROLL
     for (int s = 0; s < kMixDwSlots; ++s)
       MGB_UNROLL
-      for (int c = 0; c < kMixDwCO; ++c) acc[s][c] = make_float2(0.f, 0.f);
-    for (long long r = r0; r < r1; ++r) {
-      const int b = (int)(r / N), i = (int)(r % N);
-      if (i >= n_atoms[b]) continue;
+      for (int c = 0; c < CO; ++c) acc[s][c] = make_float2(0.f, 0.f);
+    for (long long rb = r0; rb < r1; rb += kMixDwAtoms) {
       __syncthreads();
-      const float2* src = reinterpret_cast<const float2*>(dA_out) + (r * kM + l * l) * Cout;
-      for (int idx = threadIdx.x; idx < nm * Cout; idx += blockDim.x) sd[idx] = src[idx];
+      if (threadIdx.x == 0) {   // compact the valid atoms of this group
+        int cnt = 0;
+        for (long long r = rb; r < r1 && r < rb + kMixDwAtoms; ++r)
+          if ((int)(r % N) < n_atoms[r / N]) s_row[cnt++] = r;
+        s_cnt = cnt;
+      }
       __syncthreads();
-      const float2* cr = reinterpret_cast<const float2*>(cat) + r * L.totA + L.offA[l];
-      for (int m = 0; m < nm; ++m) {
-        float2 xv[kMixDwSlots];
-        MGB_UNROLL
-        for (int s = 0; s < kMixDwSlots; ++s) {
-          const int k = threadIdx.x + s * kMixDwThreads;
-          xv[s] = k < K ? cr[m * K + k] : make_float2(0.f, 0.f);
-        }
-        MGB_UNROLL
-        for (int c = 0; c < kMixDwCO; ++c) {
-          if (c0 + c < Cout) {
-            const float2 g = sd[m * Cout + c0 + c];
-            MGB_UNROLL
-            for (int s = 0; s < kMixDwSlots; ++s) cfmacl(acc[s][c], xv[s], g);
+      const int cnt = s_cnt;
+      for (int idx = threadIdx.x; idx < cnt * nm * Cout; idx += blockDim.x) {
+        const int a = idx / (nm * Cout), rem = idx - a * nm * Cout;
+        sd[idx] = reinterpret_cast<const float2*>(dA_out)[(s_row[a] * kM + l * l) * Cout + rem];
+      }
+      __syncthreads();
+      for (int a = 0; a < cnt; ++a) {
+        const float2* cr = reinterpret_cast<const float2*>(cat) + s_row[a] * L.totA + L.offA[l];
+        const float2* ga = sd + a * nm * Cout + c0;
+#pragma unroll 3
+        for (int m = 0; m < nm; ++m) {
+          float2 xv[kMixDwSlots];
+          MGB_UNROLL
+          for (int s = 0; s < kMixDwSlots; ++s) {
+            const int k = threadIdx.x + s * kMixDwThreads;
+            xv[s] = k < K ? cr[m * K + k] : make_float2(0.f, 0.f);
+          }
+          MGB_UNROLL
+          for (int c = 0; c < CO; ++c) {
+            if (c0 + c < Cout) {
+              const float2 g = ga[m * Cout + c];
+              MGB_UNROLL
+              for (int s = 0; s < kMixDwSlots; ++s) cfmacl(acc[s][c], xv[s], g);
+            }
           }
         }
       }
@@ -515,7 +574,7 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
       const int k = threadIdx.x + s * kMixDwThreads;
       if (k < K) {
         MGB_UNROLL
-        for (int c = 0; c < kMixDwCO; ++c) {
+        for (int c = 0; c < CO; ++c) {
           if (c0 + c < Cout) {
             float* dst = grad + L.p_atomW + 2ll * (L.offWA[l] + (long long)(c0 + c) * K + k);
             if (acc[s][c].x != 0.f) atomicAdd(dst, acc[s][c].x);
@@ -528,178 +587,172 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Edge level backward.  Persistent CTAs over (b, i) rows; each round handles one pair per warp.  Weight cotangents
-// (edge mix, radial linears, scales/phases) are accumulated in registers and flushed once per CTA.
+// Edge level backward.  Persistent CTAs over the flat pair list; each round handles one pair per warp, then all threads
+// fold the round into the weight cotangents they own (edge mix, radial linears) held in registers; scale / phase
+// cotangents are per-lane.  Everything is flushed once per CTA.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kEdgeBwdThreads = 192;
+constexpr int kEdgeBwdThreads = 384;
 constexpr int kEdgeBwdWarps = kEdgeBwdThreads / 32;
-constexpr int kEdgeSlots = 2;        // sum_l catE[l] <= 2 * 192
-constexpr int kEdgeMaxC = 10;
-constexpr int kRadSlots = (kNL * 2 * kEdgeMaxC * kRadFeat + kEdgeBwdThreads - 1) / kEdgeBwdThreads;   // 17
+constexpr int kEdgeMaxC = 12;
+constexpr int kRadSlots = (kNL * 2 * kEdgeMaxC * kRadFeat + kEdgeBwdThreads - 1) / kEdgeBwdThreads;   // 10
 
 template <int NLIN>
 __global__ void __launch_bounds__(kEdgeBwdThreads)
 k_edge_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
-           const float* __restrict__ pos, const int* __restrict__ n_atoms, const float* __restrict__ A_in,
-           const float* __restrict__ E_prev, const float* __restrict__ dE, float* __restrict__ dE_prev,
-           float* __restrict__ dD, float* __restrict__ grad) {
+           const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
+           const float* __restrict__ A_in, const float* __restrict__ E_prev, const float* __restrict__ dE,
+           float* __restrict__ dE_prev, float* __restrict__ dD, float* __restrict__ grad) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C, C2 = 2 * C;
   constexpr int NLM = NLIN * NLIN;
   MGB_DYN_SMEM(float2, smem);
-  float2* sAi = smem;                                                  // [NLM][C]
-  const int per_warp = L.sumCatE + 16 + kNL * C;                       // catbuf + f + dpre
-  float2* wbase = sAi + NLM * C;
+  const int per_warp = edge_warp_floats2(L, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* catbuf = wbase + warp * per_warp;
+  float2* sA = smem + warp * per_warp;
+  float2* catbuf = sA + 2 * NLM * C;
   float* f = reinterpret_cast<float*>(catbuf + L.sumCatE);
   float2* dpre = catbuf + L.sumCatE + 16;
-  __shared__ int s_j[kEdgeBwdWarps];
+  const int cat_off = 2 * NLM * C;   // offset of catbuf inside a warp's region
+  __shared__ int s_act[kEdgeBwdWarps];
 
-  // slot ownership for the edge-mix weights: slot -> (l, k)
-  int sl_l[kEdgeSlots], sl_k[kEdgeSlots], sl_off[kEdgeSlots];
-  float2 we[kEdgeSlots][kEdgeMaxC], dwe[kEdgeSlots][kEdgeMaxC];
-  MGB_UNROLL
-  for (int s = 0; s < kEdgeSlots; ++s) {
-    int e = threadIdx.x + s * kEdgeBwdThreads;
-    sl_l[s] = -1; sl_k[s] = 0; sl_off[s] = 0;
-    int off = 0;
+  // edge-mix weight ownership: thread -> (l, k)
+  int sl_l = -1, sl_k = 0, sl_off = 0;
+  {
+    int e = threadIdx.x, off = 0;
     for (int l = 0; l < kNL; ++l) {
-      if (sl_l[s] < 0 && e < L.catE[l]) { sl_l[s] = l; sl_k[s] = e; sl_off[s] = off; }
-      if (sl_l[s] < 0) e -= L.catE[l];
+      if (sl_l < 0 && e < L.catE[l]) { sl_l = l; sl_k = e; sl_off = off; }
+      if (sl_l < 0) e -= L.catE[l];
       off += L.catE[l];
     }
-    MGB_UNROLL
-    for (int c = 0; c < kEdgeMaxC; ++c) {
-      dwe[s][c] = make_float2(0.f, 0.f);
-      we[s][c] = (sl_l[s] >= 0 && c < C)
-                     ? reinterpret_cast<const float2*>(P + L.p_edgeW)[L.offE[sl_l[s]] + c * L.catE[sl_l[s]] + sl_k[s]]
-                     : make_float2(0.f, 0.f);
+  }
+  float2 we[kEdgeMaxC], dwe[kEdgeMaxC];
+  MGB_UNROLL
+  for (int c = 0; c < kEdgeMaxC; ++c) {
+    dwe[c] = make_float2(0.f, 0.f);
+    we[c] = (sl_l >= 0 && c < C) ? reinterpret_cast<const float2*>(P + L.p_edgeW)[L.offE[sl_l] + c * L.catE[sl_l] + sl_k]
+                                 : make_float2(0.f, 0.f);
+  }
+  // radial-weight ownership: entry e = thread + s * blockDim -> (l, o, t); radial block offsets per entry
+  float drw[kRadSlots];
+  int rad_src[kRadSlots], rad_t[kRadSlots];
+  const int n_rad = kNL * C2 * kRadFeat;
+  MGB_UNROLL
+  for (int s = 0; s < kRadSlots; ++s) {
+    drw[s] = 0.f;
+    const int e = threadIdx.x + s * kEdgeBwdThreads;
+    rad_src[s] = -1; rad_t[s] = 0;
+    if (e < n_rad) {
+      const int l = e / (C2 * kRadFeat), r = e - l * (C2 * kRadFeat), oo = r / kRadFeat;
+      int off = 0;
+      for (int q = 0; q < l; ++q) off += L.catE[q];
+      rad_src[s] = 2 * (off + L.catE[l] - C) + oo;   // float index inside catbuf
+      rad_t[s] = r - oo * kRadFeat;
     }
   }
-  float drw[kRadSlots];
-  MGB_UNROLL
-  for (int s = 0; s < kRadSlots; ++s) drw[s] = 0.f;
   float drb = 0.f;             // thread e < 5*2C owns radial bias e
+  int drb_src = -1;
+  if ((int)threadIdx.x < kNL * C2) {
+    const int l = threadIdx.x / C2, oo = threadIdx.x - l * C2;
+    int off = 0;
+    for (int q = 0; q < l; ++q) off += L.catE[q];
+    drb_src = 2 * (off + L.catE[l] - C) + oo;
+  }
   float dsc = 0.f, dph = 0.f;  // lane t accumulates its share of scale/phase cotangents
-  const int n_rad = kNL * C2 * kRadFeat;
   const float* Wt_rad = Wt + d.wt_edge[level] + 2ll * L.totE;
+  const int total = pair_off[B];
+  int off_l[kNL];
+  {
+    int o = 0;
+    for (int l = 0; l < kNL; ++l) { off_l[l] = o; o += L.catE[l]; }
+  }
 
-  for (int item = blockIdx.x; item < B * N; item += gridDim.x) {
-    const int b = item / N, i = item % N;
-    const int n = n_atoms[b];
-    if (i >= n) continue;
-    const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM * C;
-    const float* pos_b = pos + (long long)b * N * 3;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < NLM * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM * C + idx];
-    __syncthreads();
-    for (int jg = 0; jg < n; jg += kEdgeBwdWarps) {
-      const int j = jg + warp;
-      const bool act = j < n;
-      PairGeom g = PairGeom();
-      if (act) {
-        g = pair_geom(pos_b, i, j, d.cut_rad, d.cut_width);
-        const long long pair = ((long long)b * N + i) * N + j;
-        const float2* Eprev_ij = L.has_prev ? reinterpret_cast<const float2*>(E_prev) + pair * kNL * C : nullptr;
-        edge_build_cat<NLIN>(L, P, Wt_rad, g, sAi, Ab + (long long)j * NLM * C, Eprev_ij, catbuf, f, lane);
-        const float2* dE_ij = reinterpret_cast<const float2*>(dE) + pair * kNL * C;
-        for (int idx = lane; idx < kNL * C; idx += 32) dpre[idx] = make_float2(dE_ij[idx].x * g.s, dE_ij[idx].y * g.s);
-      }
-      if (lane == 0) s_j[warp] = act ? j : -1;
-      __syncthreads();
-      // phase 2: all threads, slot ownership; in place catbuf -> dcat
-      MGB_UNROLL
-      for (int s = 0; s < kEdgeSlots; ++s) {
-        if (sl_l[s] < 0) continue;
-        for (int w = 0; w < kEdgeBwdWarps; ++w) {
-          if (s_j[w] < 0) continue;
-          float2* cb = wbase + w * per_warp;
-          const float2* dp_w = cb + L.sumCatE + 16 + sl_l[s] * C;
-          const float2 xk = cb[sl_off[s] + sl_k[s]];
-          float2 dc = make_float2(0.f, 0.f);
-          MGB_UNROLL
-          for (int c = 0; c < kEdgeMaxC; ++c) {
-            if (c < C) {
-              const float2 gq = dp_w[c];
-              cfmacl(dwe[s][c], xk, gq);
-              cfmacl(dc, we[s][c], gq);
-            }
-          }
-          cb[sl_off[s] + sl_k[s]] = dc;
-        }
-      }
-      __syncthreads();
-      // phase 3a: all threads: radial weight / bias cotangents from dR (radial part of dcat) and f
-      for (int w = 0; w < kEdgeBwdWarps; ++w) {
-        if (s_j[w] < 0) continue;
-        const float2* cb = wbase + w * per_warp;
-        const float* fw = reinterpret_cast<const float*>(cb + L.sumCatE);
-        MGB_UNROLL
-        for (int s = 0; s < kRadSlots; ++s) {
-          const int e = threadIdx.x + s * kEdgeBwdThreads;
-          if (e < n_rad) {
-            const int l = e / (C2 * kRadFeat), r = e % (C2 * kRadFeat), oo = r / kRadFeat, t = r % kRadFeat;
-            int off = 0;
-            for (int q = 0; q < l; ++q) off += L.catE[q];
-            const float dR = reinterpret_cast<const float*>(cb + off + L.catE[l] - C)[oo];
-            drw[s] = fmaf(dR, fw[t], drw[s]);
-          }
-        }
-        if ((int)threadIdx.x < kNL * C2) {
-          const int l = threadIdx.x / C2, oo = threadIdx.x % C2;
-          int off = 0;
-          for (int q = 0; q < l; ++q) off += L.catE[q];
-          drb += reinterpret_cast<const float*>(cb + off + L.catE[l] - C)[oo];
-        }
-      }
-      // phase 3b: per warp: previous-edge and dot cotangents out, scale/phase cotangents
-      if (act) {
-        const long long pair = ((long long)b * N + i) * N + j;
-        int off_l[kNL];
-        {
-          int o = 0;
-          for (int l = 0; l < kNL; ++l) { off_l[l] = o; o += L.catE[l]; }
-        }
-        if (L.has_prev) {
-          float2* dst = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C;
-          for (int idx = lane; idx < kNL * C; idx += 32) dst[idx] = catbuf[off_l[idx / C] + idx % C];
-        }
-        {
-          float2* dst = reinterpret_cast<float2*>(dD) + pair * kNL * C;
-          const int kdot = L.has_prev ? C : 0;
-          for (int idx = lane; idx < NLIN * C; idx += 32) {
-            float2 acc = make_float2(0.f, 0.f);
-            for (int l = 0; l < NLIN; ++l) { acc.x += catbuf[off_l[l] + kdot + idx].x; acc.y += catbuf[off_l[l] + kdot + idx].y; }
-            dst[idx] = acc;
-          }
-        }
-        // df[t] = sum_{l,o} W_l[o][t] dR_l[o]   (lane = t)
-        float df = 0.f;
-        for (int l = 0; l < kNL; ++l) {
-          const float* dR = reinterpret_cast<const float*>(catbuf + off_l[l] + L.catE[l] - C);
-          const float* w = Wt_rad + ((long long)l * kRadFeat + lane) * C2;
-          for (int oo = 0; oo < C2; ++oo) df = fmaf(w[oo], dR[oo], df);
-        }
-        float dval;
-        rad_feature(lane, g, P + L.p_scales, P + L.p_phases, &dval);
-        dph = fmaf(df, dval, dph);
-        dsc = fmaf(df, dval * kTwoPi * g.r, dsc);
-      }
-      __syncthreads();
+  for (int p0 = blockIdx.x * kEdgeBwdWarps; p0 < total; p0 += gridDim.x * kEdgeBwdWarps) {
+    const int p = p0 + warp;
+    const bool act = p < total;
+    PairGeom g = PairGeom();
+    long long pair = 0;
+    if (act) {
+      const PairId id = decode_pair(p, B, pair_off, n_atoms);
+      const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)id.b * N * NLM * C;
+      g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
+      pair = ((long long)id.b * N + id.i) * N + id.j;
+      const float2* Eprev_ij = L.has_prev ? reinterpret_cast<const float2*>(E_prev) + pair * kNL * C : nullptr;
+      edge_build_cat<NLIN>(L, P, Wt_rad, g, Ab + (long long)id.i * NLM * C, Ab + (long long)id.j * NLM * C, Eprev_ij, sA, catbuf, f,
+                           lane);
+      const float2* dE_ij = reinterpret_cast<const float2*>(dE) + pair * kNL * C;
+      for (int idx = lane; idx < kNL * C; idx += 32) dpre[idx] = make_float2(dE_ij[idx].x * g.s, dE_ij[idx].y * g.s);
     }
+    if (lane == 0) s_act[warp] = act ? 1 : 0;
+    __syncthreads();
+    // phase 2: all threads, (l, k) ownership; in place catbuf -> dcat
+    if (sl_l >= 0) {
+      for (int w = 0; w < kEdgeBwdWarps; ++w) {
+        if (!s_act[w]) continue;
+        float2* cb = smem + w * per_warp + cat_off;
+        const float2* dp_w = cb + L.sumCatE + 16 + sl_l * C;
+        const float2 xk = cb[sl_off + sl_k];
+        float2 dc = make_float2(0.f, 0.f);
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeMaxC; ++c) {
+          if (c < C) {
+            const float2 gq = dp_w[c];
+            cfmacl(dwe[c], xk, gq);
+            cfmacl(dc, we[c], gq);
+          }
+        }
+        cb[sl_off + sl_k] = dc;
+      }
+    }
+    __syncthreads();
+    // phase 3a: all threads: radial weight / bias cotangents from dR (radial part of dcat) and f
+    for (int w = 0; w < kEdgeBwdWarps; ++w) {
+      if (!s_act[w]) continue;
+      const float* cbf = reinterpret_cast<const float*>(smem + w * per_warp + cat_off);
+      const float* fw = cbf + 2 * L.sumCatE;
+      MGB_UNROLL
+      for (int s = 0; s < kRadSlots; ++s)
+        if (rad_src[s] >= 0) drw[s] = fmaf(cbf[rad_src[s]], fw[rad_t[s]], drw[s]);
+      if (drb_src >= 0) drb += cbf[drb_src];
+    }
+    // phase 3b: per warp: previous-edge and dot cotangents out, scale/phase cotangents
+    if (act) {
+      if (L.has_prev) {
+        float2* dst = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C;
+        for (int idx = lane; idx < kNL * C; idx += 32) dst[idx] = catbuf[off_l[idx / C] + idx % C];
+      }
+      {
+        float2* dst = reinterpret_cast<float2*>(dD) + pair * kNL * C;
+        const int kdot = L.has_prev ? C : 0;
+        for (int idx = lane; idx < NLIN * C; idx += 32) {
+          float2 acc = make_float2(0.f, 0.f);
+          for (int l = 0; l < NLIN; ++l) { acc.x += catbuf[off_l[l] + kdot + idx].x; acc.y += catbuf[off_l[l] + kdot + idx].y; }
+          dst[idx] = acc;
+        }
+      }
+      // df[t] = sum_{l,o} W_l[o][t] dR_l[o]   (lane = t)
+      float df0 = 0.f, df1 = 0.f;
+      for (int l = 0; l < kNL; ++l) {
+        const float* dR = reinterpret_cast<const float*>(catbuf + off_l[l] + L.catE[l] - C);
+        const float* w = Wt_rad + ((long long)l * kRadFeat + lane) * C2;
+#pragma unroll 4
+        for (int oo = 0; oo < C2; oo += 2) { df0 = fmaf(w[oo], dR[oo], df0); df1 = fmaf(w[oo + 1], dR[oo + 1], df1); }
+      }
+      float dval;
+      rad_feature(lane, g, P + L.p_scales, P + L.p_phases, &dval);
+      dph = fmaf(df0 + df1, dval, dph);
+      dsc = fmaf(df0 + df1, dval * kTwoPi * g.r, dsc);
+    }
+    __syncthreads();
   }
   // flush
-  MGB_UNROLL
-  for (int s = 0; s < kEdgeSlots; ++s) {
-    if (sl_l[s] < 0) continue;
+  if (sl_l >= 0) {
     MGB_UNROLL
     for (int c = 0; c < kEdgeMaxC; ++c) {
       if (c < C) {
-        float* dst = grad + L.p_edgeW + 2ll * (L.offE[sl_l[s]] + c * L.catE[sl_l[s]] + sl_k[s]);
-        if (dwe[s][c].x != 0.f) atomicAdd(dst, dwe[s][c].x);
-        if (dwe[s][c].y != 0.f) atomicAdd(dst + 1, dwe[s][c].y);
+        float* dst = grad + L.p_edgeW + 2ll * (L.offE[sl_l] + c * L.catE[sl_l] + sl_k);
+        if (dwe[c].x != 0.f) atomicAdd(dst, dwe[c].x);
+        if (dwe[c].y != 0.f) atomicAdd(dst + 1, dwe[c].y);
       }
     }
   }

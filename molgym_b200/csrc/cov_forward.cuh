@@ -19,12 +19,19 @@ struct TransposeSeg {
   int rows, cols, elem;
 };
 
-__global__ void k_prep_params(const TransposeSeg* __restrict__ segs, const float* __restrict__ P, float* __restrict__ Wt) {
-  const TransposeSeg s = segs[blockIdx.x];
-  const int n = s.rows * s.cols;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int r = idx / s.cols, c = idx % s.cols;
-    for (int e = 0; e < s.elem; ++e) Wt[s.dst + ((long long)c * s.rows + r) * s.elem + e] = P[s.src + (long long)idx * s.elem + e];
+__global__ void k_prep_params(const TransposeSeg* __restrict__ segs, int n_seg, long long total, const float* __restrict__ P,
+                              float* __restrict__ Wt) {
+  // one thread per destination float (coalesced writes); segments tile [0, total) in order of their dst offsets
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (segs[mid].dst <= idx) lo = mid; else hi = mid;
+    }
+    const TransposeSeg s = segs[lo];
+    const int local = (int)(idx - s.dst), e = local % s.elem, t = local / s.elem;
+    const int c = t / s.rows, r = t - c * s.rows;
+    Wt[idx] = P[s.src + ((long long)r * s.cols + c) * s.elem + e];
   }
 }
 
@@ -109,100 +116,168 @@ __device__ __forceinline__ float rad_feature(int t, const PairGeom& g, const flo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Edge level: E[b,i,j,l,c'] = s_ij * sum_k WE_l[c',k] catE_ijl[k],  catE = [E_prev | dot(A_i, A_j) | radial_l]
-// (cormorant CormorantEdgeLevel: DotMatrix + CatMixRepsScalar + MaskLevel).  One CTA per (b, i), one warp per j.
+// Flat list of valid (b, i, j) pairs: pair_off[b] = sum_{b' < b} n_b'^2, pair_off[B] = total.  One CTA.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kEdgeThreads = 128;
+__global__ void k_pair_offsets(int B, const int* __restrict__ n_atoms, int* __restrict__ pair_off) {
+  __shared__ int part[1024];
+  const int per = (B + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * per, hi = min(B, lo + per);
+  int sum = 0;
+  for (int b = lo; b < hi; ++b) sum += n_atoms[b] * n_atoms[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) { const int v = part[t]; part[t] = run; run += v; }
+    pair_off[B] = run;
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int b = lo; b < hi; ++b) { pair_off[b] = run; run += n_atoms[b] * n_atoms[b]; }
+}
 
-// Fills the per-warp cat buffer for one pair; returns with the warp synchronised.  catbuf: [sumCatE] complex,
-// l-major.  f: [32] radial features (written here).  Also used by the backward kernel.
+struct PairId { int b, i, j; };
+__device__ __forceinline__ PairId decode_pair(int p, int B, const int* __restrict__ pair_off, const int* __restrict__ n_atoms) {
+  int lo = 0, hi = B;   // largest b with pair_off[b] <= p
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pair_off[mid] <= p) lo = mid; else hi = mid;
+  }
+  const int r = p - pair_off[lo], n = n_atoms[lo];
+  PairId id;
+  id.b = lo; id.i = r / n; id.j = r - id.i * n;
+  return id;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Edge level: E[b,i,j,l,c'] = s_ij * sum_k WE_l[c',k] catE_ijl[k],  catE = [E_prev | dot(A_i, A_j) | radial_l]
+// (cormorant CormorantEdgeLevel: DotMatrix + CatMixRepsScalar + MaskLevel).  One warp per valid pair of the minibatch.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kEdgeThreads = 256;
+
+__host__ __device__ inline int edge_warp_floats2(const LevelDesc& L, bool backward) {
+  return 2 * L.nlm_in * L.C + L.sumCatE + 16 + (backward ? kNL * L.C : 0);
+}
+
+// Fills the per-warp cat buffer for one pair; returns with the warp synchronised.  catbuf: [sumCatE] complex, l-major.
+// f: [32] radial features (written here).  sA: [2][NLM][C] staging for A_i, A_j.  Also used by the backward kernel.
 template <int NLIN>
 __device__ __forceinline__ void edge_build_cat(const LevelDesc& L, const float* __restrict__ P, const float* __restrict__ Wt_rad,
-                                               const PairGeom& g, const float2* __restrict__ sAi,
-                                               const float2* __restrict__ Aj, const float2* __restrict__ Eprev_ij,
-                                               float2* catbuf, float* f, int lane) {
-  const int C = L.C;
+                                               const PairGeom& g, const float2* __restrict__ Ai, const float2* __restrict__ Aj,
+                                               const float2* __restrict__ Eprev_ij, float2* sA, float2* catbuf, float* f, int lane) {
+  const int C = L.C, C2 = 2 * C;
+  constexpr int NLM = NLIN * NLIN;
+  for (int idx = lane; idx < NLM * C; idx += 32) { sA[idx] = Ai[idx]; sA[NLM * C + idx] = Aj[idx]; }
   f[lane] = rad_feature(lane, g, P + L.p_scales, P + L.p_phases, nullptr);
-  __syncwarp();
-  // radial filters: R_l[o] = b_l[o] + sum_t W_l[o][t] f[t]   (Wt_rad: [l][t][2C])
-  const int C2 = 2 * C;
   int off_l[kNL];
   {
     int o = 0;
     for (int l = 0; l < kNL; ++l) { off_l[l] = o; o += L.catE[l]; }
   }
-  for (int idx = lane; idx < kNL * C2; idx += 32) {
-    const int l = idx / C2, o = idx % C2;
-    float acc = P[L.p_radb + l * C2 + o];
-    const float* w = Wt_rad + (long long)l * kRadFeat * C2 + o;
-    for (int t = 0; t < kRadFeat; ++t) acc = fmaf(w[t * C2], f[t], acc);
-    const int krad = L.catE[l] - C;  // radial block is last
-    reinterpret_cast<float*>(catbuf + off_l[l] + krad)[o] = acc;
+  if (L.has_prev) {
+    for (int idx = lane; idx < kNL * C; idx += 32) {
+      const int l = idx / C, c = idx - l * C;
+      catbuf[off_l[l] + c] = Eprev_ij[idx];
+    }
+  }
+  __syncwarp();
+  // radial filters: R_l[o] = b_l[o] + sum_t W_l[o][t] f[t]   (Wt_rad: [l][t][2C]); each lane owns <= 4 outputs
+  {
+    float acc[4];
+    const float* wp[4];
+    bool on[4];
+    MGB_UNROLL
+    for (int r = 0; r < 4; ++r) {
+      const int idx = lane + 32 * r;
+      on[r] = idx < kNL * C2;
+      const int l = on[r] ? idx / C2 : 0, o = on[r] ? idx - l * C2 : 0;
+      acc[r] = on[r] ? P[L.p_radb + l * C2 + o] : 0.f;
+      wp[r] = Wt_rad + (long long)l * kRadFeat * C2 + o;
+    }
+#pragma unroll 8
+    for (int t = 0; t < kRadFeat; ++t) {
+      const float ft = f[t];
+      MGB_UNROLL
+      for (int r = 0; r < 4; ++r)
+        if (on[r]) acc[r] = fmaf(wp[r][t * C2], ft, acc[r]);
+    }
+    MGB_UNROLL
+    for (int r = 0; r < 4; ++r) {
+      const int idx = lane + 32 * r;
+      if (on[r]) {
+        const int l = idx / C2, o = idx - l * C2;
+        reinterpret_cast<float*>(catbuf + off_l[l] + L.catE[l] - C)[o] = acc[r];   // radial block is last
+      }
+    }
   }
   // dot matrix D[l',c] = sum_m (-1)^m A_i[l',m,c] A_j[l',-m,c]
   for (int idx = lane; idx < NLIN * C; idx += 32) {
-    const int lp = idx / C, c = idx % C;
+    const int lp = idx / C, c = idx - lp * C;
     float2 acc = make_float2(0.f, 0.f);
     for (int m = -lp; m <= lp; ++m) {
-      const float2 a = sAi[lm_index(lp, m) * C + c];
-      const float2 bj = Aj[lm_index(lp, -m) * C + c];
-      float2 pr = cmul(a, bj);
+      const float2 pr = cmul(sA[lm_index(lp, m) * C + c], sA[NLM * C + lm_index(lp, -m) * C + c]);
       if (m & 1) { acc.x -= pr.x; acc.y -= pr.y; } else { acc.x += pr.x; acc.y += pr.y; }
     }
     const int kdot = L.has_prev ? C : 0;
     for (int l = 0; l < NLIN; ++l) catbuf[off_l[l] + kdot + idx] = acc;
-  }
-  if (L.has_prev) {
-    for (int idx = lane; idx < kNL * C; idx += 32) {
-      const int l = idx / C, c = idx % C;
-      catbuf[off_l[l] + c] = Eprev_ij[idx];
-    }
   }
   __syncwarp();
 }
 
 template <int NLIN>
 __global__ void __launch_bounds__(kEdgeThreads)
-k_edge_fwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ P, const float* __restrict__ Wt,
-           const float* __restrict__ pos, const int* __restrict__ n_atoms, const float* __restrict__ A_in,
-           const float* __restrict__ E_prev, float* __restrict__ E_out) {
+k_edge_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
+           const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
+           const float* __restrict__ A_in, const float* __restrict__ E_prev, float* __restrict__ E_out) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C;
-  const int b = blockIdx.x / N, i = blockIdx.x % N;
-  const int n = n_atoms[b];
-  if (i >= n) return;
   constexpr int NLM = NLIN * NLIN;
   MGB_DYN_SMEM(float2, smem);
-  float2* sAi = smem;                                  // [NLM][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float2* catbuf = sAi + NLM * C + warp * (L.sumCatE + 16);
+  float2* sA = smem + warp * edge_warp_floats2(L, false);
+  float2* catbuf = sA + 2 * NLM * C;
   float* f = reinterpret_cast<float*>(catbuf + L.sumCatE);
-  const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM * C;
-  for (int idx = threadIdx.x; idx < NLM * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM * C + idx];
-  __syncthreads();
   const float* Wt_rad = Wt + d.wt_edge[level] + 2ll * L.totE;  // radial transposes follow the edge weights
   const float2* WEt = reinterpret_cast<const float2*>(Wt + d.wt_edge[level]);
-  const float* pos_b = pos + (long long)b * N * 3;
-  for (int j = warp; j < n; j += nwarps) {
-    const PairGeom g = pair_geom(pos_b, i, j, d.cut_rad, d.cut_width);
-    const long long pair = ((long long)b * N + i) * N + j;
+  const int total = pair_off[B];
+  for (int p = blockIdx.x * nwarps + warp; p < total; p += gridDim.x * nwarps) {
+    const PairId id = decode_pair(p, B, pair_off, n_atoms);
+    const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)id.b * N * NLM * C;
+    const PairGeom g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
+    const long long pair = ((long long)id.b * N + id.i) * N + id.j;
     const float2* Eprev_ij = L.has_prev ? reinterpret_cast<const float2*>(E_prev) + pair * kNL * C : nullptr;
-    edge_build_cat<NLIN>(L, P, Wt_rad, g, sAi, Ab + (long long)j * NLM * C, Eprev_ij, catbuf, f, lane);
+    edge_build_cat<NLIN>(L, P, Wt_rad, g, Ab + (long long)id.i * NLM * C, Ab + (long long)id.j * NLM * C, Eprev_ij, sA, catbuf, f,
+                         lane);
     float2* Eo = reinterpret_cast<float2*>(E_out) + pair * kNL * C;
-    int off = 0, l = 0, nextl = C;
-    for (int idx = lane; idx < kNL * C; idx += 32) {
-      l = idx / C;
-      off = 0;
+    // mix: lane owns outputs idx = lane, lane + 32 of the 5*C
+    float2 acc[2];
+    const float2* w[2];
+    const float2* x[2];
+    int K[2], Kmax = 0;
+    MGB_UNROLL
+    for (int r = 0; r < 2; ++r) {
+      const int idx = lane + 32 * r;
+      const bool on = idx < kNL * C;
+      const int l = on ? idx / C : 0, cp = on ? idx - l * C : 0;
+      int off = 0;
       for (int q = 0; q < l; ++q) off += L.catE[q];
-      (void)nextl;
-      const int cp = idx % C;
-      const float2* w = WEt + L.offE[l] + cp;  // [k][c']
-      const float2* x = catbuf + off;
-      float2 acc = make_float2(0.f, 0.f);
-      const int K = L.catE[l];
-      for (int k = 0; k < K; ++k) cfma(acc, w[k * C], x[k]);
-      Eo[idx] = make_float2(acc.x * g.s, acc.y * g.s);
+      w[r] = WEt + L.offE[l] + cp;   // [k][c']
+      x[r] = catbuf + off;
+      K[r] = on ? L.catE[l] : 0;
+      Kmax = max(Kmax, K[r]);
+      acc[r] = make_float2(0.f, 0.f);
+    }
+#pragma unroll 4
+    for (int k = 0; k < Kmax; ++k) {
+      MGB_UNROLL
+      for (int r = 0; r < 2; ++r)
+        if (k < K[r]) cfma(acc[r], w[r][k * C], x[r][k]);
+    }
+    MGB_UNROLL
+    for (int r = 0; r < 2; ++r) {
+      const int idx = lane + 32 * r;
+      if (idx < kNL * C) Eo[idx] = make_float2(acc[r].x * g.s, acc[r].y * g.s);
     }
     __syncwarp();
   }
@@ -253,26 +328,26 @@ __device__ __forceinline__ void mix_rows(const MixUnit* __restrict__ units, int 
   }
 }
 
-// CG gather out of shared memory: cat[dest(o), c] = sum_terms coef * (T[lm1][lm2][c])   or  A[lm1][c]*A[lm2][c]
-// SQUARE=false: sT is [n_pair][C];  SQUARE=true: sT is the rep A [nlm][C] and the pair product is formed on the fly.
+// CG gather out of shared memory: cat[out_dst(o) + c] = sum_terms coef * T[a + c]   or  coef * A[a + c] * A[b + c]
+// (tables resolved on the host against this use site, see resolve_cg_table).
 template <bool SQUARE>
-__device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2* __restrict__ sT, const int* catA,
-                                          const int* offA, int block0_of_l[kNL], float2* __restrict__ sCat, float scale) {
+__device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2* __restrict__ sT, float2* __restrict__ sCat) {
   const int total = t.n_out * C;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int o = idx / C, c = idx % C;
+    const int o = idx / C, c = idx - o * C;
     float2 acc = make_float2(0.f, 0.f);
     const int t0 = t.term_start[o], t1 = t.term_start[o + 1];
+#pragma unroll 4
     for (int q = t0; q < t1; ++q) {
       const float cf = t.term_coef[q];
+      const int2 src = t.term_src[q];
       float2 v;
-      if (SQUARE) v = cmul(sT[t.term_lm1[q] * C + c], sT[t.term_lm2[q] * C + c]);
-      else v = sT[(t.term_lm1[q] * t.nlm2 + t.term_lm2[q]) * C + c];
+      if (SQUARE) v = cmul(sT[src.x + c], sT[src.y + c]);
+      else v = sT[src.x + c];
       acc.x = fmaf(cf, v.x, acc.x);
       acc.y = fmaf(cf, v.y, acc.y);
     }
-    const int l = t.out_l[o];
-    sCat[offA[l] + t.out_m[o] * catA[l] + (block0_of_l[l] + t.out_block[o]) * C + c] = make_float2(acc.x * scale, acc.y * scale);
+    sCat[t.out_dst[o] + c] = acc;
   }
 }
 
@@ -282,7 +357,7 @@ __device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2*
 //   ag = CG T ; sq = CG (A_i x A_i) ; cat_l = [ag | A_i | sq] ; A_out[l, m, c'] = sum_k W_l[c', k] cat_l[m][k]
 // One CTA per (b, i).  The cat vector is also written to HBM: the weight-gradient kernel reads it back.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kAtomThreads = 256;
+constexpr int kAtomThreads = 512;
 constexpr int kJChunk = 8;
 
 __host__ __device__ inline int atom_smem_floats(const LevelDesc& L) {
@@ -360,11 +435,8 @@ k_atom_fwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int q = 0; q < NLM2; ++q) sT[(lm1 * NLM2 + q) * C + c] = acc[q];
   }
   __syncthreads();
-  int zero_blocks[kNL] = {0, 0, 0, 0, 0};
-  int sq_blocks[kNL];
-  for (int l = 0; l < kNL; ++l) sq_blocks[l] = L.sq_block[l];
-  cg_gather<false>(L.ag, C, sT, L.catA, L.offA, zero_blocks, sCat, 1.f);
-  cg_gather<true>(L.sq, C, sAi, L.catA, L.offA, sq_blocks, sCat, 1.f);
+  cg_gather<false>(L.ag, C, sT, sCat);
+  cg_gather<true>(L.sq, C, sAi, sCat);
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) {
     const int lm = idx / C, cc = idx % C, l = ell_of_lm(lm);
     sCat[L.offA[l] + (lm - l * l) * L.catA[l] + L.in_block[l] * C + cc] = sAi[idx];

@@ -10,7 +10,8 @@
 namespace mgb {
 
 constexpr int kRowTile = 8;
-constexpr int kHeadThreads = 128;
+constexpr int kHeadThreads = 128;     // row-MLP kernels
+constexpr int kPolicyThreads = 256;   // per-canvas policy kernels
 constexpr float kF32Eps = 1.1920928955078125e-07f;
 constexpr float kLogSqrt2Pi = 0.9189385332046727f;
 constexpr float kLog4Pi = 2.5310242469692907f;
@@ -60,6 +61,7 @@ k_rows_mlp_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, cons
     MGB_UNROLL
     for (int q = 0; q < kRowTile; ++q) acc[q] = bias;
     const float* w = Wt + M.W0t + o;
+#pragma unroll 8
     for (int k = 0; k < K; ++k) {
       const float wk = w[(long long)k * Wd];
       MGB_UNROLL
@@ -79,6 +81,7 @@ k_rows_mlp_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, cons
     MGB_UNROLL
     for (int q = 0; q < kRowTile; ++q) acc[q] = bias;
     const float* w = Wt + M.W1t + o;
+#pragma unroll 8
     for (int k = 0; k < Wd; ++k) {
       const float wk = w[(long long)k * No];
       MGB_UNROLL
@@ -132,6 +135,7 @@ k_rows_mlp_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, cons
     for (int q = 0; q < kRowTile; ++q) acc[q] = 0.f;
     // trans: dH1[r][h] = relu'(H1) * sum_o W1[o][h] dY[r][o]
     const float* w = P + d.trans.W1 + h;
+#pragma unroll 8
     for (int o = 0; o < Wd; ++o) {
       const float wo = w[(long long)o * Wd];
       MGB_UNROLL
@@ -159,6 +163,7 @@ k_rows_mlp_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, cons
     for (int q = 0; q < kRowTile; ++q) acc[q] = 0.f;
     const float* w0 = P + d.focus.W0 + k;
     const float* w1 = P + d.trans.W0 + k;
+#pragma unroll 4
     for (int h = 0; h < Wd; ++h) {
       const float a = w0[(long long)h * K], bq = w1[(long long)h * K];
       MGB_UNROLL
@@ -172,7 +177,8 @@ k_rows_mlp_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, cons
 
 // ------------------------------------------------------------------------------------------------------------
 // Grouped weight gradient: for each problem p, dW[o][k] += sum_rows dY[r][o] X[r][k], db[o] += sum_rows dY[r][o].
-// grid = (chunks, problems); a CTA walks `rows_per_cta` rows, threads over k, register tile of 16 outputs.
+// grid = (row chunks, work items); a work item is (problem, tile of 32 outputs); threads over k (k == K is the bias
+// column), 32 accumulators in registers, dY tile staged in shared memory, X rows streamed coalesced from HBM.
 // ------------------------------------------------------------------------------------------------------------
 struct DwProblem {
   const float* X;
@@ -181,51 +187,52 @@ struct DwProblem {
   int K, No, mode;
   long long dW, db;  // float offsets into the gradient buffer
 };
-constexpr int kDwThreads = 128;
-constexpr int kDwTileO = 16;
-constexpr int kDwRowChunk = 16;
+struct DwWork { int prob, o0; };
+constexpr int kDwThreads = 256;
+constexpr int kDwTileO = 32;
+constexpr int kDwRowChunk = 32;
 
 __global__ void __launch_bounds__(kDwThreads)
-k_dw_grouped(const DwProblem* __restrict__ probs, const int* __restrict__ n_atoms, int N, float* __restrict__ grad) {
-  const DwProblem pr = probs[blockIdx.y];
+k_dw_grouped(const DwProblem* __restrict__ probs, const DwWork* __restrict__ work, const int* __restrict__ n_atoms, int N,
+             float* __restrict__ grad) {
+  const DwWork wk = work[blockIdx.y];
+  const DwProblem pr = probs[wk.prob];
   const long long per = (pr.rows + gridDim.x - 1) / gridDim.x;
   const long long r_begin = per * blockIdx.x, r_end = (r_begin + per < pr.rows) ? r_begin + per : pr.rows;
   if (r_begin >= r_end) return;
-  MGB_DYN_SMEM(float, sdy);  // [kDwRowChunk][No]
+  __shared__ float sdy[kDwRowChunk][kDwTileO];
   __shared__ int s_on[kDwRowChunk];
-  const int K = pr.K, No = pr.No;
-  for (int o0 = 0; o0 < No; o0 += kDwTileO) {
-    for (int k0 = 0; k0 < K + 1; k0 += blockDim.x) {  // k == K is the bias column
-      const int k = k0 + threadIdx.x;
-      float acc[kDwTileO];
-      MGB_UNROLL
-      for (int q = 0; q < kDwTileO; ++q) acc[q] = 0.f;
-      for (long long rc = r_begin; rc < r_end; rc += kDwRowChunk) {
-        const int nr = (int)((r_end - rc) < kDwRowChunk ? (r_end - rc) : kDwRowChunk);
-        __syncthreads();
-        if ((int)threadIdx.x < nr) s_on[threadIdx.x] = row_on(pr.mode, n_atoms, N, rc + threadIdx.x) ? 1 : 0;
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < nr * kDwTileO; idx += blockDim.x) {
-          const int q = idx / kDwTileO, o = o0 + idx % kDwTileO;
-          sdy[idx] = (s_on[q] && o < No) ? pr.dY[(rc + q) * No + o] : 0.f;
-        }
-        __syncthreads();
-        if (k <= K) {
-          for (int q = 0; q < nr; ++q) {
-            if (!s_on[q]) continue;
-            const float x = k < K ? pr.X[(rc + q) * K + k] : 1.f;
-            MGB_UNROLL
-            for (int o = 0; o < kDwTileO; ++o) acc[o] = fmaf(sdy[q * kDwTileO + o], x, acc[o]);
-          }
+  const int K = pr.K, No = pr.No, o0 = wk.o0;
+  for (int k0 = 0; k0 < K + 1; k0 += blockDim.x) {
+    const int k = k0 + threadIdx.x;
+    float acc[kDwTileO];
+    MGB_UNROLL
+    for (int q = 0; q < kDwTileO; ++q) acc[q] = 0.f;
+    for (long long rc = r_begin; rc < r_end; rc += kDwRowChunk) {
+      const int nr = (int)((r_end - rc) < kDwRowChunk ? (r_end - rc) : kDwRowChunk);
+      __syncthreads();
+      if ((int)threadIdx.x < nr) s_on[threadIdx.x] = row_on(pr.mode, n_atoms, N, rc + threadIdx.x) ? 1 : 0;
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nr * kDwTileO; idx += blockDim.x) {
+        const int q = idx / kDwTileO, o = o0 + idx % kDwTileO;
+        sdy[q][idx % kDwTileO] = (s_on[q] && o < No) ? pr.dY[(rc + q) * No + o] : 0.f;
+      }
+      __syncthreads();
+      if (k <= K) {
+#pragma unroll 4
+        for (int q = 0; q < nr; ++q) {
+          const float x = !s_on[q] ? 0.f : (k < K ? pr.X[(rc + q) * K + k] : 1.f);
+          MGB_UNROLL
+          for (int o = 0; o < kDwTileO; ++o) acc[o] = fmaf(sdy[q][o], x, acc[o]);
         }
       }
-      if (k <= K) {
-        MGB_UNROLL
-        for (int o = 0; o < kDwTileO; ++o) {
-          if (o0 + o < No && acc[o] != 0.f) {
-            if (k < K) atomicAdd(grad + pr.dW + (long long)(o0 + o) * K + k, acc[o]);
-            else atomicAdd(grad + pr.db + o0 + o, acc[o]);
-          }
+    }
+    if (k <= K) {
+      MGB_UNROLL
+      for (int o = 0; o < kDwTileO; ++o) {
+        if (o0 + o < No && acc[o] != 0.f) {
+          if (k < K) atomicAdd(grad + pr.dW + (long long)(o0 + o) * K + k, acc[o]);
+          else atomicAdd(grad + pr.db + o0 + o, acc[o]);
         }
       }
     }
@@ -330,13 +337,30 @@ __device__ inline void categorical_bwd(const float* p, const float* logp, const 
   }
 }
 
-// y[o] = b[o] + sum_k Wt[k][o] x[k]  for o < n_out (threads over o); optional relu.  x in shared memory.
-__device__ __forceinline__ void gemv_t(const float* __restrict__ Wt, const float* __restrict__ bias, const float* x, int K,
-                                       int n_out, bool relu, float* y) {
-  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-    float acc = bias[o];
-    for (int k = 0; k < K; ++k) acc = fmaf(Wt[(long long)k * n_out + o], x[k], acc);
-    y[o] = relu ? fmaxf(acc, 0.f) : acc;
+// y[o] = b[o] + sum_k W[o][k] x[k]  (reference layout [n_out][K]); a warp owns 4 outputs at a time, lanes stride k
+// (coalesced), shuffle reduction.  x in shared memory.  All threads of the block must call.
+__device__ __forceinline__ void gemv_rows(const float* __restrict__ W, const float* __restrict__ bias, const float* x, int K,
+                                          int n_out, bool relu, float* y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int o0 = warp * 4; o0 < n_out; o0 += nwarps * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = W + (long long)o0 * K;
+    const int no = min(4, n_out - o0);
+#pragma unroll 2
+    for (int k = lane; k < K; k += 32) {
+      const float xk = x[k];
+      MGB_UNROLL
+      for (int q = 0; q < 4; ++q)
+        if (q < no) acc[q] = fmaf(w[(long long)q * K + k], xk, acc[q]);
+    }
+    MGB_UNROLL
+    for (int q = 0; q < 4; ++q) {
+      const float v = warp_sum(acc[q]);
+      if (lane == 0 && q < no) {
+        const float r = v + bias[o0 + q];
+        y[o0 + q] = relu ? fmaxf(r, 0.f) : r;
+      }
+    }
   }
 }
 
@@ -357,6 +381,18 @@ __device__ __forceinline__ float2 sph_sum(const float2* a, const float2* y) {
   for (int q = 0; q < kM; ++q) cfma(s, a[q], y[q]);
   return s;
 }
+// same with the Lebedev table layout [25][n_grid] (lanes over grid points read coalesced)
+__device__ __forceinline__ float2 sph_sum_grid(const float2* a, const float2* __restrict__ y, int stride) {
+  float2 yv[kM];
+  MGB_UNROLL
+  for (int q = 0; q < kM; ++q) yv[q] = y[(long long)q * stride];
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+  MGB_UNROLL
+  for (int q = 0; q < kM; ++q) {
+    if (q & 1) cfma(s1, a[q], yv[q]); else cfma(s0, a[q], yv[q]);
+  }
+  return make_float2(s0.x + s1.x, s0.y + s1.y);
+}
 
 // Mixer cat vector (covariant/modules.py:180-190): ag = d * ecov ; sq = CG(ag x ag) ; cat_l = [ag | sq | ecov]
 __device__ __forceinline__ void mixer_build_cat(const CovDesc& d, const float2* ecov, float dist, float2* scratch_ag, float2* cat) {
@@ -371,8 +407,7 @@ __device__ __forceinline__ void mixer_build_cat(const CovDesc& d, const float2* 
     cat[base + d.inM_block[l] * CPE + c] = e;
   }
   __syncthreads();
-  int sqb[kNL] = {1, 1, 1, 1, 1};
-  cg_gather<true>(d.mix_sq, CPE, scratch_ag, d.catM, d.offM, sqb, cat, 1.f);
+  cg_gather<true>(d.mix_sq, CPE, scratch_ag, cat);
   __syncthreads();
 }
 
@@ -381,7 +416,8 @@ __device__ inline void policy_forward(const CovDesc& d, const float* __restrict_
                                       const int* __restrict__ n_atoms, const float* __restrict__ bags,
                                       const float* __restrict__ actions, const float* __restrict__ A_last,
                                       const float* __restrict__ inv, const float* __restrict__ flogit,
-                                      const float* __restrict__ trans, PolicySmem& s, PolicyScalars& ps) {
+                                      const float* __restrict__ trans, PolicySmem& s, PolicyScalars& ps,
+                                      const float2* __restrict__ lse_saved) {
   const int N = d.N, Z = d.Z, CPE = d.CPE, Wd = d.Wd, G = d.G, tau = d.Cout;
   const int n = n_atoms[b];
   const float* act = actions + (long long)b * 6;
@@ -414,16 +450,16 @@ __device__ inline void policy_forward(const CovDesc& d, const float* __restrict_
     s.misc[0] = ps.ent_f; s.misc[1] = ps.aux_f.mx; s.misc[2] = ps.aux_f.s1; s.misc[3] = ps.aux_f.s2;
   }
   // --- element (agent.py:243-259)
-  gemv_t(Wt + d.element.W0t, P + d.element.b0, s.finv, d.lat, Wd, true, s.he);
+  gemv_rows(P + d.element.W0, P + d.element.b0, s.finv, d.lat, Wd, true, s.he);
   atomic_scalars_row(s.ecov, CPE, CPE, s.einv, threadIdx.x, blockDim.x);
   __syncthreads();
-  gemv_t(Wt + d.element.W1t, P + d.element.b1, s.he, Wd, Z, false, s.el);
+  gemv_rows(P + d.element.W1, P + d.element.b1, s.he, Wd, Z, false, s.el);
   // --- distance (agent.py:263-276)
-  gemv_t(Wt + d.dist.W0t, P + d.dist.b0, s.einv, d.latE, Wd, true, s.hd);
+  gemv_rows(P + d.dist.W0, P + d.dist.b0, s.einv, d.latE, Wd, true, s.hd);
   // --- value (agent.py:313-316)
-  gemv_t(Wt + d.value.W0t, P + d.value.b0, s.vf, Wd, Wd, true, s.hv);
+  gemv_rows(P + d.value.W0, P + d.value.b0, s.vf, Wd, Wd, true, s.hv);
   __syncthreads();
-  gemv_t(Wt + d.dist.W1t, P + d.dist.b1, s.hd, Wd, 2 * G, false, s.yd);
+  gemv_rows(P + d.dist.W1, P + d.dist.b1, s.hd, Wd, 2 * G, false, s.yd);
   if (threadIdx.x == 0) {
     bool mask[MGB_MAX_SPECIES];
     for (int z = 0; z < Z; ++z) mask[z] = bags[(long long)b * Z + z] > 0.f;
@@ -461,7 +497,7 @@ __device__ inline void policy_forward(const CovDesc& d, const float* __restrict_
   }
   // --- condition on distance + spherical distribution (agent.py:279-292)
   mixer_build_cat(d, s.ecov, ps.dist, s.cond /* scratch for ag */, s.cat);
-  mix_rows<4, 3>(d.units_hidden, d.n_units_hidden, d.catM, d.offM, d.offWM, CPE,
+  mix_rows<4, 2>(d.units_hidden, d.n_units_hidden, d.catM, d.offM, d.offWM, CPE,
                  reinterpret_cast<const float2*>(P + d.p_mixW), s.cat, s.cond);
   __syncthreads();
   if (threadIdx.x < kM) {
@@ -494,18 +530,20 @@ __device__ inline void policy_forward(const CovDesc& d, const float* __restrict_
   const float so2 = ps.s_o.x * ps.s_o.x + ps.s_o.y * ps.s_o.y;
   if (d.has_beta) {
     // log Z = log 4 pi + logsumexp_g(-beta |s(x_g)|^2 + log w_g)   (spherical_dists.py:208-215)
-    float mx = -3.0e38f;
-    for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
-      const float2 sg = sph_sum(a_loc, reinterpret_cast<const float2*>(d.leb_y) + (long long)g * kM);
-      mx = fmaxf(mx, -d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g]);
+    float mx, sum;
+    if (lse_saved) {
+      mx = lse_saved[b].x;
+      sum = lse_saved[b].y;
+    } else {
+      float m_run = -3.0e38f, s_run = 0.f;   // online logsumexp over this thread's grid points
+      for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
+        const float2 sg = sph_sum_grid(a_loc, reinterpret_cast<const float2*>(d.leb_y) + g, d.n_grid);
+        const float t = -d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g];
+        if (t > m_run) { s_run = s_run * expf(m_run - t) + 1.f; m_run = t; } else { s_run += expf(t - m_run); }
+      }
+      mx = block_max(m_run, s.red);
+      sum = block_sum(s_run * expf(m_run - mx), s.red);
     }
-    mx = block_max(mx, s.red);
-    float sum = 0.f;
-    for (int g = threadIdx.x; g < d.n_grid; g += blockDim.x) {
-      const float2 sg = sph_sum(a_loc, reinterpret_cast<const float2*>(d.leb_y) + (long long)g * kM);
-      sum += expf(-d.beta * (sg.x * sg.x + sg.y * sg.y) + d.leb_logw[g] - mx);
-    }
-    sum = block_sum(sum, s.red);
     ps.lse_max = mx;
     ps.lse_sum = sum;
     ps.log_z = kLog4Pi + mx + logf(sum);
@@ -517,19 +555,20 @@ __device__ inline void policy_forward(const CovDesc& d, const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kPolicyThreads)
 k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
-             const float* __restrict__ trans, mgb_cov_outputs out) {
+             const float* __restrict__ trans, float2* __restrict__ lse_out, mgb_cov_outputs out) {
   const CovDesc& d = *dp;
   MGB_DYN_SMEM(float, sm);
   PolicySmem s = policy_smem_carve(d, sm);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     PolicyScalars ps;
     __syncthreads();
-    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps);
+    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps, nullptr);
     if (threadIdx.x == 0) {
+      lse_out[b] = make_float2(ps.lse_max, ps.lse_sum);
       out.logp[b] = ((ps.logp_f + ps.logp_e) + ps.logp_d) + ps.logp_o;
       out.ent[b] = ps.ent_f + ps.ent_e;
       out.v[b] = ps.v;

@@ -52,7 +52,7 @@ struct CovDesc {
   long long n_wt;                // floats of transposed-weight scratch
   long long wt_edge[kMaxLevels]; // float offset of transposed edge weights [l][k][c'][2] in the scratch
   int n_grid;                    // Lebedev points
-  const float* leb_y;            // [n_grid][25][2]  Y_lm(x_g), 'qm' norm, no conjugation
+  const float* leb_y;            // [25][n_grid][2]  Y_lm(x_g), 'qm' norm, no conjugation
   const float* leb_logw;         // [n_grid]
   int n_units_hidden, n_units_out;
   MixUnit units_hidden[kMaxMixUnits], units_out[kMaxMixUnits];
@@ -96,7 +96,31 @@ struct HostCgTable {
   std::vector<float> term_coef;
   std::vector<int> pair_start, pair_out;
   std::vector<float> pair_coef;
+  std::vector<int> out_dst, term_src, pair_ent;   // resolved (term_src / pair_ent hold 2 ints per term)
 };
+
+// Resolve a table against one use site: cat_l = [...blocks of C channels...] with per-l size catA[l], per-atom offset
+// offA[l] (complex units), first block of this product block0[l].
+inline void resolve_cg_table(HostCgTable& t, const int* catA, const int* offA, const int* block0, int C, bool square) {
+  t.out_dst.resize(t.n_out);
+  for (int o = 0; o < t.n_out; ++o) {
+    const int l = t.out_l[o];
+    t.out_dst[o] = offA[l] + t.out_m[o] * catA[l] + (block0[l] + t.out_block[o]) * C;
+  }
+  const size_t nt = t.term_lm1.size();
+  t.term_src.resize(2 * nt);
+  for (size_t q = 0; q < nt; ++q) {
+    t.term_src[2 * q] = square ? t.term_lm1[q] * C : (t.term_lm1[q] * t.nlm2 + t.term_lm2[q]) * C;
+    t.term_src[2 * q + 1] = square ? t.term_lm2[q] * C : 0;
+  }
+  t.pair_ent.resize(2 * nt);
+  for (size_t q = 0; q < nt; ++q) {
+    t.pair_ent[2 * q] = t.out_dst[t.pair_out[q]];
+    int bits;
+    std::memcpy(&bits, &t.pair_coef[q], 4);
+    t.pair_ent[2 * q + 1] = bits;
+  }
+}
 
 // CG product table for rep1 with ells 0..n1-1 and rep2 with ells 0..n2-1, truncated at kL, paths enumerated
 // l1 outer / l2 inner and outputs of one l concatenated in that order (cg_lib.py::cg_product).

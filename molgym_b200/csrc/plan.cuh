@@ -43,7 +43,7 @@ struct TableArena {
 };
 struct PendingTable {
   CgTable* dst;
-  size_t o_out_l, o_out_m, o_out_block, o_term_start, o_lm1, o_lm2, o_coef, o_pstart, o_pout, o_pcoef;
+  size_t o_out_l, o_out_m, o_out_block, o_term_start, o_lm1, o_lm2, o_coef, o_pstart, o_pout, o_pcoef, o_dst, o_src, o_ent;
 };
 inline PendingTable stage_table(TableArena& a, const HostCgTable& h, CgTable* dst) {
   dst->n_out = h.n_out; dst->n_pair = h.n_pair; dst->nlm2 = h.nlm2;
@@ -54,6 +54,7 @@ inline PendingTable stage_table(TableArena& a, const HostCgTable& h, CgTable* ds
   p.o_out_l = vi(h.out_l); p.o_out_m = vi(h.out_m); p.o_out_block = vi(h.out_block); p.o_term_start = vi(h.term_start);
   p.o_lm1 = vi(h.term_lm1); p.o_lm2 = vi(h.term_lm2); p.o_coef = vf(h.term_coef);
   p.o_pstart = vi(h.pair_start); p.o_pout = vi(h.pair_out); p.o_pcoef = vf(h.pair_coef);
+  p.o_dst = vi(h.out_dst); p.o_src = vi(h.term_src); p.o_ent = vi(h.pair_ent);
   return p;
 }
 inline void resolve_table(const PendingTable& p, const unsigned char* base) {
@@ -63,6 +64,8 @@ inline void resolve_table(const PendingTable& p, const unsigned char* base) {
   t->term_lm1 = (const int*)(base + p.o_lm1); t->term_lm2 = (const int*)(base + p.o_lm2);
   t->term_coef = (const float*)(base + p.o_coef); t->pair_start = (const int*)(base + p.o_pstart);
   t->pair_out = (const int*)(base + p.o_pout); t->pair_coef = (const float*)(base + p.o_pcoef);
+  t->out_dst = (const int*)(base + p.o_dst); t->term_src = (const int2*)(base + p.o_src);
+  t->pair_ent = (const int2*)(base + p.o_ent);
 }
 
 // Complex spherical harmonics on the host in double (same closed forms as sph_harm_l4), 'qm' norm, no conjugation,
@@ -109,12 +112,14 @@ inline void fill_mlp(MlpDesc& m, int in, int hidden, int out, long long& p, long
 // ------------------------------------------------------------------------------------------------------------
 struct CovWs {
   int* n_atoms;
+  int* pair_off;                  // [B+1] prefix of n_b^2 (flat list of valid pairs)
   float* Wt;                      // transposed weights scratch
   float* X;                       // [B,N,S_in]
   float* A[kMaxLevels + 1];       // A[0] [B,N,1,C,2]; A[k] [B,N,25,C_k,2]
   float* E[kMaxLevels];           // [B,N,N,5,C,2]
   float* cat[kMaxLevels];         // [B,N,totA_k,2]
   float* inv;                     // [B,N,lat]
+  float* lse;                     // [B,2] running max / sum of the log Z quadrature (saved for backward)
   float* hf, *flogit, *ht0, *trans;       // rows
   // backward
   float* finv, *he, *einv, *hd, *vf, *hv;  // per canvas activations saved by policy_bwd for the weight gradients
@@ -125,6 +130,7 @@ struct CovWs {
   float* dD;                      // [B,N,N,5C,2]
   double* loss_acc;               // [16]
   DwProblem* dw_probs;            // [16]
+  DwWork* dw_work;                // [64]
   size_t bytes;
 };
 
@@ -140,6 +146,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   const int C = d.C;
   int cmax = std::max(C, d.Cout);
   w.n_atoms = (int*)take(sizeof(int) * B);
+  w.pair_off = (int*)take(sizeof(int) * (B + 1));
   w.Wt = (float*)take(sizeof(float) * d.n_wt);
   w.X = (float*)take(sizeof(float) * BN * d.S_in);
   w.A[0] = (float*)take(sizeof(float) * BN * C * 2);
@@ -149,6 +156,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
     w.cat[k] = (float*)take(sizeof(float) * BN * d.lv[k].totA * 2);
   }
   w.inv = (float*)take(sizeof(float) * BN * d.lat);
+  w.lse = (float*)take(sizeof(float) * B * 2);
   w.hf = (float*)take(sizeof(float) * BN * d.Wd);
   w.flogit = (float*)take(sizeof(float) * BN);
   w.ht0 = (float*)take(sizeof(float) * BN * d.Wd);
@@ -176,6 +184,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.loss_acc = (double*)take(sizeof(double) * 16);
   w.dw_probs = (DwProblem*)take(sizeof(DwProblem) * 16);
+  w.dw_work = (DwWork*)take(sizeof(DwWork) * 64);
   w.bytes = off;
   return w;
 }
