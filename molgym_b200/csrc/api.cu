@@ -149,6 +149,8 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
       const int zero[kNL] = {0, 0, 0, 0, 0};
       resolve_cg_table(ag, L.catA, L.offA, zero, C, false);
       resolve_cg_table(sq, L.catA, L.offA, L.sq_block, C, true);
+      if (!finalize_cg_table(ag, kAtomThreads / C, false) || !finalize_cg_table(sq, kAtomThreads / C, true))
+        return fail(MGB_ERR_INVALID, "internal: CG pair table wider than kCgPad");
     }
     pending.push_back(stage_table(arena, ag, &L.ag));
     pending.push_back(stage_table(arena, sq, &L.sq));
@@ -167,6 +169,7 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     {
       const int one[kNL] = {1, 1, 1, 1, 1};
       resolve_cg_table(sq_full, d.catM, d.offM, one, d.CPE, true);
+      if (!finalize_cg_table(sq_full, kPolicyThreads / d.CPE, true)) return fail(MGB_ERR_INVALID, "internal: CG pair table wider than kCgPad");
     }
     pending.push_back(stage_table(arena, sq_full, &d.mix_sq));
   }

@@ -53,6 +53,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   const int cmax = std::max(d.C, d.Cout);
   if (!accumulate) MGB_CUDA_OK(cudaMemsetAsync(grad, 0, sizeof(float) * d.n_params, st));
   MGB_CUDA_OK(cudaMemsetAsync(w.dinv, 0, sizeof(float) * BN * d.lat, st));
+  MGB_CUDA_OK(cudaMemsetAsync(w.mix_stage, 0, sizeof(float) * 2 * d.totWM, st));
   MGB_CUDA_OK(cudaMemsetAsync(w.dA[K & 1], 0, sizeof(float) * BN * kM * cmax * 2, st));
   {
     PolicyBwdOut o{w.finv, w.he, w.einv, w.hd, w.vf, w.hv, w.dhe, w.dye, w.dhd, w.dyd, w.dhv, w.dyv, w.dvf, w.dflogit, w.dinv, w.dA[K & 1]};
@@ -60,8 +61,10 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int grid = std::min(B, 148 * 2);
     MGB_LAUNCH(k_policy_bwd, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
-               w.trans, d.has_beta ? reinterpret_cast<const float2*>(w.lse) : (const float2*)nullptr, g_logp, g_ent, g_v, o, grad);
+               w.trans, d.has_beta ? reinterpret_cast<const float2*>(w.lse) : (const float2*)nullptr, g_logp, g_ent, g_v, o, w.mix_stage, grad);
     MGB_LAUNCH_OK("k_policy_bwd");
+    MGB_LAUNCH(k_mixer_dw_finish, 2, 256, 0, st, plan->d_desc, w.mix_stage, grad);
+    MGB_LAUNCH_OK("k_mixer_dw_finish");
   }
   {
     const long long rows = (long long)BN;

@@ -137,7 +137,14 @@ struct CgTable {
   const int* out_dst;      // [n_out]  destination inside the cat vector
   const int2* term_src;    // [n_term] (a, b): product table -> a = (lm1*nlm2+lm2)*C ; square -> a = lm1*C, b = lm2*C
   const int2* pair_ent;    // [n_term] (destination inside the cat vector, float bits of the coefficient)
+  // flat forms for the kernels
+  const int4* flat;        // [n_term] output-major: (a, b, dst << 1 | last-term-of-output, float bits of the coefficient)
+  const int* slot_start;   // [n_slots + 1] term ranges (whole outputs) of equal work
+  int n_slots;
+  const int2* pad_pair;    // [n_pair][kCgPad] (dst, coef bits), zero-padded: transposed table with a fixed trip count
+  const int2* pad_sym;     // [n_pair][2 * kCgPad] entries of (x, y) and of (y, x)  (square tables only)
 };
+constexpr int kCgPad = 5;    // max number of l values a pair (l1 m1, l2 m2) couples to for l <= 4
 
 // One Cormorant level (edge network + atom network), everything the kernels need by value.
 struct LevelDesc {

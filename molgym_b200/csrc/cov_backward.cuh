@@ -15,6 +15,24 @@ __device__ __forceinline__ void atomic_add2(float2* p, float2 v) { atomicAdd(p, 
 #endif
 __device__ __forceinline__ void smem_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
 
+// g = sum over the (zero-padded, fixed trip count) table entries of pair p: coef * dcat[dst + c]
+template <int NPAD>
+__device__ __forceinline__ float2 pair_scatter(const int2* __restrict__ tab, int p, const float2* __restrict__ sDcat, int c) {
+  const int2* e = tab + (long long)p * NPAD;
+  int2 ent[NPAD];
+  MGB_UNROLL
+  for (int q = 0; q < NPAD; ++q) ent[q] = e[q];
+  float2 g = make_float2(0.f, 0.f);
+  MGB_UNROLL
+  for (int q = 0; q < NPAD; ++q) {
+    const float cf = __int_as_float(ent[q].y);
+    const float2 dc = sDcat[ent[q].x + c];
+    g.x = fmaf(cf, dc.x, g.x);
+    g.y = fmaf(cf, dc.y, g.y);
+  }
+  return g;
+}
+
 // cotangent of atomic_scalars_row: d a[lm][t] += ...   (a: [25][stride] complex, dinv: [(L+2)*tau*2])
 __device__ __forceinline__ float2 scalars_bwd_elem(const float2* __restrict__ a, int tau, int stride, const float* __restrict__ dinv,
                                                    int lm, int t) {
@@ -57,7 +75,7 @@ struct PolicyBwdOut {
 __device__ __forceinline__ void gemv_n(const float* __restrict__ W, const float* x, int rows, int cols, float* y) {
   for (int k = threadIdx.x; k < cols; k += blockDim.x) {
     float acc = 0.f;
-#pragma unroll 8
+#pragma unroll 16
     for (int h = 0; h < rows; ++h) acc = fmaf(W[(long long)h * cols + k], x[h], acc);
     y[k] = acc;
   }
@@ -68,7 +86,8 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
              const float* __restrict__ trans, const float2* __restrict__ lse_saved, const float* __restrict__ g_logp,
-             const float* __restrict__ g_ent, const float* __restrict__ g_v, PolicyBwdOut o, float* __restrict__ grad) {
+             const float* __restrict__ g_ent, const float* __restrict__ g_v, PolicyBwdOut o, float* __restrict__ mix_stage,
+             float* __restrict__ grad) {
   const CovDesc& d = *dp;
   MGB_DYN_SMEM(float, sm);
   PolicySmem s = policy_smem_carve(d, sm);
@@ -77,7 +96,7 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
   float* s_dh = extra;                                                // [Wd] scratch
   float* s_dx = s_dh + Wd;                                            // [max(lat, Wd)]
   float2* s_dcat = reinterpret_cast<float2*>(s_dx + (d.lat > Wd ? d.lat : Wd));   // [totM]
-  float2* s_dWM = s_dcat + d.totM;                                    // [totWM]  accumulated over canvases
+  float2* s_dWM = s_dcat + d.totM;                                    // [sum_l catM] one per (l, k): identical for every c'
   float2* s_decov = s_dWM + d.totWM;                                  // [25][CPE]
   float2* s_ag = s_decov + kM * CPE;                                  // [25][CPE]
   float2* s_da = s_ag + kM * CPE;                                     // [25]
@@ -263,7 +282,8 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
           s_dcat[d.offM[l] + m * Kc + k] = dc;
           cfmacl(dw, x, g);               // conj(cat) * g
         }
-        for (int c = 0; c < CPE; ++c) { s_dWM[d.offWM[l] + c * Kc + k].x += dw.x; s_dWM[d.offWM[l] + c * Kc + k].y += dw.y; }
+        s_dWM[d.offWM[l] / CPE + k].x += dw.x;
+        s_dWM[d.offWM[l] / CPE + k].y += dw.y;
       }
     }
     // ag = dist * ecov (recomputed)
@@ -275,19 +295,8 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
       const int x = idx / CPE, c = idx % CPE, l = ell_of_lm(x);
       const int base = d.offM[l] + (x - l * l) * d.catM[l];
       float2 dag = s_dcat[base + c];
-      const CgTable& t = d.mix_sq;
       for (int y = 0; y < kM; ++y) {
-        float2 g = make_float2(0.f, 0.f);
-        for (int q = t.pair_start[x * kM + y]; q < t.pair_start[x * kM + y + 1]; ++q) {
-          const int oo = t.pair_out[q], lo = t.out_l[oo];
-          const float2 dc = s_dcat[d.offM[lo] + t.out_m[oo] * d.catM[lo] + (1 + t.out_block[oo]) * CPE + c];
-          g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
-        }
-        for (int q = t.pair_start[y * kM + x]; q < t.pair_start[y * kM + x + 1]; ++q) {
-          const int oo = t.pair_out[q], lo = t.out_l[oo];
-          const float2 dc = s_dcat[d.offM[lo] + t.out_m[oo] * d.catM[lo] + (1 + t.out_block[oo]) * CPE + c];
-          g.x = fmaf(t.pair_coef[q], dc.x, g.x); g.y = fmaf(t.pair_coef[q], dc.y, g.y);
-        }
+        const float2 g = pair_scatter<2 * kCgPad>(d.mix_sq.pad_sym, x * kM + y, s_dcat, c);
         cfmacl(dag, s_ag[y * CPE + c], g);   // conj(ag_y) * g
       }
       float2 de = s_dcat[base + d.inM_block[l] * CPE + c];
@@ -301,12 +310,24 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < d.totWM; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < d.totWM / CPE; idx += blockDim.x) {   // compact staging, expanded by k_mixer_dw_finish
     const float2 v = s_dWM[idx];
-    if (v.x != 0.f) atomicAdd(grad + d.p_mixW + 2ll * idx, v.x);
-    if (v.y != 0.f) atomicAdd(grad + d.p_mixW + 2ll * idx + 1, v.y);
+    if (v.x != 0.f) atomicAdd(mix_stage + 2 * idx, v.x);
+    if (v.y != 0.f) atomicAdd(mix_stage + 2 * idx + 1, v.y);
   }
   if ((int)threadIdx.x < G && acc_logstd[threadIdx.x] != 0.f) atomicAdd(grad + d.p_logstd + threadIdx.x, acc_logstd[threadIdx.x]);
+}
+// grad[mixer W_l[c'][k]] += stage[l][k] for every c'
+__global__ void k_mixer_dw_finish(const CovDesc* __restrict__ dp, const float* __restrict__ stage, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < d.totWM; idx += gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < kNL && idx >= d.offWM[l + 1]) ++l;
+    const int Kc = d.catM[l], k = (idx - d.offWM[l]) % Kc;
+    const int src = d.offWM[l] / d.CPE + k;
+    grad[d.p_mixW + 2ll * idx] += stage[2 * src];
+    grad[d.p_mixW + 2ll * idx + 1] += stage[2 * src + 1];
+  }
 }
 __host__ __device__ inline int policy_bwd_extra_floats(const CovDesc& d) {
   return d.Wd + (d.lat > d.Wd ? d.lat : d.Wd) + 2 * d.totM + 2 * d.totWM + 2 * kM * d.CPE * 2 + 2 * kM + 64 + 16;
@@ -357,7 +378,7 @@ __device__ __forceinline__ void mix_rows_bwd(const MixUnit* __restrict__ units, 
         if (sIdx < nslot && k < K) {
           float2 w[CO];
           MGB_UNROLL
-          for (int c = 0; c < CO; ++c) w[c] = (c0 + c < Cout) ? Wl[c * K + k] : make_float2(0.f, 0.f);
+          for (int c = 0; c < CO; ++c) w[c] = Wl[(c0 + c < Cout ? c : 0) * K + k];   // g0/g1 are zero beyond Cout
           MGB_UNROLL
           for (int c = 0; c < CO; ++c) { cfmacl(acc0[sIdx], w[c], g0[c]); cfmacl(acc1[sIdx], w[c], g1[c]); }
         }
@@ -372,20 +393,6 @@ __device__ __forceinline__ void mix_rows_bwd(const MixUnit* __restrict__ units, 
       }
     }
   }
-}
-
-// g = sum over the table entries of pair p: coef * dcat[dst + c]
-__device__ __forceinline__ float2 pair_scatter(const CgTable& t, int p, const float2* __restrict__ sDcat, int c) {
-  float2 g = make_float2(0.f, 0.f);
-  const int q0 = t.pair_start[p], q1 = t.pair_start[p + 1];
-  for (int q = q0; q < q1; ++q) {
-    const int2 e = t.pair_ent[q];
-    const float cf = __int_as_float(e.y);
-    const float2 dc = sDcat[e.x + c];
-    g.x = fmaf(cf, dc.x, g.x);
-    g.y = fmaf(cf, dc.y, g.y);
-  }
-  return g;
 }
 
 template <int NLM2, int CO>
@@ -432,7 +439,7 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     float2 dTrow[NLM2];   // dT[x][y], y < NLM2
     if (owner) {
       MGB_UNROLL
-      for (int y = 0; y < NLM2; ++y) dTrow[y] = pair_scatter(L.ag, x * NLM2 + y, sDcat, c);
+      for (int y = 0; y < NLM2; ++y) dTrow[y] = pair_scatter<kCgPad>(L.ag.pad_pair, x * NLM2 + y, sDcat, c);
     }
     for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
       const int nj = min(kJChunkBwd, n - j0);
@@ -469,13 +476,13 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     float2 dTcol[kM];     // dT[y][x], y < 25   (threads x < NLM2)
     if (col_owner) {
       MGB_UNROLL
-      for (int y = 0; y < kM; ++y) dTcol[y] = pair_scatter(L.ag, y * NLM2 + x, sDcat, c);
+      for (int y = 0; y < kM; ++y) dTcol[y] = pair_scatter<kCgPad>(L.ag.pad_pair, y * NLM2 + x, sDcat, c);
       // own atom: pass-through block and CG square
       const int base = L.offA[l1] + (x - l1 * l1) * L.catA[l1];
       float2 dai = sDcat[base + L.in_block[l1] * C + c];
       for (int y = 0; y < NLM2; ++y) {
-        const float2 g1 = pair_scatter(L.sq, x * NLM2 + y, sDcat, c), g2 = pair_scatter(L.sq, y * NLM2 + x, sDcat, c);
-        cfmacl(dai, sAi[y * C + c], make_float2(g1.x + g2.x, g1.y + g2.y));
+        const float2 g = pair_scatter<2 * kCgPad>(L.sq.pad_sym, x * NLM2 + y, sDcat, c);   // entries of (x,y) and (y,x)
+        cfmacl(dai, sAi[y * C + c], g);
       }
       atomic_add2(dAb + (long long)i * NLM2 * C + x * C + c, dai);
     }

@@ -194,12 +194,17 @@ __device__ __forceinline__ void edge_build_cat(const LevelDesc& L, const float* 
       acc[r] = on[r] ? P[L.p_radb + l * C2 + o] : 0.f;
       wp[r] = Wt_rad + (long long)l * kRadFeat * C2 + o;
     }
-#pragma unroll 8
-    for (int t = 0; t < kRadFeat; ++t) {
-      const float ft = f[t];
+    MGB_UNROLL
+    for (int r = 0; r < 4; ++r)
+      if (!on[r]) wp[r] = Wt_rad;   // valid address, result discarded
+#pragma unroll 4
+    for (int t = 0; t < kRadFeat; t += 2) {
+      float wv[2][4];
       MGB_UNROLL
-      for (int r = 0; r < 4; ++r)
-        if (on[r]) acc[r] = fmaf(wp[r][t * C2], ft, acc[r]);
+      for (int r = 0; r < 4; ++r) { wv[0][r] = wp[r][t * C2]; wv[1][r] = wp[r][(t + 1) * C2]; }
+      const float f0 = f[t], f1 = f[t + 1];
+      MGB_UNROLL
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(wv[1][r], f1, fmaf(wv[0][r], f0, acc[r]));
     }
     MGB_UNROLL
     for (int r = 0; r < 4; ++r) {
@@ -268,11 +273,18 @@ k_edge_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* __rest
       Kmax = max(Kmax, K[r]);
       acc[r] = make_float2(0.f, 0.f);
     }
+    // rows beyond K[r] multiply a zero-padded x (catbuf rows are read clamped, weight reads stay inside the level's block)
 #pragma unroll 4
     for (int k = 0; k < Kmax; ++k) {
+      float2 wv[2], xv[2];
       MGB_UNROLL
-      for (int r = 0; r < 2; ++r)
-        if (k < K[r]) cfma(acc[r], w[r][k * C], x[r][k]);
+      for (int r = 0; r < 2; ++r) {
+        const int kk = k < K[r] ? k : 0;
+        wv[r] = w[r][kk * C];
+        xv[r] = k < K[r] ? x[r][kk] : make_float2(0.f, 0.f);
+      }
+      MGB_UNROLL
+      for (int r = 0; r < 2; ++r) cfma(acc[r], wv[r], xv[r]);
     }
     MGB_UNROLL
     for (int r = 0; r < 2; ++r) {
@@ -303,18 +315,29 @@ __device__ __forceinline__ void mix_rows(const MixUnit* __restrict__ units, int 
         MGB_UNROLL
         for (int c = 0; c < CO; ++c) acc[q][c] = make_float2(0.f, 0.f);
       const float2* Wl = W + offW[un.l] + (long long)c0 * K;
-      for (int k = lane; k < K; k += 32) {
+      const int cmax = Cout - 1 - c0;   // rows beyond Cout are clamped (loaded twice, results discarded)
+      // all CO weights of one k are loaded into distinct registers before any use, and the next k is prefetched while
+      // the current one is consumed: the loop is otherwise bound by L2 latency (the weights stream from L2 / L1)
+      float2 wn[CO];
+      int k = lane;
+      if (k < K) {
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) wn[c] = Wl[(long long)(c < cmax ? c : cmax) * K + k];
+      }
+      for (; k < K; k += 32) {
+        float2 w[CO];
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) w[c] = wn[c];
+        const int kn = (k + 32 < K) ? k + 32 : k;
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) wn[c] = Wl[(long long)(c < cmax ? c : cmax) * K + kn];
         float2 x[NM];
         MGB_UNROLL
-        for (int q = 0; q < NM; ++q) x[q] = (q < un.nm) ? cat0[q * K + k] : make_float2(0.f, 0.f);
+        for (int q = 0; q < NM; ++q) x[q] = cat0[(q < un.nm ? q : 0) * K + k];
         MGB_UNROLL
-        for (int c = 0; c < CO; ++c) {
-          if (c0 + c < Cout) {
-            const float2 w = Wl[c * K + k];
-            MGB_UNROLL
-            for (int q = 0; q < NM; ++q) cfma(acc[q][c], w, x[q]);
-          }
-        }
+        for (int c = 0; c < CO; ++c)
+          MGB_UNROLL
+          for (int q = 0; q < NM; ++q) cfma(acc[q][c], w[c], x[q]);
       }
       MGB_UNROLL
       for (int q = 0; q < NM; ++q)
@@ -332,22 +355,27 @@ __device__ __forceinline__ void mix_rows(const MixUnit* __restrict__ units, int 
 // (tables resolved on the host against this use site, see resolve_cg_table).
 template <bool SQUARE>
 __device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2* __restrict__ sT, float2* __restrict__ sCat) {
-  const int total = t.n_out * C;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int o = idx / C, c = idx - o * C;
+  // thread = (slot, channel): a slot walks a contiguous run of whole outputs of the output-major table
+  const int lanes = blockDim.x / C;
+  const int s0 = threadIdx.x / C, c = threadIdx.x - s0 * C;
+  if (s0 >= lanes) return;
+  for (int s = s0; s < t.n_slots; s += lanes) {
+    const int q0 = t.slot_start[s], q1 = t.slot_start[s + 1];
     float2 acc = make_float2(0.f, 0.f);
-    const int t0 = t.term_start[o], t1 = t.term_start[o + 1];
 #pragma unroll 4
-    for (int q = t0; q < t1; ++q) {
-      const float cf = t.term_coef[q];
-      const int2 src = t.term_src[q];
+    for (int q = q0; q < q1; ++q) {
+      const int4 e = t.flat[q];
+      const float cf = __int_as_float(e.w);
       float2 v;
-      if (SQUARE) v = cmul(sT[src.x + c], sT[src.y + c]);
-      else v = sT[src.x + c];
+      if (SQUARE) v = cmul(sT[e.x + c], sT[e.y + c]);
+      else v = sT[e.x + c];
       acc.x = fmaf(cf, v.x, acc.x);
       acc.y = fmaf(cf, v.y, acc.y);
+      if (e.z & 1) {
+        sCat[(e.z >> 1) + c] = acc;
+        acc = make_float2(0.f, 0.f);
+      }
     }
-    sCat[t.out_dst[o] + c] = acc;
   }
 }
 

@@ -346,12 +346,19 @@ __device__ __forceinline__ void gemv_rows(const float* __restrict__ W, const flo
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const float* w = W + (long long)o0 * K;
     const int no = min(4, n_out - o0);
-#pragma unroll 2
-    for (int k = lane; k < K; k += 32) {
-      const float xk = x[k];
+    // two k-steps x four outputs = eight independent loads in flight per lane (rows beyond n_out are read clamped)
+    for (int k = lane; k < K; k += 64) {
+      const int k1 = k + 32 < K ? k + 32 : k;
+      float wv[2][4];
       MGB_UNROLL
-      for (int q = 0; q < 4; ++q)
-        if (q < no) acc[q] = fmaf(w[(long long)q * K + k], xk, acc[q]);
+      for (int q = 0; q < 4; ++q) {
+        const long long row = (long long)(q < no ? q : no - 1) * K;
+        wv[0][q] = w[row + k];
+        wv[1][q] = w[row + k1];
+      }
+      const float x0 = x[k], x1 = k + 32 < K ? x[k1] : 0.f;
+      MGB_UNROLL
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(wv[1][q], x1, fmaf(wv[0][q], x0, acc[q]));
     }
     MGB_UNROLL
     for (int q = 0; q < 4; ++q) {

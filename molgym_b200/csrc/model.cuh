@@ -97,6 +97,8 @@ struct HostCgTable {
   std::vector<int> pair_start, pair_out;
   std::vector<float> pair_coef;
   std::vector<int> out_dst, term_src, pair_ent;   // resolved (term_src / pair_ent hold 2 ints per term)
+  std::vector<int> flat, slot_start, pad_pair, pad_sym;
+  int n_slots = 0;
 };
 
 // Resolve a table against one use site: cat_l = [...blocks of C channels...] with per-l size catA[l], per-atom offset
@@ -120,6 +122,56 @@ inline void resolve_cg_table(HostCgTable& t, const int* catA, const int* offA, c
     std::memcpy(&bits, &t.pair_coef[q], 4);
     t.pair_ent[2 * q + 1] = bits;
   }
+}
+
+// Flat / padded forms.  n_slots = number of (thread / C) lanes that walk the output-major table.
+inline bool finalize_cg_table(HostCgTable& t, int n_slots, bool square) {
+  const size_t nt = t.term_lm1.size();
+  t.flat.resize(4 * nt);
+  for (int o = 0; o < t.n_out; ++o)
+    for (int q = t.term_start[o]; q < t.term_start[o + 1]; ++q) {
+      int bits;
+      std::memcpy(&bits, &t.term_coef[q], 4);
+      t.flat[4 * q + 0] = t.term_src[2 * q];
+      t.flat[4 * q + 1] = t.term_src[2 * q + 1];
+      t.flat[4 * q + 2] = (t.out_dst[o] << 1) | (q == t.term_start[o + 1] - 1 ? 1 : 0);
+      t.flat[4 * q + 3] = bits;
+    }
+  t.n_slots = n_slots;
+  t.slot_start.assign(n_slots + 1, (int)nt);
+  t.slot_start[0] = 0;
+  {
+    int o = 0;
+    for (int s = 1; s < n_slots; ++s) {
+      const long long target = (long long)nt * s / n_slots;
+      while (o < t.n_out && t.term_start[o] < target) ++o;
+      t.slot_start[s] = o < t.n_out ? t.term_start[o] : (int)nt;
+    }
+  }
+  t.pad_pair.assign((size_t)t.n_pair * kCgPad * 2, 0);
+  for (int p = 0; p < t.n_pair; ++p) {
+    const int n = t.pair_start[p + 1] - t.pair_start[p];
+    if (n > kCgPad) return false;
+    for (int q = 0; q < n; ++q) {
+      t.pad_pair[((size_t)p * kCgPad + q) * 2 + 0] = t.pair_ent[2 * (t.pair_start[p] + q)];
+      t.pad_pair[((size_t)p * kCgPad + q) * 2 + 1] = t.pair_ent[2 * (t.pair_start[p] + q) + 1];
+    }
+  }
+  if (square) {
+    const int n = t.nlm2;   // square: nlm1 == nlm2
+    t.pad_sym.assign((size_t)t.n_pair * 2 * kCgPad * 2, 0);
+    for (int x = 0; x < n; ++x)
+      for (int y = 0; y < n; ++y)
+        for (int h = 0; h < 2; ++h) {
+          const int p = h == 0 ? x * n + y : y * n + x;
+          for (int q = 0; q < t.pair_start[p + 1] - t.pair_start[p]; ++q) {
+            const size_t dst = (((size_t)(x * n + y) * 2 + h) * kCgPad + q) * 2;
+            t.pad_sym[dst + 0] = t.pair_ent[2 * (t.pair_start[p] + q)];
+            t.pad_sym[dst + 1] = t.pair_ent[2 * (t.pair_start[p] + q) + 1];
+          }
+        }
+  }
+  return true;
 }
 
 // CG product table for rep1 with ells 0..n1-1 and rep2 with ells 0..n2-1, truncated at kL, paths enumerated

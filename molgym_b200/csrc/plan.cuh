@@ -43,7 +43,8 @@ struct TableArena {
 };
 struct PendingTable {
   CgTable* dst;
-  size_t o_out_l, o_out_m, o_out_block, o_term_start, o_lm1, o_lm2, o_coef, o_pstart, o_pout, o_pcoef, o_dst, o_src, o_ent;
+  size_t o_out_l, o_out_m, o_out_block, o_term_start, o_lm1, o_lm2, o_coef, o_pstart, o_pout, o_pcoef, o_dst, o_src, o_ent, o_flat, o_slot, o_pad, o_sym;
+  bool has_sym;
 };
 inline PendingTable stage_table(TableArena& a, const HostCgTable& h, CgTable* dst) {
   dst->n_out = h.n_out; dst->n_pair = h.n_pair; dst->nlm2 = h.nlm2;
@@ -55,6 +56,10 @@ inline PendingTable stage_table(TableArena& a, const HostCgTable& h, CgTable* ds
   p.o_lm1 = vi(h.term_lm1); p.o_lm2 = vi(h.term_lm2); p.o_coef = vf(h.term_coef);
   p.o_pstart = vi(h.pair_start); p.o_pout = vi(h.pair_out); p.o_pcoef = vf(h.pair_coef);
   p.o_dst = vi(h.out_dst); p.o_src = vi(h.term_src); p.o_ent = vi(h.pair_ent);
+  p.o_flat = vi(h.flat); p.o_slot = vi(h.slot_start); p.o_pad = vi(h.pad_pair);
+  p.has_sym = !h.pad_sym.empty();
+  p.o_sym = p.has_sym ? vi(h.pad_sym) : 0;
+  dst->n_slots = h.n_slots;
   return p;
 }
 inline void resolve_table(const PendingTable& p, const unsigned char* base) {
@@ -66,6 +71,9 @@ inline void resolve_table(const PendingTable& p, const unsigned char* base) {
   t->pair_out = (const int*)(base + p.o_pout); t->pair_coef = (const float*)(base + p.o_pcoef);
   t->out_dst = (const int*)(base + p.o_dst); t->term_src = (const int2*)(base + p.o_src);
   t->pair_ent = (const int2*)(base + p.o_ent);
+  t->flat = (const int4*)(base + p.o_flat); t->slot_start = (const int*)(base + p.o_slot);
+  t->pad_pair = (const int2*)(base + p.o_pad);
+  t->pad_sym = p.has_sym ? (const int2*)(base + p.o_sym) : nullptr;
 }
 
 // Complex spherical harmonics on the host in double (same closed forms as sph_harm_l4), 'qm' norm, no conjugation,
@@ -129,6 +137,7 @@ struct CovWs {
   float* dE[2];                   // ping-pong, each [B,N,N,5,C,2]
   float* dD;                      // [B,N,N,5C,2]
   double* loss_acc;               // [16]
+  float* mix_stage;               // [sum_l catM, 2] compact mixer-weight cotangent
   DwProblem* dw_probs;            // [16]
   DwWork* dw_work;                // [64]
   size_t bytes;
@@ -183,6 +192,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   for (int q = 0; q < 2; ++q) w.dE[q] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.loss_acc = (double*)take(sizeof(double) * 16);
+  w.mix_stage = (float*)take(sizeof(float) * 2 * d.totWM);
   w.dw_probs = (DwProblem*)take(sizeof(DwProblem) * 16);
   w.dw_work = (DwWork*)take(sizeof(DwWork) * 64);
   w.bytes = off;
