@@ -127,6 +127,51 @@ int mgb_ppo_loss(int32_t batch, const float* d_logp, const float* d_ent, const f
                  const double* d_adv, const double* d_ret, double clip_ratio, double vf_coef, double entropy_coef,
                  double inv_global_batch, double* d_info, float* d_g_logp, float* d_g_ent, float* d_g_v, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Internal-coordinate (SchNet) actor-critic: SchNetAC.step(observations, actions) in evaluate mode and its backward,
+ * molgym/agents/internal/agent.py:181-353 (make_atomic_tensors :112-151, surrogate_features :153-179) on
+ * schnetpack 0.3's representation.SchNet(n_atom_basis = network_width / 2).
+ *
+ * Every canvas contributes three "molecules" of up to M = canvas_size + 1 atoms: [0] the canvas itself, [1] and [2] the
+ * canvas plus the hypothetical new atom placed by the z-matrix for dihedral and -dihedral (the placement itself,
+ * zmat.py:99-133, is float64 host arithmetic and stays with the caller).  d_numbers[B,3,M] i32 atomic numbers (0 = empty
+ * slot, real atoms first), d_positions[B,3,M,3] f32, d_bags[B,Z] f32, d_actions[B,7] f32 = stop, focus, element,
+ * distance, angle, dihedral, kappa.
+ * Flat parameters, in this order (reference shapes): embedding[100,F]; per interaction t=0..2: filter.0.weight[128,25],
+ * filter.0.bias, filter.1.weight[128,128], filter.1.bias, in2f.weight[128,F], f2out.weight[F,128], f2out.bias,
+ * dense.weight[F,F], dense.bias; phi_beta, phi_focus, phi_element, phi_continuous, phi_kappa (weight0,bias0,weight1,
+ * bias1 each); critic (three layers); log_stds[3]. */
+typedef struct {
+  int32_t canvas_size;
+  int32_t num_species;
+  int32_t zs[MGB_MAX_SPECIES];
+  int32_t network_width;
+  float min_distance, max_distance;
+} mgb_int_config;
+typedef struct mgb_int_plan mgb_int_plan;
+typedef struct {
+  float* logp;           /* [B] */
+  float* ent;            /* [B] */
+  float* v;              /* [B] */
+  float* logp_terms;     /* [B,6] masked sub-action log-probabilities (may be NULL, like everything below) */
+  float* focus_probs;    /* [B,N] */
+  float* element_probs;  /* [B,Z] */
+  float* means;          /* [B,3] distance, angle, dihedral means */
+  float* kappa_logits;   /* [B,2] */
+} mgb_int_outputs;
+int mgb_int_plan_create(const mgb_int_config* cfg, mgb_int_plan** out);
+void mgb_int_plan_destroy(mgb_int_plan* plan);
+int mgb_int_param_count(const mgb_int_plan* plan);
+int mgb_int_param_layout(const mgb_int_plan* plan, int64_t* offsets, int64_t* numels, int64_t* total);
+size_t mgb_int_workspace_bytes(const mgb_int_plan* plan, int32_t batch);
+int mgb_int_forward(mgb_int_plan* plan, int32_t batch, const int32_t* d_numbers, const float* d_positions, const float* d_bags,
+                    const float* d_actions, const float* d_params, void* d_workspace, size_t workspace_bytes,
+                    const mgb_int_outputs* out, void* stream);
+int mgb_int_backward(mgb_int_plan* plan, int32_t batch, const int32_t* d_numbers, const float* d_positions, const float* d_bags,
+                     const float* d_actions, const float* d_params, void* d_workspace, size_t workspace_bytes,
+                     const float* d_g_logp, const float* d_g_ent, const float* d_g_v, float* d_grad_params, int32_t accumulate,
+                     void* stream);
+
 /* Launch accounting and per-kernel timing, for bench.py (no counterpart in the reference).
  * mgb_launch_count: kernels launched by this library in this process so far.
  * mgb_profile_kernel(substr): from now on bracket every launch whose kernel name contains `substr` with CUDA events on

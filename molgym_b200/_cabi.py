@@ -32,10 +32,20 @@ class CovOutputs(ctypes.Structure):
                                               'coefficients', 'log_z', 'covariats')]
 
 
+class IntConfig(ctypes.Structure):
+    _fields_ = [('canvas_size', c_int32), ('num_species', c_int32), ('zs', c_int32 * MGB_MAX_SPECIES), ('network_width', c_int32),
+                ('min_distance', c_float), ('max_distance', c_float)]
+
+
+class IntOutputs(ctypes.Structure):
+    _fields_ = [(name, c_void_p) for name in ('logp', 'ent', 'v', 'logp_terms', 'focus_probs', 'element_probs', 'means', 'kappa_logits')]
+
+
 EXPORTS = ('mgb_last_error', 'mgb_version', 'mgb_is_cuda_build', 'mgb_cov_plan_create', 'mgb_cov_plan_destroy',
            'mgb_cov_param_count', 'mgb_cov_param_layout', 'mgb_cov_cat_sizes', 'mgb_cov_workspace_bytes',
            'mgb_cov_forward', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_launch_count',
-           'mgb_profile_kernel', 'mgb_profile_read')
+           'mgb_profile_kernel', 'mgb_profile_read', 'mgb_int_plan_create', 'mgb_int_plan_destroy', 'mgb_int_param_count',
+           'mgb_int_param_layout', 'mgb_int_workspace_bytes', 'mgb_int_forward', 'mgb_int_backward')
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
@@ -71,6 +81,22 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     if hasattr(lib, 'mgb_pack_observations'):
         lib.mgb_pack_observations.restype = ctypes.c_int
         lib.mgb_pack_observations.argtypes = [POINTER(CovConfig), c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.mgb_int_plan_create.restype = ctypes.c_int
+    lib.mgb_int_plan_create.argtypes = [POINTER(IntConfig), POINTER(c_void_p)]
+    lib.mgb_int_plan_destroy.restype = None
+    lib.mgb_int_plan_destroy.argtypes = [c_void_p]
+    lib.mgb_int_param_count.restype = ctypes.c_int
+    lib.mgb_int_param_count.argtypes = [c_void_p]
+    lib.mgb_int_param_layout.restype = ctypes.c_int
+    lib.mgb_int_param_layout.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
+    lib.mgb_int_workspace_bytes.restype = c_size_t
+    lib.mgb_int_workspace_bytes.argtypes = [c_void_p, c_int32]
+    lib.mgb_int_forward.restype = ctypes.c_int
+    lib.mgb_int_forward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    POINTER(IntOutputs), c_void_p]
+    lib.mgb_int_backward.restype = ctypes.c_int
+    lib.mgb_int_backward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     lib.mgb_launch_count.restype = c_int64
     lib.mgb_launch_count.argtypes = []
     lib.mgb_profile_kernel.restype = ctypes.c_int
@@ -123,3 +149,29 @@ def param_names(num_cg_levels: int, maxl: int = MAXL) -> List[str]:
 def check(lib, rc: int):
     if rc != 0:
         raise RuntimeError(f'molgym_b200 C-ABI error {rc}: {lib.mgb_last_error().decode()}')
+
+
+def make_int_config(zs: Sequence[int], canvas_size: int, min_max_distance: Tuple[float, float], network_width: int) -> IntConfig:
+    cfg = IntConfig()
+    cfg.canvas_size = canvas_size
+    cfg.num_species = len(zs)
+    for i, z in enumerate(zs):
+        cfg.zs[i] = int(z)
+    cfg.network_width = network_width
+    cfg.min_distance, cfg.max_distance = float(min_max_distance[0]), float(min_max_distance[1])
+    return cfg
+
+
+def int_param_names() -> List[str]:
+    """Reference `named_parameters()` names of SchNetAC in the order of the flat buffer (include/molgym_b200.h)."""
+    names = ['embedding_fn.embedding.weight']
+    for t in range(3):
+        it = f'embedding_fn.interactions.{t}'
+        names += [f'{it}.filter_network.0.weight', f'{it}.filter_network.0.bias', f'{it}.filter_network.1.weight',
+                  f'{it}.filter_network.1.bias', f'{it}.cfconv.in2f.weight', f'{it}.cfconv.f2out.weight', f'{it}.cfconv.f2out.bias',
+                  f'{it}.dense.weight', f'{it}.dense.bias']
+    for head in ('phi_beta', 'phi_focus', 'phi_element', 'phi_continuous', 'phi_kappa'):
+        names += [f'{head}.layers.0.weight', f'{head}.layers.0.bias', f'{head}.layers.1.weight', f'{head}.layers.1.bias']
+    names += [f'critic.layers.{i}.{w}' for i in range(3) for w in ('weight', 'bias')]
+    names.append('log_stds')
+    return names

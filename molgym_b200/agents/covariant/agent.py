@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from molgym_b200 import _cabi, _lib
+from molgym_b200.agents._flat import FlatParamMixin
 from molgym_b200.agents.base import AbstractActorCritic
 from molgym_b200.agents.covariant import sampling
 from molgym_b200.agents.covariant.packing import pack_observations
@@ -30,20 +31,6 @@ def _lebedev_071():
         pts, w = lebedev_rule(71)
         _LEBEDEV = (np.ascontiguousarray(pts.T, dtype=np.float64), np.ascontiguousarray(w / (4 * np.pi), dtype=np.float64))
     return _LEBEDEV
-
-
-class _Node(nn.Module):
-    """Anonymous container used to reproduce the reference's dotted parameter names."""
-
-
-def _register(root: nn.Module, dotted: str, param: nn.Parameter):
-    parts = dotted.split('.')
-    node = root
-    for part in parts[:-1]:
-        if part not in node._modules:
-            node.add_module(part, _Node())
-        node = node._modules[part]
-    node.register_parameter(parts[-1], param)
 
 
 class _CovEvaluate(torch.autograd.Function):
@@ -73,7 +60,7 @@ class _CovEvaluate(torch.autograd.Function):
         return (None, ) * 6
 
 
-class CovariantAC(AbstractActorCritic):
+class CovariantAC(FlatParamMixin, AbstractActorCritic):
     def __init__(
         self,
         observation_space,
@@ -215,66 +202,9 @@ class CovariantAC(AbstractActorCritic):
             vals[f'{head}.layers.{layer}.weight'], vals[f'{head}.layers.{layer}.bias'] = lin.weight.data, lin.bias.data
 
     def _init_parameters(self):
-        shapes = self._param_shapes()
-        vals = self._initial_values()
-        self._flat = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
-        self._flat_grad = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
-        self._grad_scratch = None
-        # registration order follows the reference's named_parameters(): log-stds first (agent.py:131), then module tree
+        # registration order follows the reference's named_parameters(): log-stds first (agent.py:131), then the module tree
         order = ['distance_log_stds'] + [n for n in self._p_names if n != 'distance_log_stds']
-        index = {n: i for i, n in enumerate(self._p_names)}
-        self._views, self._grad_views = {}, {}
-        host = torch.zeros(self._p_total, dtype=torch.float32)
-        for name in self._p_names:
-            i = index[name]
-            o, n = self._p_offsets[i], self._p_numels[i]
-            assert int(np.prod(shapes[name])) == n, (name, shapes[name], n)
-            host[o:o + n] = vals[name].reshape(-1).to(torch.float32)
-        self._flat.copy_(host)
-        for name in order:
-            i = index[name]
-            o, n = self._p_offsets[i], self._p_numels[i]
-            p = nn.Parameter(self._flat[o:o + n].view(shapes[name]), requires_grad=True)
-            _register(self, name, p)
-            self._views[name] = p
-            self._grad_views[name] = self._flat_grad[o:o + n].view(shapes[name])
-        self._param_list = [self._views[n] for n in self._p_names]
-
-    # ------------------------------------------------------------------------------------------------------
-    # keep nn.Parameters aliased to the flat buffers (load_state_dict / optimizers keep the aliasing; .to(), pickling,
-    # or user code that rebinds .data do not)
-    # ------------------------------------------------------------------------------------------------------
-    def _params_aliased(self) -> bool:
-        base = self._flat.data_ptr()
-        first, last = self._param_list[0], self._param_list[-1]
-        return (first.data_ptr() == base + 4 * self._p_offsets[0] and last.data_ptr() == base + 4 * self._p_offsets[-1]
-                and first.device == self._flat.device)
-
-    def _realias(self):
-        with torch.no_grad():
-            for name, p, o, n in zip(self._p_names, self._param_list, self._p_offsets, self._p_numels):
-                view = self._flat[o:o + n].view(p.shape)
-                if p.data_ptr() != view.data_ptr():
-                    view.copy_(p.data.to(self._flat.device))
-                    p.data = view
-
-    def _attach_grads(self):
-        """Make every p.grad a view of the flat gradient buffer; returns True if existing values must be kept."""
-        first = self._param_list[0]
-        if first.grad is not None and first.grad.data_ptr() == self._flat_grad.data_ptr() + 4 * self._p_offsets[0]:
-            return True
-        if all(p.grad is None for p in self._param_list):
-            self._flat_grad.zero_()
-            keep = False
-        else:   # somebody assigned their own gradient tensors: fold them in
-            self._flat_grad.zero_()
-            for name, p in zip(self._p_names, self._param_list):
-                if p.grad is not None:
-                    self._grad_views[name].add_(p.grad)
-            keep = True
-        for name, p in zip(self._p_names, self._param_list):
-            p.grad = self._grad_views[name]
-        return keep
+        self._init_flat(self._param_shapes(), self._initial_values(), order)
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -286,15 +216,7 @@ class CovariantAC(AbstractActorCritic):
         self.__dict__.update(state)
         self.device = _lib.require_cuda_device(self.device)
         self._init_native()
-        named = dict(self.named_parameters())
-        self._flat = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
-        self._flat_grad = torch.zeros(self._p_total, dtype=torch.float32, device=self.device)
-        self._grad_scratch = None
-        self._views = {n: named[n] for n in self._p_names}
-        self._param_list = [self._views[n] for n in self._p_names]
-        self._grad_views = {n: self._flat_grad[o:o + k].view(self._views[n].shape)
-                            for n, o, k in zip(self._p_names, self._p_offsets, self._p_numels)}
-        self._realias()
+        self._rebuild_flat_after_unpickle()
 
     def __del__(self):
         try:
@@ -355,26 +277,13 @@ class CovariantAC(AbstractActorCritic):
         B = pos.shape[0]
         stream = torch.cuda.current_stream(dev).cuda_stream
         keep = self._attach_grads()
-        sharded = self.data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
-            and torch.distributed.get_world_size() > 1
+        target, accumulate = self._grad_target(keep)
         with torch.cuda.device(dev):
-            if sharded:
-                if self._grad_scratch is None:
-                    self._grad_scratch = torch.empty_like(self._flat_grad)
-                target, accumulate = self._grad_scratch, 0
-            else:
-                target, accumulate = self._flat_grad, 1 if keep else 0
             _cabi.check(lib, lib.mgb_cov_backward(self._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
                                                   actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(),
                                                   g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), target.data_ptr(),
                                                   accumulate, stream))
-            if sharded:
-                # the one exchange step of the path: sum of the flat gradient over ranks (NCCL over NVLink)
-                torch.distributed.all_reduce(self._grad_scratch, op=torch.distributed.ReduceOp.SUM)
-                if keep:
-                    self._flat_grad.add_(self._grad_scratch)
-                else:
-                    self._flat_grad.copy_(self._grad_scratch)
+            self._finish_grads(keep)
 
     # ------------------------------------------------------------------------------------------------------
     # the reference surface

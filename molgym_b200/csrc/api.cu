@@ -2,6 +2,7 @@
 // Compiled by nvcc for sm_100a (product) or by g++ -DMGB_CUSIM against tests/cusim/cusim.h (kernel-logic tests).
 #include "plan.cuh"
 #include "cov_backward.cuh"
+#include "internal.cuh"
 
 using namespace mgb;
 

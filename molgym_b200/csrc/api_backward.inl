@@ -2,8 +2,8 @@
 
 namespace mgb {
 struct DwProblemList {
-  DwProblem p[12];
-  DwWork w[64];
+  DwProblem p[32];
+  DwWork w[96];
   int n, nw;
 };
 __global__ void k_store_dw_problems(DwProblemList list, DwProblem* __restrict__ dst, DwWork* __restrict__ wdst) {
@@ -142,7 +142,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     for (int pi = 0; pi < q; ++pi)
       for (int o0 = 0; o0 < list.p[pi].No; o0 += kDwTileO) list.w[nw++] = DwWork{pi, o0};
     list.nw = nw;
-    MGB_LAUNCH(k_store_dw_problems, 1, 64, 0, st, list, w.dw_probs, w.dw_work);
+    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, st, list, w.dw_probs, w.dw_work);
     MGB_LAUNCH_OK("k_store_dw_problems");
     const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
     dim3 grid(chunks, nw);
@@ -218,3 +218,5 @@ int mgb_pack_observations(const mgb_cov_config* cfg, int32_t B, const int32_t* l
 }
 
 }  // extern "C"
+
+#include "api_internal.inl"

@@ -232,7 +232,7 @@ k_dw_grouped(const DwProblem* __restrict__ probs, const DwWork* __restrict__ wor
       for (int o = 0; o < kDwTileO; ++o) {
         if (o0 + o < No && acc[o] != 0.f) {
           if (k < K) atomicAdd(grad + pr.dW + (long long)(o0 + o) * K + k, acc[o]);
-          else atomicAdd(grad + pr.db + o0 + o, acc[o]);
+          else if (pr.db >= 0) atomicAdd(grad + pr.db + o0 + o, acc[o]);
         }
       }
     }

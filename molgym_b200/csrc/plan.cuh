@@ -193,8 +193,8 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.loss_acc = (double*)take(sizeof(double) * 16);
   w.mix_stage = (float*)take(sizeof(float) * 2 * d.totWM);
-  w.dw_probs = (DwProblem*)take(sizeof(DwProblem) * 16);
-  w.dw_work = (DwWork*)take(sizeof(DwWork) * 64);
+  w.dw_probs = (DwProblem*)take(sizeof(DwProblem) * 32);
+  w.dw_work = (DwWork*)take(sizeof(DwWork) * 96);
   w.bytes = off;
   return w;
 }

@@ -7,4 +7,5 @@ from oracle import refrun as _refrun
 _refrun.enable_thirdparty()
 
 from .covariant import CovariantOracle, pack_observations  # noqa: E402,F401
+from .internal import SchNetOracle  # noqa: E402,F401
 from .ppo import ppo_loss  # noqa: E402,F401

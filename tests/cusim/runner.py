@@ -133,3 +133,50 @@ def pack(zs, canvas_size, labels, xyz):
     if rc != 0:
         raise RuntimeError(L.mgb_last_error().decode())
     return pos, charges
+
+
+class CusimInt:
+    """Internal-coordinate (SchNet) agent through the emulator build."""
+
+    def __init__(self, zs, canvas_size, min_max_distance, network_width):
+        self.L = lib()
+        self.cfg = _cabi.make_int_config(zs, canvas_size, min_max_distance, network_width)
+        plan = ctypes.c_void_p()
+        _cabi.check(self.L, self.L.mgb_int_plan_create(ctypes.byref(self.cfg), ctypes.byref(plan)))
+        self.plan = plan
+        n = self.L.mgb_int_param_count(plan)
+        off = (ctypes.c_int64 * n)()
+        num = (ctypes.c_int64 * n)()
+        tot = ctypes.c_int64()
+        _cabi.check(self.L, self.L.mgb_int_param_layout(plan, off, num, ctypes.byref(tot)))
+        self.offsets, self.numels, self.total = list(off), list(num), tot.value
+        self.names = _cabi.int_param_names()
+        assert len(self.names) == n, (len(self.names), n)
+        self.N, self.Z = canvas_size, len(zs)
+
+    flatten = CusimCov.flatten
+    unflatten = CusimCov.unflatten
+
+    def forward(self, numbers, positions, bags, actions, params):
+        B = len(numbers)
+        self.B = B
+        self.inputs = [np.ascontiguousarray(numbers, np.int32), np.ascontiguousarray(positions, np.float32),
+                       np.ascontiguousarray(bags, np.float32), np.ascontiguousarray(actions, np.float32),
+                       np.ascontiguousarray(params, np.float32)]
+        nbytes = self.L.mgb_int_workspace_bytes(self.plan, B)
+        self.ws = np.zeros(nbytes // 4 + 64, dtype=np.float32)
+        self.ws_bytes = nbytes
+        o = dict(logp=np.zeros(B, np.float32), ent=np.zeros(B, np.float32), v=np.zeros(B, np.float32),
+                 logp_terms=np.zeros((B, 6), np.float32), focus_probs=np.zeros((B, self.N), np.float32),
+                 element_probs=np.zeros((B, self.Z), np.float32), means=np.zeros((B, 3), np.float32),
+                 kappa_logits=np.zeros((B, 2), np.float32))
+        outs = _cabi.IntOutputs(**{k: ptr(v) for k, v in o.items()})
+        _cabi.check(self.L, self.L.mgb_int_forward(self.plan, B, *[ptr(a) for a in self.inputs], ptr(self.ws), nbytes, ctypes.byref(outs), None))
+        return o
+
+    def backward(self, g_logp, g_ent, g_v):
+        grad = np.zeros(self.total, np.float32)
+        g = [np.ascontiguousarray(x, np.float32) for x in (g_logp, g_ent, g_v)]
+        _cabi.check(self.L, self.L.mgb_int_backward(self.plan, self.B, *[ptr(a) for a in self.inputs], ptr(self.ws), self.ws_bytes,
+                                                    ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(grad), 0, None))
+        return grad
