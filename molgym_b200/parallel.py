@@ -71,3 +71,24 @@ def global_step(agent, observations: List, actions) -> dict:
     for k in ('logp', 'ent', 'v'):
         out[k] = gather_shards(pred[k], n)
     return out
+
+
+def _gloo_selftest_worker(rank, world, port, n, out):
+    """Worker of tests/test_parallel_gloo.py (lives here so that spawned processes can import it by an unambiguous module
+    path): a stand-in "logp" of the local shard is gathered, a loss over the GLOBAL batch is differentiated, and the
+    parameter gradients are summed over ranks — the data-parallel path's host logic, on CPU with gloo."""
+    import os
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    theta = torch.tensor([0.3, -0.7], requires_grad=True)
+    x = torch.linspace(-1, 1, n)
+    lo, hi = shard_bounds(n, rank, world)
+    local = torch.sin(theta[0] * x[lo:hi]) + theta[1] * x[lo:hi]**2
+    full = gather_shards(local, n)
+    loss = (full * torch.cos(x)).mean()
+    loss.backward()
+    g = theta.grad.clone()
+    dist.all_reduce(g)
+    out[rank] = (loss.item(), g.numpy().tolist(), full.detach().numpy().tolist())
+    dist.destroy_process_group()

@@ -21,23 +21,6 @@ def test_shard_bounds_cover_everything_once():
                 assert b == c and 0 <= (b - a) - (d - c) <= 1
 
 
-def _worker(rank, world, port, n, out):
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group('gloo', rank=rank, world_size=world)
-    torch.manual_seed(0)
-    theta = torch.tensor([0.3, -0.7], requires_grad=True)
-    x = torch.linspace(-1, 1, n)
-    lo, hi = parallel.shard_bounds(n, rank, world)
-    local = torch.sin(theta[0] * x[lo:hi]) + theta[1] * x[lo:hi]**2        # stand-in for logp of the local canvases
-    full = parallel.gather_shards(local, n)
-    loss = (full * torch.cos(x)).mean()                                    # a loss over the GLOBAL batch
-    loss.backward()
-    g = theta.grad.clone()
-    dist.all_reduce(g)                                                     # the path's one exchange: sum of gradients
-    out[rank] = (loss.item(), g.numpy().tolist(), full.detach().numpy().tolist())
-    dist.destroy_process_group()
-
-
 def test_gather_shards_gloo_world2_matches_single_process():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -46,7 +29,7 @@ def test_gather_shards_gloo_world2_matches_single_process():
     n, world = 11, 2
     manager = mp.Manager()
     out = manager.dict()
-    mp.spawn(_worker, args=(world, port, n, out), nprocs=world, join=True)
+    mp.spawn(parallel._gloo_selftest_worker, args=(world, port, n, out), nprocs=world, join=True)
     theta = torch.tensor([0.3, -0.7], requires_grad=True)
     x = torch.linspace(-1, 1, n)
     full = torch.sin(theta[0] * x) + theta[1] * x**2
