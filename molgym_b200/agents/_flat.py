@@ -90,6 +90,17 @@ class FlatParamMixin:
             p.grad = self._grad_views[name]
         return keep
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """nn.Module.zero_grad walks the module tree (hundreds of tiny containers here); the parameter list is known."""
+        if set_to_none:
+            for p in self._param_list:
+                p.grad = None
+        else:
+            self._flat_grad.zero_()
+            for p in self._param_list:
+                if p.grad is not None and p.grad.data_ptr() != self._flat_grad.data_ptr():
+                    p.grad.zero_()
+
     def _is_sharded(self) -> bool:
         return bool(getattr(self, 'data_parallel', False)) and torch.distributed.is_available() and \
             torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1

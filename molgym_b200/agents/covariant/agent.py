@@ -303,23 +303,41 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             position = (0.0, 0.0, 0.0)
         return element_index, position
 
-    def parse_observations(self, observations: List) -> Dict[str, torch.Tensor]:
-        """agent.py:165-197 — device tensors for a list of observations (one packed H2D copy per tensor)."""
-        pos, charges, bags = pack_observations(observations, self.zs, self.canvas_size)
-        dev = self.device
-        data = dict(positions=torch.from_numpy(pos).to(dev, non_blocking=True), charges=torch.from_numpy(charges).to(dev, non_blocking=True),
-                    bags=torch.from_numpy(bags).to(dev, non_blocking=True))
+    def parse_observations(self, observations: List, actions: Optional[np.ndarray] = None) -> Dict[str, torch.Tensor]:
+        """agent.py:165-197 — device tensors for a list of observations.  Everything (positions, charges, bags and, when
+        given, the actions) is packed into ONE pinned staging buffer and crosses PCIe as one non-blocking copy."""
+        B, N, Z = len(observations), self.canvas_size, len(self.zs)
+        sizes = [B * N * 3 * 4, B * N * 4, B * Z * 4, B * 6 * 4 if actions is not None else 0]
+        offs = [0]
+        for sz in sizes:
+            offs.append((offs[-1] + sz + 255) // 256 * 256)
+        stage = torch.empty(max(offs[-1], 256), dtype=torch.uint8, pin_memory=True)
+        host = stage.numpy()
+        pos = host[offs[0]:offs[0] + sizes[0]].view(np.float32).reshape(B, N, 3)
+        charges = host[offs[1]:offs[1] + sizes[1]].view(np.int32).reshape(B, N)
+        bags = host[offs[2]:offs[2] + sizes[2]].view(np.float32).reshape(B, Z)
+        pack_observations(observations, self.zs, N, cfg=self._cfg, out=(pos, charges, bags))
+        if actions is not None:
+            host[offs[3]:offs[3] + sizes[3]].view(np.float32).reshape(B, 6)[...] = actions
+        dev = stage.to(self.device, non_blocking=True)
+        data = dict(positions=dev[offs[0]:offs[0] + sizes[0]].view(torch.float32).view(B, N, 3),
+                    charges=dev[offs[1]:offs[1] + sizes[1]].view(torch.int32).view(B, N),
+                    bags=dev[offs[2]:offs[2] + sizes[2]].view(torch.float32).view(B, Z))
+        if actions is not None:
+            data['actions'] = dev[offs[3]:offs[3] + sizes[3]].view(torch.float32).view(B, 6)
         return data
 
     def step(self, observations: List, actions: Optional[np.ndarray] = None) -> dict:
-        data = self.parse_observations(observations)
-        pos, charges, bags = data['positions'], data['charges'], data['bags']
         response: Dict[str, Any] = {}
         if actions is not None:
-            act = torch.as_tensor(actions, dtype=torch.float, device=self.device).contiguous()
-            assert act.shape == (len(observations), 6)
+            actions_np = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
+            assert actions_np.shape == (len(observations), 6)
+            data = self.parse_observations(observations, actions_np)
+            pos, charges, bags, act = data['positions'], data['charges'], data['bags'], data['actions']
             outs = self._evaluate(pos, charges, bags, act)
         else:
+            data = self.parse_observations(observations)
+            pos, charges, bags = data['positions'], data['charges'], data['bags']
             act, outs = sampling.rollout(self, pos, charges, bags, training=self.training)
             response['actions'] = [self.to_action_space(a, o) for a, o in zip(act.detach().cpu().numpy(), observations)]
         logp, ent, v, parts, fprobs, eprobs, gmm, coeff, log_z = outs

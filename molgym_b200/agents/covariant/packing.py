@@ -53,14 +53,19 @@ def flatten_observations(observations: Sequence, canvas_size: int, num_species: 
     return labels, xyz, bags.reshape(B, num_species)
 
 
-def pack_observations(observations: Sequence, zs: Sequence[int], canvas_size: int, cfg=None):
+def pack_observations(observations: Sequence, zs: Sequence[int], canvas_size: int, cfg=None, out=None):
     """-> positions[B,N,3] f32, charges[B,N] i32 (null-symbol items dropped, real atoms compacted to the front, zero
-    padding), bags[B,Z] f32."""
+    padding), bags[B,Z] f32.  `out` = (positions, charges, bags) arrays to fill (e.g. views of a pinned staging buffer)."""
     lib = _lib.load()
     labels, xyz, bags = flatten_observations(observations, canvas_size, len(zs))
     B = len(observations)
-    pos = np.empty((B, canvas_size, 3), dtype=np.float32)
-    charges = np.empty((B, canvas_size), dtype=np.int32)
+    if out is not None:
+        pos, charges, bags_out = out
+        bags_out[...] = bags
+        bags = bags_out
+    else:
+        pos = np.empty((B, canvas_size, 3), dtype=np.float32)
+        charges = np.empty((B, canvas_size), dtype=np.int32)
     if cfg is None:
         cfg = _cabi.CovConfig()
         cfg.canvas_size, cfg.num_species = canvas_size, len(zs)

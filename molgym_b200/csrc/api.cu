@@ -224,12 +224,22 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   MGB_CUDA_OK(cudaMemcpy(plan->d_desc, &d, sizeof(CovDesc), cudaMemcpyHostToDevice));
   MGB_CUDA_OK(cudaMalloc((void**)&plan->d_segs, sizeof(TransposeSeg) * plan->segs.size()));
   MGB_CUDA_OK(cudaMemcpy(plan->d_segs, plan->segs.data(), sizeof(TransposeSeg) * plan->segs.size(), cudaMemcpyHostToDevice));
+  MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
+  for (int q = 0; q <= kMaxLevels; ++q) {
+    MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork[q], cudaEventDisableTiming));
+    MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join[q], cudaEventDisableTiming));
+  }
   *out = plan.release();
   return MGB_OK;
 }
 
 void mgb_cov_plan_destroy(mgb_cov_plan* plan) {
   if (!plan) return;
+  if (plan->side) cudaStreamDestroy(plan->side);
+  for (int q = 0; q <= kMaxLevels; ++q) {
+    if (plan->ev_fork[q]) cudaEventDestroy(plan->ev_fork[q]);
+    if (plan->ev_join[q]) cudaEventDestroy(plan->ev_join[q]);
+  }
   cudaFree(plan->d_tables);
   cudaFree(plan->d_desc);
   cudaFree(plan->d_segs);

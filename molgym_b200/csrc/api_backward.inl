@@ -76,19 +76,56 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   }
   MGB_LAUNCH(k_scalars_bwd, B * N, 64, 0, st, plan->d_desc, w.n_atoms, w.A[K], w.dinv, w.dA[K & 1]);
   MGB_LAUNCH_OK("k_scalars_bwd");
+  cudaStream_t side = plan->side;
+  // fork: the MLP weight gradients only need the head kernels' outputs; they run beside the CG levels
+  MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[K], st));
+  MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[K], 0));
+  {
+    DwProblemList list;
+    int q = 0;
+    const long long rows = (long long)BN;
+    auto add = [&](const float* X, const float* dY, long long r, int Kin, int No, int mode, long long dW, long long db) {
+      list.p[q++] = DwProblem{X, dY, r, Kin, No, mode, dW, db};
+    };
+    add(w.inv, w.dhf, rows, d.lat, d.Wd, kRowsActive, d.focus.W0, d.focus.b0);
+    add(w.hf, w.dflogit, rows, d.Wd, 1, kRowsActive, d.focus.W1, d.focus.b1);
+    add(w.inv, w.dht0, rows, d.lat, d.Wd, kRowsValid, d.trans.W0, d.trans.b0);
+    add(w.ht0, w.dtrans, rows, d.Wd, d.Wd, kRowsValid, d.trans.W1, d.trans.b1);
+    add(w.finv, w.dhe, B, d.lat, d.Wd, kRowsAll, d.element.W0, d.element.b0);
+    add(w.he, w.dye, B, d.Wd, d.Z, kRowsAll, d.element.W1, d.element.b1);
+    add(w.einv, w.dhd, B, d.latE, d.Wd, kRowsAll, d.dist.W0, d.dist.b0);
+    add(w.hd, w.dyd, B, d.Wd, 2 * d.G, kRowsAll, d.dist.W1, d.dist.b1);
+    add(w.vf, w.dhv, B, d.Wd, d.Wd, kRowsAll, d.value.W0, d.value.b0);
+    add(w.hv, w.dyv, B, d.Wd, 1, kRowsAll, d.value.W1, d.value.b1);
+    list.n = q;
+    int nw = 0;
+    for (int pi = 0; pi < q; ++pi)
+      for (int o0 = 0; o0 < list.p[pi].No; o0 += kDwTileO) list.w[nw++] = DwWork{pi, o0};
+    list.nw = nw;
+    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, side, list, w.dw_probs, w.dw_work);
+    MGB_LAUNCH_OK("k_store_dw_problems");
+    const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
+    dim3 grid(chunks, nw);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, side, w.dw_probs, w.dw_work, w.n_atoms, N, grad);
+    MGB_LAUNCH_OK("k_dw_grouped");
+  }
   for (int k = K - 1; k >= 0; --k) {
     const LevelDesc& L = d.lv[k];
+    if (k < K - 1) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[k + 1], 0));   // mix_dw(k+1) still reads dA[(k+2)&1] == dA[k&1]
     MGB_CUDA_OK(cudaMemsetAsync(w.dA[k & 1], 0, sizeof(float) * BN * kM * cmax * 2, st));
     const int acc_dE = (k < K - 1) ? 1 : 0;
     int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, st);
     if (rc != MGB_OK) return rc;
     {
+      // fork: the atom-mix weight gradient (reads cat_k and dA_{k+1}) runs beside the edge level of the same k
+      MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[k], st));
+      MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[k], 0));
       const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + kMixDwAtoms - 1) / kMixDwAtoms, 148 * 2));
       dim3 grid(chunks, kNL);
       const size_t sm = sizeof(float2) * kMixDwAtoms * 9 * L.Cout;
 #define MGB_MIXDW_CASE(CO)                                                                                              \
   case CO:                                                                                                              \
-    MGB_LAUNCH(k_mix_dw<CO>, grid, kMixDwThreads, sm, st, plan->d_desc, k, B, w.n_atoms, w.cat[k], w.dA[(k + 1) & 1], grad); \
+    MGB_LAUNCH(k_mix_dw<CO>, grid, kMixDwThreads, sm, side, plan->d_desc, k, B, w.n_atoms, w.cat[k], w.dA[(k + 1) & 1], grad); \
     break;
       switch (pick_co(L.Cout)) {
         MGB_MIXDW_CASE(10)
@@ -99,6 +136,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       }
 #undef MGB_MIXDW_CASE
       MGB_LAUNCH_OK("k_mix_dw");
+      MGB_CUDA_OK(cudaEventRecord(plan->ev_join[k], side));
     }
     {
       const size_t esm = sizeof(float2) * kEdgeBwdWarps * edge_warp_floats2(L, true);
@@ -120,35 +158,21 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     }
   }
   {
+    // InputLinear weight gradient (needs dA_0) on the main stream; its problem descriptor sits after the head problems
     DwProblemList list;
-    int q = 0;
-    const long long rows = (long long)BN;
-    auto add = [&](const float* X, const float* dY, long long r, int Kin, int No, int mode, long long dW, long long db) {
-      list.p[q++] = DwProblem{X, dY, r, Kin, No, mode, dW, db};
-    };
-    add(w.inv, w.dhf, rows, d.lat, d.Wd, kRowsActive, d.focus.W0, d.focus.b0);
-    add(w.hf, w.dflogit, rows, d.Wd, 1, kRowsActive, d.focus.W1, d.focus.b1);
-    add(w.inv, w.dht0, rows, d.lat, d.Wd, kRowsValid, d.trans.W0, d.trans.b0);
-    add(w.ht0, w.dtrans, rows, d.Wd, d.Wd, kRowsValid, d.trans.W1, d.trans.b1);
-    add(w.finv, w.dhe, B, d.lat, d.Wd, kRowsAll, d.element.W0, d.element.b0);
-    add(w.he, w.dye, B, d.Wd, d.Z, kRowsAll, d.element.W1, d.element.b1);
-    add(w.einv, w.dhd, B, d.latE, d.Wd, kRowsAll, d.dist.W0, d.dist.b0);
-    add(w.hd, w.dyd, B, d.Wd, 2 * d.G, kRowsAll, d.dist.W1, d.dist.b1);
-    add(w.vf, w.dhv, B, d.Wd, d.Wd, kRowsAll, d.value.W0, d.value.b0);
-    add(w.hv, w.dyv, B, d.Wd, 1, kRowsAll, d.value.W1, d.value.b1);
-    add(w.X, w.dA[0], rows, d.S_in, 2 * d.C, kRowsValid, d.p_inW, d.p_inb);
-    list.n = q;
+    list.p[0] = DwProblem{w.X, w.dA[0], (long long)BN, d.S_in, 2 * d.C, kRowsValid, d.p_inW, d.p_inb};
+    list.n = 1;
     int nw = 0;
-    for (int pi = 0; pi < q; ++pi)
-      for (int o0 = 0; o0 < list.p[pi].No; o0 += kDwTileO) list.w[nw++] = DwWork{pi, o0};
+    for (int o0 = 0; o0 < list.p[0].No; o0 += kDwTileO) list.w[nw++] = DwWork{0, o0};
     list.nw = nw;
-    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, st, list, w.dw_probs, w.dw_work);
+    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, st, list, w.dw_probs + 16, w.dw_work + 64);
     MGB_LAUNCH_OK("k_store_dw_problems");
     const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
     dim3 grid(chunks, nw);
-    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, w.dw_probs, w.dw_work, w.n_atoms, N, grad);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, w.dw_probs + 16, w.dw_work + 64, w.n_atoms, N, grad);
     MGB_LAUNCH_OK("k_dw_grouped");
   }
+  MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[0], 0));   // join the side stream (its last work is mix_dw(0))
   return MGB_OK;
 }
 

@@ -13,6 +13,9 @@ struct mgb_cov_plan {
   std::vector<mgb::TransposeSeg> segs;
   mgb::TransposeSeg* d_segs = nullptr;
   std::vector<long long> p_offsets, p_numels;
+  // fork/join of independent backward kernels (weight-gradient reductions next to the edge level)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[mgb::kMaxLevels + 1] = {}, ev_join[mgb::kMaxLevels + 1] = {};
 };
 
 namespace mgb {

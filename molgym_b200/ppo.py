@@ -8,13 +8,21 @@ import numpy as np
 import torch
 
 
+def _to_device(x, device):
+    """torch.as_tensor(x, device=device) (ppo.py:28-30) without stalling the host behind the forward pass that was just
+    enqueued: numpy arrays go through a pinned staging copy and a non-blocking transfer."""
+    if isinstance(x, np.ndarray) and torch.device(device).type == 'cuda':
+        return torch.from_numpy(x).pin_memory().to(device, non_blocking=True)
+    return torch.as_tensor(x, device=device)
+
+
 def compute_loss(ac, data: dict, clip_ratio: float, vf_coef: float, entropy_coef: float, device=None) -> Tuple[torch.Tensor, Dict[str, float]]:
     """ppo.py:18-63, same operations in the same order (adv / ret arrive as float64 numpy -> float64 loss)."""
     pred = ac.step(data['obs'], data['act'])
     device = device if device is not None else pred['logp'].device
-    old_logp = torch.as_tensor(data['logp'], device=device)
-    adv = torch.as_tensor(data['adv'], device=device)
-    ret = torch.as_tensor(data['ret'], device=device)
+    old_logp = _to_device(data['logp'], device)
+    adv = _to_device(data['adv'], device)
+    ret = _to_device(data['ret'], device)
     ratio = torch.exp(pred['logp'] - old_logp)
     obj = ratio * adv
     clipped_obj = ratio.clamp(1 - clip_ratio, 1 + clip_ratio) * adv
