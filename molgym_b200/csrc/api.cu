@@ -17,7 +17,7 @@ static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const flo
                            cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
-  const size_t smem = sizeof(float) * atom_smem_floats(L);
+  const size_t smem = sizeof(float) * atom_smem_floats(L, d.N);
   const int co = pick_co(L.Cout);
 #define MGB_ATOM_CASE(CO)                                                                                          \
   case CO: {                                                                                                       \

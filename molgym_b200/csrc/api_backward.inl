@@ -17,7 +17,7 @@ static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const flo
                            int accumulate_dE, cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
-  const size_t smem = sizeof(float) * atom_bwd_smem_floats(L);
+  const size_t smem = sizeof(float) * atom_bwd_smem_floats(L, d.N);
 #define MGB_ATOM_BWD_CASE(CO)                                                                                          \
   case CO: {                                                                                                           \
     MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \

@@ -343,10 +343,10 @@ __host__ __device__ inline int policy_bwd_extra_floats(const CovDesc& d) {
 constexpr int kAtomBwdThreads = 256;
 constexpr int kJChunkBwd = 4;
 
-__host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L) {
+__host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
-  const int stage = kJChunkBwd * (kM + kNL * L.C + nlm2 * L.C + kM * L.C + kNL * L.C) * 2;
-  return L.totA * 2 + kM * L.Cout * 2 + stage + nlm2 * L.C * 2;
+  const int stage = kJChunkBwd * (kNL * L.C + nlm2 * L.C + kM * L.C) * 2;
+  return L.totA * 2 + kM * L.Cout * 2 + stage + nlm2 * L.C * 2 + N * kM * 2;
 }
 
 // dcat[l][m][k] = sum_c' conj(W_l[c'][k]) dOut[lm][c']   (warp units of <= 2 rows, lanes over k, dOut rows in registers)
@@ -409,18 +409,18 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   MGB_DYN_SMEM(float2, smem);
   float2* sDcat = smem;                         // [totA]
   float2* sdOut = sDcat + L.totA;               // [25][Cout]
-  float2* sY = sdOut + kM * Cout;               // [JC][25]
-  float2* sE = sY + kJChunkBwd * kM;            // [JC][5][C]
+  float2* sE = sdOut + kM * Cout;               // [JC][5][C]
   float2* sAj = sE + kJChunkBwd * kNL * C;      // [JC][NLM2][C]
-  float2* sU = sAj + kJChunkBwd * NLM2 * C;     // [JC][25][C]   E * Y
-  float2* sdE = sU + kJChunkBwd * kM * C;       // [JC][5][C]
-  float2* sAi = sdE + kJChunkBwd * kNL * C;     // [NLM2][C]
+  float2* sU = sAj + kJChunkBwd * NLM2 * C;     // [JC][25][C]   column pass: E * Y ; row pass: per-thread dE contributions
+  float2* sAi = sU + kJChunkBwd * kM * C;       // [NLM2][C]
+  float2* sYall = sAi + NLM2 * C;               // [n][25]
   const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
   const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
   float2* dE_i = reinterpret_cast<float2*>(dE) + ((long long)b * N + i) * N * kNL * C;
   float2* dAb = reinterpret_cast<float2*>(dA_in) + (long long)b * N * NLM2 * C;
   const float* pos_b = pos + (long long)b * N * 3;
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
+  neighbour_harmonics(pos_b, i, n, sYall);
   {
     const float2* src = reinterpret_cast<const float2*>(dA_out) + ((long long)b * N + i) * kM * Cout;
     for (int idx = threadIdx.x; idx < kM * Cout; idx += blockDim.x) sdOut[idx] = src[idx];
@@ -444,12 +444,11 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
       const int nj = min(kJChunkBwd, n - j0);
       __syncthreads();
-      stage_neighbours<NLM2>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
-      for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) sdE[idx] = make_float2(0.f, 0.f);
+      stage_neighbours<NLM2>(L, Ab, E_i, j0, nj, sE, sAj);
       __syncthreads();
       if (owner) {
         for (int jj = 0; jj < nj; ++jj) {
-          // dE_ij[l1, c] += conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
+          // contribution of m1 = x to dE_ij[l1, c]: conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
           float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
           const float2* a = sAj + jj * NLM2 * C + c;
           MGB_UNROLL
@@ -458,13 +457,16 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
           }
           w0.x += w1.x; w0.y += w1.y;
           float2 de = make_float2(0.f, 0.f);
-          cfmacl(de, sY[jj * kM + x], w0);
-          smem_add2(sdE + (jj * kNL + l1) * C + c, de);
+          cfmacl(de, sYall[(j0 + jj) * kM + x], w0);
+          sU[(jj * kM + x) * C + c] = de;
         }
       }
       __syncthreads();
+      // sum the 2l+1 contributions of every (j, l, c) and write dE
       for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) {
-        float2 v = sdE[idx];
+        const int jj = idx / (kNL * C), r = idx - jj * (kNL * C), l = r / C, cc = r - l * C;
+        float2 v = make_float2(0.f, 0.f);
+        for (int m = 0; m < 2 * l + 1; ++m) { const float2 t = sU[(jj * kM + l * l + m) * C + cc]; v.x += t.x; v.y += t.y; }
         float2* dst = dE_i + (long long)j0 * kNL * C + idx;
         if (accumulate_dE) { v.x += dst->x; v.y += dst->y; }
         *dst = v;
@@ -489,12 +491,10 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
       const int nj = min(kJChunkBwd, n - j0);
       __syncthreads();
-      stage_neighbours<0>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
+      stage_neighbours<0>(L, Ab, E_i, j0, nj, sE, sAj);
       __syncthreads();
-      for (int idx = threadIdx.x; idx < nj * kM * C; idx += blockDim.x) {
-        const int jj = idx / (kM * C), r = idx % (kM * C), lm = r / C, cc = r % C;
-        sU[idx] = cmul(sE[(jj * kNL + ell_of_lm(lm)) * C + cc], sY[jj * kM + lm]);
-      }
+      if (owner)
+        for (int jj = 0; jj < nj; ++jj) sU[(jj * kM + x) * C + c] = cmul(sE[(jj * kNL + l1) * C + c], sYall[(j0 + jj) * kM + x]);
       __syncthreads();
       if (col_owner) {
         for (int jj = 0; jj < nj; ++jj) {
@@ -741,9 +741,12 @@ k_edge_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* __rest
       float df0 = 0.f, df1 = 0.f;
       for (int l = 0; l < kNL; ++l) {
         const float* dR = reinterpret_cast<const float*>(catbuf + off_l[l] + L.catE[l] - C);
-        const float* w = Wt_rad + ((long long)l * kRadFeat + lane) * C2;
+        const float* w = P + L.p_radW + (long long)l * C2 * kRadFeat + lane;   // reference layout [o][t]: lanes over t coalesce
 #pragma unroll 4
-        for (int oo = 0; oo < C2; oo += 2) { df0 = fmaf(w[oo], dR[oo], df0); df1 = fmaf(w[oo + 1], dR[oo + 1], df1); }
+        for (int oo = 0; oo < C2; oo += 2) {
+          df0 = fmaf(w[oo * kRadFeat], dR[oo], df0);
+          df1 = fmaf(w[(oo + 1) * kRadFeat], dR[oo + 1], df1);
+        }
       }
       float dval;
       rad_feature(lane, g, P + L.p_scales, P + L.p_phases, &dval);

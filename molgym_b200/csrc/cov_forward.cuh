@@ -388,27 +388,30 @@ __device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2*
 constexpr int kAtomThreads = 512;
 constexpr int kJChunk = 8;
 
-__host__ __device__ inline int atom_smem_floats(const LevelDesc& L) {
+__host__ __device__ inline int atom_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
-  const int stage = kJChunk * (kM + kNL * L.C + nlm2 * L.C) * 2;
+  const int stage = kJChunk * (kNL * L.C + nlm2 * L.C) * 2;
   const int tsz = kM * nlm2 * L.C * 2;
-  return (stage > tsz ? stage : tsz) + L.totA * 2 + nlm2 * L.C * 2;
+  return (stage > tsz ? stage : tsz) + L.totA * 2 + nlm2 * L.C * 2 + N * kM * 2;
 }
 
-// Stage one chunk of neighbours j0..j0+nj-1 of atom i into shared memory: Y_ij (conj, 'unit' norm, un-normalised
-// argument: SphericalHarmonicsRel(conj=True), covariant/modules.py:52-56), E_ij, A_j.
-template <int NLM2>
-__device__ __forceinline__ void stage_neighbours(const CovDesc& d, const LevelDesc& L, const float* __restrict__ pos_b,
-                                                 const float2* __restrict__ Ab, const float2* __restrict__ E_i, int i, int j0,
-                                                 int nj, float2* sY, float2* sE, float2* sAj) {
-  const int C = L.C;
-  if ((int)threadIdx.x < nj) {
-    const int j = j0 + threadIdx.x;
+// Y_lm(r_i - r_j) for every neighbour j of atom i, once per CTA (conj, 'unit' norm, un-normalised argument:
+// SphericalHarmonicsRel(conj=True), covariant/modules.py:52-56).  sYall: [n][25]
+__device__ __forceinline__ void neighbour_harmonics(const float* __restrict__ pos_b, int i, int n, float2* sYall) {
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
     float2 y[kM];
     sph_harm_l4(pos_b[i * 3 + 0] - pos_b[j * 3 + 0], pos_b[i * 3 + 1] - pos_b[j * 3 + 1], pos_b[i * 3 + 2] - pos_b[j * 3 + 2], true,
                 true, y);
-    for (int q = 0; q < kM; ++q) sY[threadIdx.x * kM + q] = y[q];
+    MGB_UNROLL
+    for (int q = 0; q < kM; ++q) sYall[j * kM + q] = y[q];
   }
+}
+
+// Stage one chunk of neighbours j0..j0+nj-1 of atom i into shared memory: E_ij and (NLM2 > 0) A_j.
+template <int NLM2>
+__device__ __forceinline__ void stage_neighbours(const LevelDesc& L, const float2* __restrict__ Ab, const float2* __restrict__ E_i,
+                                                 int j0, int nj, float2* sE, float2* sAj) {
+  const int C = L.C;
   for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) sE[idx] = E_i[(long long)j0 * kNL * C + idx];
   for (int idx = threadIdx.x; idx < nj * NLM2 * C; idx += blockDim.x) sAj[idx] = Ab[(long long)j0 * NLM2 * C + idx];
 }
@@ -425,17 +428,18 @@ k_atom_fwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const int n = n_atoms[b];
   if (i >= n) return;
   MGB_DYN_SMEM(float2, smem);
-  const int stage = kJChunk * (kM + kNL * C + NLM2 * C), tsz = kM * NLM2 * C;
+  const int stage = kJChunk * (kNL * C + NLM2 * C), tsz = kM * NLM2 * C;
   float2* sT = smem;
-  float2* sY = smem;
-  float2* sE = sY + kJChunk * kM;
+  float2* sE = smem;
   float2* sAj = sE + kJChunk * kNL * C;
   float2* sCat = smem + (stage > tsz ? stage : tsz);
   float2* sAi = sCat + L.totA;
+  float2* sYall = sAi + NLM2 * C;
   const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
   const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
   const float* pos_b = pos + (long long)b * N * 3;
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
+  neighbour_harmonics(pos_b, i, n, sYall);
 
   const bool owner = (int)threadIdx.x < kM * C;
   const int lm1 = owner ? threadIdx.x / C : 0, c = owner ? threadIdx.x % C : 0;
@@ -446,11 +450,11 @@ k_atom_fwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   for (int j0 = 0; j0 < n; j0 += kJChunk) {
     const int nj = min(kJChunk, n - j0);
     __syncthreads();
-    stage_neighbours<NLM2>(d, L, pos_b, Ab, E_i, i, j0, nj, sY, sE, sAj);
+    stage_neighbours<NLM2>(L, Ab, E_i, j0, nj, sE, sAj);
     __syncthreads();
     if (owner) {
       for (int jj = 0; jj < nj; ++jj) {
-        const float2 u = cmul(sE[(jj * kNL + l1) * C + c], sY[jj * kM + lm1]);
+        const float2 u = cmul(sE[(jj * kNL + l1) * C + c], sYall[(j0 + jj) * kM + lm1]);
         const float2* a = sAj + jj * NLM2 * C + c;
         MGB_UNROLL
         for (int q = 0; q < NLM2; ++q) cfma(acc[q], u, a[q * C]);
