@@ -214,6 +214,7 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     o_leb_w = arena.add(lw.data(), lw.size() * sizeof(float));
   }
   MGB_CUDA_OK(cudaMalloc(&plan->d_tables, arena.host.size()));
+  plan->table_bytes = arena.host.size();
   MGB_CUDA_OK(cudaMemcpy(plan->d_tables, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice));
   for (auto& pt : pending) resolve_table(pt, (const unsigned char*)plan->d_tables);
   if (d.has_beta) {
@@ -284,7 +285,8 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = d.N;
-  MGB_LAUNCH(k_prep_params, (int)((d.n_wt + 255) / 256), 256, 0, st, plan->d_segs, (int)plan->segs.size(), (long long)d.n_wt, P, w.Wt);
+  MGB_LAUNCH(k_prep_params, (int)((d.n_wt + 255) / 256), 256, 0, st, plan->d_segs, (int)plan->segs.size(), (long long)d.n_wt, P, w.Wt,
+             (long long)d.n_params, (const char*)plan->d_tables, (long long)plan->table_bytes);
   MGB_LAUNCH_OK("k_prep_params");
   MGB_LAUNCH(k_input_fwd, B, 128, sizeof(float) * N * d.S_in, st, plan->d_desc, P, charges, bags, w.n_atoms, w.X, w.A[0]);
   MGB_LAUNCH_OK("k_input_fwd");

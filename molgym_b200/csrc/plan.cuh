@@ -10,6 +10,7 @@ struct mgb_cov_plan {
   mgb::CovDesc desc;                 // host copy (device pointers inside)
   mgb::CovDesc* d_desc = nullptr;    // device copy
   void* d_tables = nullptr;          // one allocation holding every table
+  size_t table_bytes = 0;
   std::vector<mgb::TransposeSeg> segs;
   mgb::TransposeSeg* d_segs = nullptr;
   std::vector<long long> p_offsets, p_numels;
