@@ -12,29 +12,53 @@ using namespace mgb;
     if (e_ != cudaSuccess) return fail(MGB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e_)); \
   } while (0)
 
+template <int CO, bool BACKWARD, int KS>
+static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const LevelDesc& L = d.lv[level];
+  int kmax = 0;
+  for (int l = 0; l < kNL; ++l) kmax = std::max(kmax, L.catA[l]);
+  const size_t smem = sizeof(float2) * (size_t)kmax * CO;
+  MGB_CUDA_OK(cudaFuncSetAttribute((k_mix_rows<CO, BACKWARD, KS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long rows_per_cta = kMixThreads / KS;
+  dim3 grid((unsigned)(((long long)B * d.N * 9 + rows_per_cta - 1) / rows_per_cta), kNL);
+  MGB_LAUNCH((k_mix_rows<CO, BACKWARD, KS>), grid, kMixThreads, smem, st, plan->d_desc, level, w.Wt, w.atom_off, w.atom_list, B,
+             w.cat[level], A_out, out);
+  MGB_LAUNCH_OK("k_mix_rows");
+  return MGB_OK;
+}
+template <int CO, bool BACKWARD>
+static int launch_mix_rows_co(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
+  // small minibatches: split every row over 8 lanes so that the GPU has enough warps; large ones: one thread per row
+  const long long slots = (long long)B * plan->desc.N;
+  if (slots * 25 < 148ll * 2048 * 2) return launch_mix_rows_ks<CO, BACKWARD, 8>(plan, level, B, w, A_out, out, st);
+  return launch_mix_rows_ks<CO, BACKWARD, 1>(plan, level, B, w, A_out, out, st);
+}
+template <bool BACKWARD>
+static int launch_mix_rows(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
+  switch (pick_co_rows(plan->desc.lv[level].Cout)) {
+    case 4: return launch_mix_rows_co<4, BACKWARD>(plan, level, B, w, A_out, out, st);
+    case 8: return launch_mix_rows_co<8, BACKWARD>(plan, level, B, w, A_out, out, st);
+    case 10: return launch_mix_rows_co<10, BACKWARD>(plan, level, B, w, A_out, out, st);
+    case 12: return launch_mix_rows_co<12, BACKWARD>(plan, level, B, w, A_out, out, st);
+    case 16: return launch_mix_rows_co<16, BACKWARD>(plan, level, B, w, A_out, out, st);
+    case 20: return launch_mix_rows_co<20, BACKWARD>(plan, level, B, w, A_out, out, st);
+    default: return launch_mix_rows_co<32, BACKWARD>(plan, level, B, w, A_out, out, st);
+  }
+}
+
 template <int NLM2>
 static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
                            cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
   const size_t smem = sizeof(float) * atom_smem_floats(L, d.N);
-  const int co = pick_co(L.Cout);
-#define MGB_ATOM_CASE(CO)                                                                                          \
-  case CO: {                                                                                                       \
-    MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_fwd<NLM2, CO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    MGB_LAUNCH((k_atom_fwd<NLM2, CO, 2>), B * d.N, kAtomThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms,  \
-               w.A[level], w.E[level], w.cat[level], w.A[level + 1]);                                             \
-  } break;
-  switch (co) {
-    MGB_ATOM_CASE(10)
-    MGB_ATOM_CASE(8)
-    MGB_ATOM_CASE(6)
-    MGB_ATOM_CASE(5)
-    MGB_ATOM_CASE(4)
-  }
-#undef MGB_ATOM_CASE
-  MGB_LAUNCH_OK("k_atom_fwd");
-  return MGB_OK;
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGB_LAUNCH(k_atom_cat<NLM2>, B * d.N, kAtomThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+             w.A[level], w.E[level], w.cat[level]);
+  MGB_LAUNCH_OK("k_atom_cat");
+  (void)P;
+  return launch_mix_rows<false>(plan, level, B, w, nullptr, w.A[level + 1], st);
 }
 
 static int launch_policy_fwd(const mgb_cov_plan* plan, int B, const float* bags, const float* actions, const float* P,
@@ -146,6 +170,10 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     for (int l = 0; l < kNL; ++l)
       plan->segs.push_back(TransposeSeg{L.p_radW + (long long)l * C2 * kRadFeat, wt + (long long)l * C2 * kRadFeat, C2, kRadFeat, 1});
     wt += (long long)kNL * C2 * kRadFeat;
+    d.wt_atom[k] = wt;   // atom-mix weights transposed to [l][k][c'][2]
+    for (int l = 0; l < kNL; ++l)
+      plan->segs.push_back(TransposeSeg{L.p_atomW + 2ll * L.offWA[l], wt + 2ll * L.offWA[l], L.Cout, L.catA[l], 2});
+    wt += 2ll * L.totWA;
     {
       const int zero[kNL] = {0, 0, 0, 0, 0};
       resolve_cg_table(ag, L.catA, L.offA, zero, C, false);
@@ -292,22 +320,28 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   MGB_LAUNCH_OK("k_input_fwd");
   if (out->covariats)   // padded atoms carry zero representations in the reference; the level kernels skip them
     MGB_CUDA_OK(cudaMemsetAsync(w.A[d.K], 0, sizeof(float) * (size_t)B * N * kM * d.Cout * 2, st));
-  MGB_LAUNCH(k_pair_offsets, 1, 1024, 0, st, B, w.n_atoms, w.pair_off);
+  MGB_LAUNCH(k_pair_offsets, 1, 1024, 0, st, B, N, w.n_atoms, w.pair_off, w.atom_off, w.atom_list);
   MGB_LAUNCH_OK("k_pair_offsets");
-  const int pair_ctas = (int)std::min<long long>(((long long)B * N * N + 7) / 8, 148 * 8);
+  const unsigned pair_blocks = (unsigned)(((long long)B * N * N + kPairThreads - 1) / kPairThreads);
   for (int k = 0; k < d.K; ++k) {
     const LevelDesc& L = d.lv[k];
-    const size_t esm = sizeof(float2) * (kEdgeThreads / 32) * edge_warp_floats2(L, false);
+    const size_t dsm = sizeof(float2) * (size_t)N * L.nlm_in * L.C;
+    const size_t esm = sizeof(float2) * 70 * kEdgeC + sizeof(float) * (2 * L.C * (kRadFeat + 1));
+    dim3 egrid(pair_blocks, kNL);
     if (k == 0) {
-      MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-      MGB_LAUNCH(k_edge_fwd<1>, pair_ctas, kEdgeThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
+      MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
+      MGB_LAUNCH_OK("k_dot_fwd");
+      MGB_LAUNCH(k_edge_pairs_fwd<1>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D,
                  (const float*)nullptr, w.E[k]);
     } else {
-      MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-      MGB_LAUNCH(k_edge_fwd<kNL>, pair_ctas, kEdgeThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
+      MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
+      MGB_LAUNCH_OK("k_dot_fwd");
+      MGB_LAUNCH(k_edge_pairs_fwd<kNL>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D,
                  w.E[k - 1], w.E[k]);
     }
-    MGB_LAUNCH_OK("k_edge_fwd");
+    MGB_LAUNCH_OK("k_edge_pairs_fwd");
     int rc = k == 0 ? launch_atom_fwd<1>(plan, k, B, P, pos, w, st) : launch_atom_fwd<kM>(plan, k, B, P, pos, w, st);
     if (rc != MGB_OK) return rc;
   }

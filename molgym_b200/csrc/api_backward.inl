@@ -17,21 +17,14 @@ static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const flo
                            int accumulate_dE, cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
+  (void)P;
+  // dcat = W^H dA_{level+1}, row-parallel, into HBM; the atom kernel stages its atom's slice in shared memory
+  int rc = launch_mix_rows<true>(plan, level, B, w, w.dA[(level + 1) & 1], w.dcat, st);
+  if (rc != MGB_OK) return rc;
   const size_t smem = sizeof(float) * atom_bwd_smem_floats(L, d.N);
-#define MGB_ATOM_BWD_CASE(CO)                                                                                          \
-  case CO: {                                                                                                           \
-    MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    MGB_LAUNCH((k_atom_bwd<NLM2, CO>), B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, P, pos, w.n_atoms,      \
-               w.A[level], w.E[level], w.dA[(level + 1) & 1], w.dA[level & 1], w.dE[level & 1], accumulate_dE);        \
-  } break;
-  switch (pick_co(L.Cout)) {
-    MGB_ATOM_BWD_CASE(10)
-    MGB_ATOM_BWD_CASE(8)
-    MGB_ATOM_BWD_CASE(6)
-    MGB_ATOM_BWD_CASE(5)
-    MGB_ATOM_BWD_CASE(4)
-  }
-#undef MGB_ATOM_BWD_CASE
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+             w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE);
   MGB_LAUNCH_OK("k_atom_bwd");
   return MGB_OK;
 }
@@ -139,19 +132,33 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       MGB_CUDA_OK(cudaEventRecord(plan->ev_join[k], side));
     }
     {
-      const size_t esm = sizeof(float2) * kEdgeBwdWarps * edge_warp_floats2(L, true);
-      const int grid = (int)std::min<size_t>((BN * N + kEdgeBwdWarps - 1) / kEdgeBwdWarps, 148);
+      const unsigned pair_blocks = (unsigned)((BN * N + kPairThreads - 1) / kPairThreads);
+      const size_t dsm = sizeof(float2) * (size_t)N * L.nlm_in * L.C;
+      const size_t esm = sizeof(float2) * (size_t)L.sumCatE * kEdgeC + sizeof(float) * (kNL * 2 * L.C * (kRadFeat + 1));
+      EdgeScratch sc{w.e_dpre, w.e_R, w.e_dR, w.e_f};
+      const int dw_chunks = (int)std::max<size_t>(1, std::min<size_t>((BN * N + kEdgeDwSub - 1) / kEdgeDwSub, 148 * 4));
+      dim3 dwgrid(dw_chunks, kNL);
       if (k == 0) {
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-        MGB_LAUNCH(k_edge_bwd<1>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
-                   (const float*)nullptr, w.dE[k & 1], (float*)nullptr, w.dD, grad);
-        MGB_LAUNCH_OK("k_edge_bwd");
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+        MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
+        MGB_LAUNCH_OK("k_dot_fwd");
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_pairs_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+        MGB_LAUNCH(k_edge_pairs_bwd<1>, pair_blocks, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,
+                   w.dE[k & 1], (float*)nullptr, w.dD, sc, grad);
+        MGB_LAUNCH_OK("k_edge_pairs_bwd");
+        MGB_LAUNCH(k_edge_dw<1>, dwgrid, kEdgeDwThreads, 0, st, plan->d_desc, k, B, w.n_atoms, w.pair_off, (const float*)nullptr, w.D, sc, grad);
+        MGB_LAUNCH_OK("k_edge_dw");
         MGB_LAUNCH(k_dot_bwd<1>, B * N, 64, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
       } else {
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_bwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-        MGB_LAUNCH(k_edge_bwd<kNL>, grid, kEdgeBwdThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.A[k],
-                   w.E[k - 1], w.dE[k & 1], w.dE[(k - 1) & 1], w.dD, grad);
-        MGB_LAUNCH_OK("k_edge_bwd");
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+        MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
+        MGB_LAUNCH_OK("k_dot_fwd");
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_pairs_bwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+        MGB_LAUNCH(k_edge_pairs_bwd<kNL>, pair_blocks, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,
+                   w.dE[k & 1], w.dE[(k - 1) & 1], w.dD, sc, grad);
+        MGB_LAUNCH_OK("k_edge_pairs_bwd");
+        MGB_LAUNCH(k_edge_dw<kNL>, dwgrid, kEdgeDwThreads, 0, st, plan->d_desc, k, B, w.n_atoms, w.pair_off, w.E[k - 1], w.D, sc, grad);
+        MGB_LAUNCH_OK("k_edge_dw");
         MGB_LAUNCH(k_dot_bwd<kNL>, B * N, 256, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
       }
       MGB_LAUNCH_OK("k_dot_bwd");

@@ -346,70 +346,25 @@ constexpr int kJChunkBwd = 4;
 __host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
   const int stage = kJChunkBwd * (kNL * L.C + nlm2 * L.C + kM * L.C) * 2;
-  return L.totA * 2 + kM * L.Cout * 2 + stage + nlm2 * L.C * 2 + N * kM * 2;
+  return L.totA * 2 + stage + nlm2 * L.C * 2 + N * kM * 2;
 }
 
-// dcat[l][m][k] = sum_c' conj(W_l[c'][k]) dOut[lm][c']   (warp units of <= 2 rows, lanes over k, dOut rows in registers)
-template <int CO>
-__device__ __forceinline__ void mix_rows_bwd(const MixUnit* __restrict__ units, int n_units, const int* catA, const int* offA,
-                                             const int* offW, int Cout, const float2* __restrict__ W,
-                                             const float2* __restrict__ sdOut, float2* __restrict__ sDcat) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int u = warp; u < n_units; u += nwarps) {
-    const MixUnit un = units[u];
-    const int K = catA[un.l];
-    const int lm0 = un.l * un.l + un.m0;
-    float2 acc0[12], acc1[12];   // up to 12 k-slots per lane (K <= 384)
-    const int nslot = (K + 31) >> 5;
-    MGB_UNROLL
-    for (int sIdx = 0; sIdx < 12; ++sIdx) { acc0[sIdx] = make_float2(0.f, 0.f); acc1[sIdx] = make_float2(0.f, 0.f); }
-    for (int c0 = 0; c0 < Cout; c0 += CO) {
-      float2 g0[CO], g1[CO];
-      MGB_UNROLL
-      for (int c = 0; c < CO; ++c) {
-        const bool on = c0 + c < Cout;
-        g0[c] = on ? sdOut[lm0 * Cout + c0 + c] : make_float2(0.f, 0.f);
-        g1[c] = (on && un.nm > 1) ? sdOut[(lm0 + 1) * Cout + c0 + c] : make_float2(0.f, 0.f);
-      }
-      const float2* Wl = W + offW[un.l] + (long long)c0 * K;
-      MGB_UNROLL
-      for (int sIdx = 0; sIdx < 12; ++sIdx) {
-        const int k = lane + 32 * sIdx;
-        if (sIdx < nslot && k < K) {
-          float2 w[CO];
-          MGB_UNROLL
-          for (int c = 0; c < CO; ++c) w[c] = Wl[(c0 + c < Cout ? c : 0) * K + k];   // g0/g1 are zero beyond Cout
-          MGB_UNROLL
-          for (int c = 0; c < CO; ++c) { cfmacl(acc0[sIdx], w[c], g0[c]); cfmacl(acc1[sIdx], w[c], g1[c]); }
-        }
-      }
-    }
-    MGB_UNROLL
-    for (int sIdx = 0; sIdx < 12; ++sIdx) {
-      const int k = lane + 32 * sIdx;
-      if (sIdx < nslot && k < K) {
-        sDcat[offA[un.l] + un.m0 * K + k] = acc0[sIdx];
-        if (un.nm > 1) sDcat[offA[un.l] + (un.m0 + 1) * K + k] = acc1[sIdx];
-      }
-    }
-  }
-}
-
-template <int NLM2, int CO>
+template <int NLM2>
 __global__ void __launch_bounds__(kAtomBwdThreads, 2)
-k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ P, const float* __restrict__ pos,
-           const int* __restrict__ n_atoms, const float* __restrict__ A_in, const float* __restrict__ E,
-           const float* __restrict__ dA_out, float* __restrict__ dA_in, float* __restrict__ dE, int accumulate_dE) {
+k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ pos, const int* __restrict__ n_atoms,
+           const int* __restrict__ atom_off, const int* __restrict__ atom_list, int B, const float* __restrict__ A_in,
+           const float* __restrict__ E, const float* __restrict__ dcat, float* __restrict__ dA_in, float* __restrict__ dE,
+           int accumulate_dE) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
-  const int N = d.N, C = L.C, Cout = L.Cout;
-  const int b = blockIdx.x / N, i = blockIdx.x % N;
+  const int N = d.N, C = L.C;
+  if ((int)blockIdx.x >= atom_off[B]) return;
+  const int slot = atom_list[blockIdx.x];
+  const int b = slot / N, i = slot - b * N;
   const int n = n_atoms[b];
-  if (i >= n) return;
   MGB_DYN_SMEM(float2, smem);
-  float2* sDcat = smem;                         // [totA]
-  float2* sdOut = sDcat + L.totA;               // [25][Cout]
-  float2* sE = sdOut + kM * Cout;               // [JC][5][C]
+  float2* sDcat = smem;                         // [totA]  cotangent of the cat vector (written by k_mix_rows<.., true>)
+  float2* sE = sDcat + L.totA;                  // [JC][5][C]
   float2* sAj = sE + kJChunkBwd * kNL * C;      // [JC][NLM2][C]
   float2* sU = sAj + kJChunkBwd * NLM2 * C;     // [JC][25][C]   column pass: E * Y ; row pass: per-thread dE contributions
   float2* sAi = sU + kJChunkBwd * kM * C;       // [NLM2][C]
@@ -422,12 +377,15 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
   neighbour_harmonics(pos_b, i, n, sYall);
   {
-    const float2* src = reinterpret_cast<const float2*>(dA_out) + ((long long)b * N + i) * kM * Cout;
-    for (int idx = threadIdx.x; idx < kM * Cout; idx += blockDim.x) sdOut[idx] = src[idx];
+    const float2* src2 = reinterpret_cast<const float2*>(dcat) + (long long)slot * L.totA;
+    if ((L.totA & 1) == 0) {   // 16-byte aligned slices
+      const float4* src = reinterpret_cast<const float4*>(src2);
+      float4* dst = reinterpret_cast<float4*>(sDcat);
+      for (int idx = threadIdx.x; idx < L.totA / 2; idx += blockDim.x) dst[idx] = src[idx];
+    } else {
+      for (int idx = threadIdx.x; idx < L.totA; idx += blockDim.x) sDcat[idx] = src2[idx];
+    }
   }
-  __syncthreads();
-  mix_rows_bwd<CO>(d.units_hidden, d.n_units_hidden, L.catA, L.offA, L.offWA, Cout, reinterpret_cast<const float2*>(P + L.p_atomW),
-                   sdOut, sDcat);
   __syncthreads();
 
   const bool owner = (int)threadIdx.x < kM * C;
@@ -589,196 +547,6 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
           }
         }
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Edge level backward.  Persistent CTAs over the flat pair list; each round handles one pair per warp, then all threads
-// fold the round into the weight cotangents they own (edge mix, radial linears) held in registers; scale / phase
-// cotangents are per-lane.  Everything is flushed once per CTA.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kEdgeBwdThreads = 384;
-constexpr int kEdgeBwdWarps = kEdgeBwdThreads / 32;
-constexpr int kEdgeMaxC = 12;
-constexpr int kRadSlots = (kNL * 2 * kEdgeMaxC * kRadFeat + kEdgeBwdThreads - 1) / kEdgeBwdThreads;   // 10
-
-template <int NLIN>
-__global__ void __launch_bounds__(kEdgeBwdThreads)
-k_edge_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
-           const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
-           const float* __restrict__ A_in, const float* __restrict__ E_prev, const float* __restrict__ dE,
-           float* __restrict__ dE_prev, float* __restrict__ dD, float* __restrict__ grad) {
-  const CovDesc& d = *dp;
-  const LevelDesc& L = d.lv[level];
-  const int N = d.N, C = L.C, C2 = 2 * C;
-  constexpr int NLM = NLIN * NLIN;
-  MGB_DYN_SMEM(float2, smem);
-  const int per_warp = edge_warp_floats2(L, true);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* sA = smem + warp * per_warp;
-  float2* catbuf = sA + 2 * NLM * C;
-  float* f = reinterpret_cast<float*>(catbuf + L.sumCatE);
-  float2* dpre = catbuf + L.sumCatE + 16;
-  const int cat_off = 2 * NLM * C;   // offset of catbuf inside a warp's region
-  __shared__ int s_act[kEdgeBwdWarps];
-
-  // edge-mix weight ownership: thread -> (l, k)
-  int sl_l = -1, sl_k = 0, sl_off = 0;
-  {
-    int e = threadIdx.x, off = 0;
-    for (int l = 0; l < kNL; ++l) {
-      if (sl_l < 0 && e < L.catE[l]) { sl_l = l; sl_k = e; sl_off = off; }
-      if (sl_l < 0) e -= L.catE[l];
-      off += L.catE[l];
-    }
-  }
-  float2 we[kEdgeMaxC], dwe[kEdgeMaxC];
-  MGB_UNROLL
-  for (int c = 0; c < kEdgeMaxC; ++c) {
-    dwe[c] = make_float2(0.f, 0.f);
-    we[c] = (sl_l >= 0 && c < C) ? reinterpret_cast<const float2*>(P + L.p_edgeW)[L.offE[sl_l] + c * L.catE[sl_l] + sl_k]
-                                 : make_float2(0.f, 0.f);
-  }
-  // radial-weight ownership: entry e = thread + s * blockDim -> (l, o, t); radial block offsets per entry
-  float drw[kRadSlots];
-  int rad_src[kRadSlots], rad_t[kRadSlots];
-  const int n_rad = kNL * C2 * kRadFeat;
-  MGB_UNROLL
-  for (int s = 0; s < kRadSlots; ++s) {
-    drw[s] = 0.f;
-    const int e = threadIdx.x + s * kEdgeBwdThreads;
-    rad_src[s] = -1; rad_t[s] = 0;
-    if (e < n_rad) {
-      const int l = e / (C2 * kRadFeat), r = e - l * (C2 * kRadFeat), oo = r / kRadFeat;
-      int off = 0;
-      for (int q = 0; q < l; ++q) off += L.catE[q];
-      rad_src[s] = 2 * (off + L.catE[l] - C) + oo;   // float index inside catbuf
-      rad_t[s] = r - oo * kRadFeat;
-    }
-  }
-  float drb = 0.f;             // thread e < 5*2C owns radial bias e
-  int drb_src = -1;
-  if ((int)threadIdx.x < kNL * C2) {
-    const int l = threadIdx.x / C2, oo = threadIdx.x - l * C2;
-    int off = 0;
-    for (int q = 0; q < l; ++q) off += L.catE[q];
-    drb_src = 2 * (off + L.catE[l] - C) + oo;
-  }
-  float dsc = 0.f, dph = 0.f;  // lane t accumulates its share of scale/phase cotangents
-  const float* Wt_rad = Wt + d.wt_edge[level] + 2ll * L.totE;
-  const int total = pair_off[B];
-  int off_l[kNL];
-  {
-    int o = 0;
-    for (int l = 0; l < kNL; ++l) { off_l[l] = o; o += L.catE[l]; }
-  }
-
-  for (int p0 = blockIdx.x * kEdgeBwdWarps; p0 < total; p0 += gridDim.x * kEdgeBwdWarps) {
-    const int p = p0 + warp;
-    const bool act = p < total;
-    PairGeom g = PairGeom();
-    long long pair = 0;
-    if (act) {
-      const PairId id = decode_pair(p, B, pair_off, n_atoms);
-      const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)id.b * N * NLM * C;
-      g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
-      pair = ((long long)id.b * N + id.i) * N + id.j;
-      const float2* Eprev_ij = L.has_prev ? reinterpret_cast<const float2*>(E_prev) + pair * kNL * C : nullptr;
-      edge_build_cat<NLIN>(L, P, Wt_rad, g, Ab + (long long)id.i * NLM * C, Ab + (long long)id.j * NLM * C, Eprev_ij, sA, catbuf, f,
-                           lane);
-      const float2* dE_ij = reinterpret_cast<const float2*>(dE) + pair * kNL * C;
-      for (int idx = lane; idx < kNL * C; idx += 32) dpre[idx] = make_float2(dE_ij[idx].x * g.s, dE_ij[idx].y * g.s);
-    }
-    if (lane == 0) s_act[warp] = act ? 1 : 0;
-    __syncthreads();
-    // phase 2: all threads, (l, k) ownership; in place catbuf -> dcat
-    if (sl_l >= 0) {
-      for (int w = 0; w < kEdgeBwdWarps; ++w) {
-        if (!s_act[w]) continue;
-        float2* cb = smem + w * per_warp + cat_off;
-        const float2* dp_w = cb + L.sumCatE + 16 + sl_l * C;
-        const float2 xk = cb[sl_off + sl_k];
-        float2 dc = make_float2(0.f, 0.f);
-        MGB_UNROLL
-        for (int c = 0; c < kEdgeMaxC; ++c) {
-          if (c < C) {
-            const float2 gq = dp_w[c];
-            cfmacl(dwe[c], xk, gq);
-            cfmacl(dc, we[c], gq);
-          }
-        }
-        cb[sl_off + sl_k] = dc;
-      }
-    }
-    __syncthreads();
-    // phase 3a: all threads: radial weight / bias cotangents from dR (radial part of dcat) and f
-    for (int w = 0; w < kEdgeBwdWarps; ++w) {
-      if (!s_act[w]) continue;
-      const float* cbf = reinterpret_cast<const float*>(smem + w * per_warp + cat_off);
-      const float* fw = cbf + 2 * L.sumCatE;
-      MGB_UNROLL
-      for (int s = 0; s < kRadSlots; ++s)
-        if (rad_src[s] >= 0) drw[s] = fmaf(cbf[rad_src[s]], fw[rad_t[s]], drw[s]);
-      if (drb_src >= 0) drb += cbf[drb_src];
-    }
-    // phase 3b: per warp: previous-edge and dot cotangents out, scale/phase cotangents
-    if (act) {
-      if (L.has_prev) {
-        float2* dst = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C;
-        for (int idx = lane; idx < kNL * C; idx += 32) dst[idx] = catbuf[off_l[idx / C] + idx % C];
-      }
-      {
-        float2* dst = reinterpret_cast<float2*>(dD) + pair * kNL * C;
-        const int kdot = L.has_prev ? C : 0;
-        for (int idx = lane; idx < NLIN * C; idx += 32) {
-          float2 acc = make_float2(0.f, 0.f);
-          for (int l = 0; l < NLIN; ++l) { acc.x += catbuf[off_l[l] + kdot + idx].x; acc.y += catbuf[off_l[l] + kdot + idx].y; }
-          dst[idx] = acc;
-        }
-      }
-      // df[t] = sum_{l,o} W_l[o][t] dR_l[o]   (lane = t)
-      float df0 = 0.f, df1 = 0.f;
-      for (int l = 0; l < kNL; ++l) {
-        const float* dR = reinterpret_cast<const float*>(catbuf + off_l[l] + L.catE[l] - C);
-        const float* w = P + L.p_radW + (long long)l * C2 * kRadFeat + lane;   // reference layout [o][t]: lanes over t coalesce
-#pragma unroll 4
-        for (int oo = 0; oo < C2; oo += 2) {
-          df0 = fmaf(w[oo * kRadFeat], dR[oo], df0);
-          df1 = fmaf(w[(oo + 1) * kRadFeat], dR[oo + 1], df1);
-        }
-      }
-      float dval;
-      rad_feature(lane, g, P + L.p_scales, P + L.p_phases, &dval);
-      dph = fmaf(df0 + df1, dval, dph);
-      dsc = fmaf(df0 + df1, dval * kTwoPi * g.r, dsc);
-    }
-    __syncthreads();
-  }
-  // flush
-  if (sl_l >= 0) {
-    MGB_UNROLL
-    for (int c = 0; c < kEdgeMaxC; ++c) {
-      if (c < C) {
-        float* dst = grad + L.p_edgeW + 2ll * (L.offE[sl_l] + c * L.catE[sl_l] + sl_k);
-        if (dwe[c].x != 0.f) atomicAdd(dst, dwe[c].x);
-        if (dwe[c].y != 0.f) atomicAdd(dst + 1, dwe[c].y);
-      }
-    }
-  }
-  MGB_UNROLL
-  for (int s = 0; s < kRadSlots; ++s) {
-    const int e = threadIdx.x + s * kEdgeBwdThreads;
-    if (e < n_rad && drw[s] != 0.f) atomicAdd(grad + L.p_radW + e, drw[s]);
-  }
-  if ((int)threadIdx.x < kNL * C2 && drb != 0.f) atomicAdd(grad + L.p_radb + threadIdx.x, drb);
-  {
-    // lanes t = trig*4 + p share a (scale, phase): reduce over p inside the warp
-    dsc += __shfl_xor_sync(0xffffffffu, dsc, 1); dsc += __shfl_xor_sync(0xffffffffu, dsc, 2);
-    dph += __shfl_xor_sync(0xffffffffu, dph, 1); dph += __shfl_xor_sync(0xffffffffu, dph, 2);
-    if ((lane & 3) == 0) {
-      if (dsc != 0.f) atomicAdd(grad + L.p_scales + (lane >> 2), dsc);
-      if (dph != 0.f) atomicAdd(grad + L.p_phases + (lane >> 2), dph);
     }
   }
 }

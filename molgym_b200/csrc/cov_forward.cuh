@@ -134,22 +134,35 @@ __device__ __forceinline__ float rad_feature(int t, const PairGeom& g, const flo
 // ------------------------------------------------------------------------------------------------------------
 // Flat list of valid (b, i, j) pairs: pair_off[b] = sum_{b' < b} n_b'^2, pair_off[B] = total.  One CTA.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_pair_offsets(int B, const int* __restrict__ n_atoms, int* __restrict__ pair_off) {
-  __shared__ int part[1024];
+__global__ void k_pair_offsets(int B, int N, const int* __restrict__ n_atoms, int* __restrict__ pair_off, int* __restrict__ atom_off,
+                               int* __restrict__ atom_list) {
+  __shared__ int part[1024], parta[1024];
   const int per = (B + blockDim.x - 1) / blockDim.x;
   const int lo = threadIdx.x * per, hi = min(B, lo + per);
-  int sum = 0;
-  for (int b = lo; b < hi; ++b) sum += n_atoms[b] * n_atoms[b];
+  int sum = 0, suma = 0;
+  for (int b = lo; b < hi; ++b) { sum += n_atoms[b] * n_atoms[b]; suma += n_atoms[b]; }
   part[threadIdx.x] = sum;
+  parta[threadIdx.x] = suma;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int run = 0;
-    for (int t = 0; t < (int)blockDim.x; ++t) { const int v = part[t]; part[t] = run; run += v; }
+    int run = 0, runa = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      const int v = part[t], va = parta[t];
+      part[t] = run; parta[t] = runa;
+      run += v; runa += va;
+    }
     pair_off[B] = run;
+    atom_off[B] = runa;
   }
   __syncthreads();
-  int run = part[threadIdx.x];
-  for (int b = lo; b < hi; ++b) { pair_off[b] = run; run += n_atoms[b] * n_atoms[b]; }
+  int run = part[threadIdx.x], runa = parta[threadIdx.x];
+  for (int b = lo; b < hi; ++b) {
+    pair_off[b] = run;
+    atom_off[b] = runa;
+    for (int i = 0; i < n_atoms[b]; ++i) atom_list[runa + i] = b * N + i;   // flat list of valid atoms (slot index b*N + i)
+    run += n_atoms[b] * n_atoms[b];
+    runa += n_atoms[b];
+  }
 }
 
 struct PairId { int b, i, j; };
@@ -165,151 +178,7 @@ __device__ __forceinline__ PairId decode_pair(int p, int B, const int* __restric
   return id;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Edge level: E[b,i,j,l,c'] = s_ij * sum_k WE_l[c',k] catE_ijl[k],  catE = [E_prev | dot(A_i, A_j) | radial_l]
-// (cormorant CormorantEdgeLevel: DotMatrix + CatMixRepsScalar + MaskLevel).  One warp per valid pair of the minibatch.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kEdgeThreads = 256;
-
-__host__ __device__ inline int edge_warp_floats2(const LevelDesc& L, bool backward) {
-  return 2 * L.nlm_in * L.C + L.sumCatE + 16 + (backward ? kNL * L.C : 0);
-}
-
-// Fills the per-warp cat buffer for one pair; returns with the warp synchronised.  catbuf: [sumCatE] complex, l-major.
-// f: [32] radial features (written here).  sA: [2][NLM][C] staging for A_i, A_j.  Also used by the backward kernel.
-template <int NLIN>
-__device__ __forceinline__ void edge_build_cat(const LevelDesc& L, const float* __restrict__ P, const float* __restrict__ Wt_rad,
-                                               const PairGeom& g, const float2* __restrict__ Ai, const float2* __restrict__ Aj,
-                                               const float2* __restrict__ Eprev_ij, float2* sA, float2* catbuf, float* f, int lane) {
-  const int C = L.C, C2 = 2 * C;
-  constexpr int NLM = NLIN * NLIN;
-  for (int idx = lane; idx < NLM * C; idx += 32) { sA[idx] = Ai[idx]; sA[NLM * C + idx] = Aj[idx]; }
-  f[lane] = rad_feature(lane, g, P + L.p_scales, P + L.p_phases, nullptr);
-  int off_l[kNL];
-  {
-    int o = 0;
-    for (int l = 0; l < kNL; ++l) { off_l[l] = o; o += L.catE[l]; }
-  }
-  if (L.has_prev) {
-    for (int idx = lane; idx < kNL * C; idx += 32) {
-      const int l = idx / C, c = idx - l * C;
-      catbuf[off_l[l] + c] = Eprev_ij[idx];
-    }
-  }
-  __syncwarp();
-  // radial filters: R_l[o] = b_l[o] + sum_t W_l[o][t] f[t]   (Wt_rad: [l][t][2C]); each lane owns <= 4 outputs
-  {
-    float acc[4];
-    const float* wp[4];
-    bool on[4];
-    MGB_UNROLL
-    for (int r = 0; r < 4; ++r) {
-      const int idx = lane + 32 * r;
-      on[r] = idx < kNL * C2;
-      const int l = on[r] ? idx / C2 : 0, o = on[r] ? idx - l * C2 : 0;
-      acc[r] = on[r] ? P[L.p_radb + l * C2 + o] : 0.f;
-      wp[r] = Wt_rad + (long long)l * kRadFeat * C2 + o;
-    }
-    MGB_UNROLL
-    for (int r = 0; r < 4; ++r)
-      if (!on[r]) wp[r] = Wt_rad;   // valid address, result discarded
-#pragma unroll 4
-    for (int t = 0; t < kRadFeat; t += 2) {
-      float wv[2][4];
-      MGB_UNROLL
-      for (int r = 0; r < 4; ++r) { wv[0][r] = wp[r][t * C2]; wv[1][r] = wp[r][(t + 1) * C2]; }
-      const float f0 = f[t], f1 = f[t + 1];
-      MGB_UNROLL
-      for (int r = 0; r < 4; ++r) acc[r] = fmaf(wv[1][r], f1, fmaf(wv[0][r], f0, acc[r]));
-    }
-    MGB_UNROLL
-    for (int r = 0; r < 4; ++r) {
-      const int idx = lane + 32 * r;
-      if (on[r]) {
-        const int l = idx / C2, o = idx - l * C2;
-        reinterpret_cast<float*>(catbuf + off_l[l] + L.catE[l] - C)[o] = acc[r];   // radial block is last
-      }
-    }
-  }
-  // dot matrix D[l',c] = sum_m (-1)^m A_i[l',m,c] A_j[l',-m,c]
-  for (int idx = lane; idx < NLIN * C; idx += 32) {
-    const int lp = idx / C, c = idx - lp * C;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int m = -lp; m <= lp; ++m) {
-      const float2 pr = cmul(sA[lm_index(lp, m) * C + c], sA[NLM * C + lm_index(lp, -m) * C + c]);
-      if (m & 1) { acc.x -= pr.x; acc.y -= pr.y; } else { acc.x += pr.x; acc.y += pr.y; }
-    }
-    const int kdot = L.has_prev ? C : 0;
-    for (int l = 0; l < NLIN; ++l) catbuf[off_l[l] + kdot + idx] = acc;
-  }
-  __syncwarp();
-}
-
-template <int NLIN>
-__global__ void __launch_bounds__(kEdgeThreads)
-k_edge_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
-           const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
-           const float* __restrict__ A_in, const float* __restrict__ E_prev, float* __restrict__ E_out) {
-  const CovDesc& d = *dp;
-  const LevelDesc& L = d.lv[level];
-  const int N = d.N, C = L.C;
-  constexpr int NLM = NLIN * NLIN;
-  MGB_DYN_SMEM(float2, smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float2* sA = smem + warp * edge_warp_floats2(L, false);
-  float2* catbuf = sA + 2 * NLM * C;
-  float* f = reinterpret_cast<float*>(catbuf + L.sumCatE);
-  const float* Wt_rad = Wt + d.wt_edge[level] + 2ll * L.totE;  // radial transposes follow the edge weights
-  const float2* WEt = reinterpret_cast<const float2*>(Wt + d.wt_edge[level]);
-  const int total = pair_off[B];
-  for (int p = blockIdx.x * nwarps + warp; p < total; p += gridDim.x * nwarps) {
-    const PairId id = decode_pair(p, B, pair_off, n_atoms);
-    const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)id.b * N * NLM * C;
-    const PairGeom g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
-    const long long pair = ((long long)id.b * N + id.i) * N + id.j;
-    const float2* Eprev_ij = L.has_prev ? reinterpret_cast<const float2*>(E_prev) + pair * kNL * C : nullptr;
-    edge_build_cat<NLIN>(L, P, Wt_rad, g, Ab + (long long)id.i * NLM * C, Ab + (long long)id.j * NLM * C, Eprev_ij, sA, catbuf, f,
-                         lane);
-    float2* Eo = reinterpret_cast<float2*>(E_out) + pair * kNL * C;
-    // mix: lane owns outputs idx = lane, lane + 32 of the 5*C
-    float2 acc[2];
-    const float2* w[2];
-    const float2* x[2];
-    int K[2], Kmax = 0;
-    MGB_UNROLL
-    for (int r = 0; r < 2; ++r) {
-      const int idx = lane + 32 * r;
-      const bool on = idx < kNL * C;
-      const int l = on ? idx / C : 0, cp = on ? idx - l * C : 0;
-      int off = 0;
-      for (int q = 0; q < l; ++q) off += L.catE[q];
-      w[r] = WEt + L.offE[l] + cp;   // [k][c']
-      x[r] = catbuf + off;
-      K[r] = on ? L.catE[l] : 0;
-      Kmax = max(Kmax, K[r]);
-      acc[r] = make_float2(0.f, 0.f);
-    }
-    // rows beyond K[r] multiply a zero-padded x (catbuf rows are read clamped, weight reads stay inside the level's block)
-#pragma unroll 4
-    for (int k = 0; k < Kmax; ++k) {
-      float2 wv[2], xv[2];
-      MGB_UNROLL
-      for (int r = 0; r < 2; ++r) {
-        const int kk = k < K[r] ? k : 0;
-        wv[r] = w[r][kk * C];
-        xv[r] = k < K[r] ? x[r][kk] : make_float2(0.f, 0.f);
-      }
-      MGB_UNROLL
-      for (int r = 0; r < 2; ++r) cfma(acc[r], wv[r], xv[r]);
-    }
-    MGB_UNROLL
-    for (int r = 0; r < 2; ++r) {
-      const int idx = lane + 32 * r;
-      if (idx < kNL * C) Eo[idx] = make_float2(acc[r].x * g.s, acc[r].y * g.s);
-    }
-    __syncwarp();
-  }
-}
+// (the edge level lives in edge.cuh)
 
 // ------------------------------------------------------------------------------------------------------------
 // Channel mixing out of shared memory: out[l, m, c'] = sum_k W_l[c', k] cat_l[m][k]  (complex), one warp per unit of
@@ -401,14 +270,14 @@ __device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2*
 //   ag = CG T ; sq = CG (A_i x A_i) ; cat_l = [ag | A_i | sq] ; A_out[l, m, c'] = sum_k W_l[c', k] cat_l[m][k]
 // One CTA per (b, i).  The cat vector is also written to HBM: the weight-gradient kernel reads it back.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kAtomThreads = 512;
+constexpr int kAtomThreads = 256;
 constexpr int kJChunk = 8;
 
 __host__ __device__ inline int atom_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
   const int stage = kJChunk * (kNL * L.C + nlm2 * L.C) * 2;
   const int tsz = kM * nlm2 * L.C * 2;
-  return (stage > tsz ? stage : tsz) + L.totA * 2 + nlm2 * L.C * 2 + N * kM * 2;
+  return (stage > tsz ? stage : tsz) + nlm2 * L.C * 2 + N * kM * 2;
 }
 
 // Y_lm(r_i - r_j) for every neighbour j of atom i, once per CTA (conj, 'unit' norm, un-normalised argument:
@@ -432,28 +301,30 @@ __device__ __forceinline__ void stage_neighbours(const LevelDesc& L, const float
   for (int idx = threadIdx.x; idx < nj * NLM2 * C; idx += blockDim.x) sAj[idx] = Ab[(long long)j0 * NLM2 * C + idx];
 }
 
-template <int NLM2, int CO, int NM>
+// cg_gather writes straight to the atom's cat vector in HBM (coalesced over the channel index).
+template <int NLM2>
 __global__ void __launch_bounds__(kAtomThreads)
-k_atom_fwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ P, const float* __restrict__ pos,
-           const int* __restrict__ n_atoms, const float* __restrict__ A_in, const float* __restrict__ E,
-           float* __restrict__ cat_out, float* __restrict__ A_out) {
+k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ pos, const int* __restrict__ n_atoms,
+           const int* __restrict__ atom_off, const int* __restrict__ atom_list, int B, const float* __restrict__ A_in,
+           const float* __restrict__ E, float* __restrict__ cat_out) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C;
-  const int b = blockIdx.x / N, i = blockIdx.x % N;
+  if ((int)blockIdx.x >= atom_off[B]) return;
+  const int slot = atom_list[blockIdx.x];
+  const int b = slot / N, i = slot - b * N;
   const int n = n_atoms[b];
-  if (i >= n) return;
   MGB_DYN_SMEM(float2, smem);
   const int stage = kJChunk * (kNL * C + NLM2 * C), tsz = kM * NLM2 * C;
   float2* sT = smem;
   float2* sE = smem;
   float2* sAj = sE + kJChunk * kNL * C;
-  float2* sCat = smem + (stage > tsz ? stage : tsz);
-  float2* sAi = sCat + L.totA;
+  float2* sAi = smem + (stage > tsz ? stage : tsz);
   float2* sYall = sAi + NLM2 * C;
   const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
   const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
   const float* pos_b = pos + (long long)b * N * 3;
+  float2* co = reinterpret_cast<float2*>(cat_out) + (long long)slot * L.totA;
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
   neighbour_harmonics(pos_b, i, n, sYall);
 
@@ -483,21 +354,101 @@ k_atom_fwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int q = 0; q < NLM2; ++q) sT[(lm1 * NLM2 + q) * C + c] = acc[q];
   }
   __syncthreads();
-  cg_gather<false>(L.ag, C, sT, sCat);
-  cg_gather<true>(L.sq, C, sAi, sCat);
+  cg_gather<false>(L.ag, C, sT, co);
+  cg_gather<true>(L.sq, C, sAi, co);
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) {
     const int lm = idx / C, cc = idx % C, l = ell_of_lm(lm);
-    sCat[L.offA[l] + (lm - l * l) * L.catA[l] + L.in_block[l] * C + cc] = sAi[idx];
+    co[L.offA[l] + (lm - l * l) * L.catA[l] + L.in_block[l] * C + cc] = sAi[idx];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Channel mix as a row-parallel kernel: one thread per (valid atom, l, m) row of the cat vector,
+//   out[row][c'] = sum_k W_l[c'][k] cat[row][k]      (forward)
+//   dcat[row][k] = sum_c' conj(W_l[c'][k]) dOut[row][c']   (backward)
+// W_l transposed to [k][c'] sits in shared memory and is read as warp-uniform (broadcast) vector loads; the accumulators
+// are registers; no cross-lane reduction.  grid = (row blocks, 5 ells).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMixThreads = 128;
+
+template <int CO, bool BACKWARD, int KS>
+__global__ void __launch_bounds__(kMixThreads)
+k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ Wt, const int* __restrict__ atom_off,
+           const int* __restrict__ atom_list, int B, const float* __restrict__ cat, const float* __restrict__ A_out,
+           float* __restrict__ out) {
+  // KS adjacent lanes share a row and split its k range (k = ks, ks + KS, ...): more parallelism for small minibatches and
+  // coalesced reads of the row; the forward reduces the KS partial sums with shuffles, the backward needs no reduction.
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1, Cout = L.Cout;
+  const int rows = atom_off[B] * nm;
+  constexpr int kRowsPerCta = kMixThreads / KS;
+  if ((int)(blockIdx.x * kRowsPerCta) >= rows) return;
+  MGB_DYN_SMEM(float2, sW);   // [K][CO]
+  {
+    const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_atom[level]) + L.offWA[l];   // [k][c'] (transposed by k_prep_params)
+    for (int idx = threadIdx.x; idx < K * CO; idx += blockDim.x) {
+      const int k = idx / CO, c = idx - k * CO;
+      sW[idx] = c < Cout ? src[k * Cout + c] : make_float2(0.f, 0.f);
+    }
   }
   __syncthreads();
-  if (cat_out) {
-    float2* co = reinterpret_cast<float2*>(cat_out) + ((long long)b * N + i) * L.totA;
-    for (int idx = threadIdx.x; idx < L.totA; idx += blockDim.x) co[idx] = sCat[idx];
+  const int ks = threadIdx.x % KS;
+  const int row_raw = blockIdx.x * kRowsPerCta + threadIdx.x / KS;
+  const bool valid = row_raw < rows;
+  const int row = valid ? row_raw : rows - 1;   // clamp: every lane takes part in the shuffles
+  const int a = row / nm, m = row - a * nm;
+  const long long slot = atom_list[a];
+  const float2* crow = reinterpret_cast<const float2*>(cat) + slot * L.totA + L.offA[l] + m * K;
+  const long long orow = (slot * kM + l * l + m) * Cout;
+  if (!BACKWARD) {
+    float2 acc[CO];
+    MGB_UNROLL
+    for (int c = 0; c < CO; ++c) acc[c] = make_float2(0.f, 0.f);
+    int k = ks;
+    for (; k + 3 * KS < K; k += 4 * KS) {
+      float2 x[4];
+      MGB_UNROLL
+      for (int q = 0; q < 4; ++q) x[q] = crow[k + q * KS];
+      MGB_UNROLL
+      for (int q = 0; q < 4; ++q)
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) cfma(acc[c], sW[(k + q * KS) * CO + c], x[q]);
+    }
+    for (; k < K; k += KS) {
+      const float2 x = crow[k];
+      MGB_UNROLL
+      for (int c = 0; c < CO; ++c) cfma(acc[c], sW[k * CO + c], x);
+    }
+    MGB_UNROLL
+    for (int c = 0; c < CO; ++c) {
+      MGB_UNROLL
+      for (int o = KS / 2; o > 0; o >>= 1) {
+        acc[c].x += __shfl_xor_sync(0xffffffffu, acc[c].x, o);
+        acc[c].y += __shfl_xor_sync(0xffffffffu, acc[c].y, o);
+      }
+    }
+    if (valid && ks == 0) {
+      float2* o = reinterpret_cast<float2*>(out) + orow;
+      MGB_UNROLL
+      for (int c = 0; c < CO; ++c)
+        if (c < Cout) o[c] = acc[c];
+    }
+  } else {
+    float2 g[CO];
+    const float2* gi = reinterpret_cast<const float2*>(A_out) + orow;
+    MGB_UNROLL
+    for (int c = 0; c < CO; ++c) g[c] = c < Cout ? gi[c] : make_float2(0.f, 0.f);
+    float2* o = reinterpret_cast<float2*>(out) + slot * L.totA + L.offA[l] + m * K;
+    if (valid) {
+      for (int k = ks; k < K; k += KS) {
+        float2 acc = make_float2(0.f, 0.f);
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) cfmacl(acc, sW[k * CO + c], g[c]);
+        o[k] = acc;
+      }
+    }
   }
-  const bool last = (level == d.K - 1);
-  mix_rows<CO, NM>(last ? d.units_out : d.units_hidden, last ? d.n_units_out : d.n_units_hidden, L.catA, L.offA, L.offWA,
-                   L.Cout, reinterpret_cast<const float2*>(P + L.p_atomW), sCat,
-                   reinterpret_cast<float2*>(A_out) + ((long long)b * N + i) * kM * L.Cout);
 }
 
 // ------------------------------------------------------------------------------------------------------------

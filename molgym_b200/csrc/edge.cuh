@@ -1,0 +1,381 @@
+// edge.cuh — the Cormorant edge level (cormorant CormorantEdgeLevel: DotMatrix + CatMixRepsScalar + MaskLevel; called from
+// molgym/agents/covariant/modules.py:110) as thread-per-pair kernels.
+//
+//   E[b,i,j,l,c'] = s_ij * sum_k WE_l[c',k] catE_ijl[k],   catE_l = [E_prev_l (C) | dot(A_i, A_j) (nLin*C) | radial_l (C)]
+//
+// Layout of the work: the flat list of valid (b, i, j) pairs (pair_off) is walked with ONE THREAD PER PAIR; all lanes of a
+// warp work on the same ell, so the mixing weights are warp-uniform and are read from shared memory as broadcast loads
+// while the accumulators stay in registers.  The dot matrix is its own per-canvas kernel (it is symmetric in (i, j) and
+// only needs the atom representations).  Weight cotangents are reductions over pairs and run as a separate kernel.
+#pragma once
+#include "cov_forward.cuh"
+
+namespace mgb {
+
+constexpr int kEdgeC = 10;          // register tile over the (<= 10) hidden channels
+constexpr int kPairThreads = 128;
+
+// radial basis of one pair: f[t], t = trig*4 + p (RadPolyTrig), and optionally d f[t] / d(arg_t)
+__device__ __forceinline__ void rad_features_all(const PairGeom& g, const float* __restrict__ scales, const float* __restrict__ phases,
+                                                 float* f, float* dfdarg) {
+  const float inv = g.mrad ? 1.f / g.r : 0.f;
+  const float pw[4] = {1.f, inv, inv * inv, inv * inv * inv};
+  MGB_UNROLL
+  for (int tt = 0; tt < kTrig; ++tt) {
+    const float arg = __fadd_rn(__fmul_rn(__fmul_rn(kTwoPi, scales[tt]), g.r), phases[tt]);
+    const float sv = g.mrad ? sinf(arg) : 0.f;
+    const float cv = (dfdarg && g.mrad) ? cosf(arg) : 0.f;
+    MGB_UNROLL
+    for (int p = 0; p < 4; ++p) {
+      f[tt * 4 + p] = sv * pw[p];
+      if (dfdarg) dfdarg[tt * 4 + p] = cv * pw[p];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Dot matrix D[b,i,j,l',c] = sum_m (-1)^m A_i[l',m,c] A_j[l',-m,c]  (cormorant DotMatrix).  One CTA per canvas.
+// ------------------------------------------------------------------------------------------------------------
+template <int NLIN>
+__global__ void __launch_bounds__(256)
+k_dot_fwd(const CovDesc* __restrict__ dp, int level, const int* __restrict__ n_atoms, const float* __restrict__ A_in,
+          float* __restrict__ D) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, b = blockIdx.x;
+  constexpr int NLM = NLIN * NLIN;
+  const int n = n_atoms[b];
+  if (n == 0) return;
+  MGB_DYN_SMEM(float2, sA);   // [n][NLM][C]
+  const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM * C;
+  for (int idx = threadIdx.x; idx < n * NLM * C; idx += blockDim.x) sA[idx] = Ab[idx];
+  __syncthreads();
+  float2* Db = reinterpret_cast<float2*>(D) + (long long)b * N * N * kNL * C;
+  const int per = NLIN * C, total = n * n * per;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pr = idx / per, r = idx - pr * per, lp = r / C, c = r - lp * C;
+    const int i = pr / n, j = pr - i * n;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int m = -lp; m <= lp; ++m) {
+      const float2 v = cmul(sA[(i * NLM + lm_index(lp, m)) * C + c], sA[(j * NLM + lm_index(lp, -m)) * C + c]);
+      if (m & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+    }
+    Db[((long long)i * N + j) * kNL * C + r] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Forward: grid = (pair blocks, 5 ells), one thread per pair.
+// ------------------------------------------------------------------------------------------------------------
+template <int NLIN>
+__global__ void __launch_bounds__(kPairThreads)
+k_edge_pairs_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
+                 const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
+                 const float* __restrict__ D, const float* __restrict__ E_prev, float* __restrict__ E_out) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
+  const int total = pair_off[B];
+  if ((int)(blockIdx.x * blockDim.x) >= total) return;
+  MGB_DYN_SMEM(float2, smem);
+  float2* sW = smem;                                          // [K][kEdgeC]   WE_l transposed ([k][c'])
+  float* sRad = reinterpret_cast<float*>(sW + K * kEdgeC);    // [2C][32] radial linear of this ell + [2C] bias
+  {
+    const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_edge[level]) + L.offE[l];
+    for (int idx = threadIdx.x; idx < K * kEdgeC; idx += blockDim.x) {
+      const int k = idx / kEdgeC, c = idx - k * kEdgeC;
+      sW[idx] = c < C ? src[k * C + c] : make_float2(0.f, 0.f);
+    }
+    for (int idx = threadIdx.x; idx < C2 * kRadFeat; idx += blockDim.x) sRad[idx] = P[L.p_radW + (long long)l * C2 * kRadFeat + idx];
+    for (int idx = threadIdx.x; idx < C2; idx += blockDim.x) sRad[C2 * kRadFeat + idx] = P[L.p_radb + l * C2 + idx];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const PairId id = decode_pair(p, B, pair_off, n_atoms);
+  const PairGeom g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
+  const long long pair = ((long long)id.b * N + id.i) * N + id.j;
+  float2 acc[kEdgeC];
+  MGB_UNROLL
+  for (int c = 0; c < kEdgeC; ++c) acc[c] = make_float2(0.f, 0.f);
+  int kk = 0;
+  if (L.has_prev) {
+    const float2* x = reinterpret_cast<const float2*>(E_prev) + pair * kNL * C + l * C;
+    for (int k = 0; k < C; ++k) {
+      const float2 xv = x[k];
+      MGB_UNROLL
+      for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+    }
+    kk += C;
+  }
+  if (l < NLIN) {
+    const float2* x = reinterpret_cast<const float2*>(D) + pair * kNL * C;
+#pragma unroll 2
+    for (int k = 0; k < NLIN * C; ++k) {
+      const float2 xv = x[k];
+      MGB_UNROLL
+      for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+    }
+    kk += NLIN * C;
+  }
+  {
+    float f[kRadFeat];
+    rad_features_all(g, P + L.p_scales, P + L.p_phases, f, nullptr);
+    for (int k = 0; k < C; ++k) {
+      float re = sRad[C2 * kRadFeat + 2 * k], im = sRad[C2 * kRadFeat + 2 * k + 1];
+      const float* wr = sRad + (2 * k) * kRadFeat;
+      MGB_UNROLL
+      for (int t = 0; t < kRadFeat; ++t) { re = fmaf(wr[t], f[t], re); im = fmaf(wr[kRadFeat + t], f[t], im); }
+      const float2 xv = make_float2(re, im);
+      MGB_UNROLL
+      for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+    }
+  }
+  float2* Eo = reinterpret_cast<float2*>(E_out) + pair * kNL * C + l * C;
+  MGB_UNROLL
+  for (int c = 0; c < kEdgeC; ++c)
+    if (c < C) Eo[c] = make_float2(acc[c].x * g.s, acc[c].y * g.s);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward, per-pair part: one thread per pair, loop over the five ells.
+//   reads  dE[pair][l][c']                      (cotangent of this level's edge scalars)
+//   writes dE_prev[pair][l][k] (assigned), dD[pair][l'*C + c] (assigned),
+//          scratch for the weight-gradient kernel: dpre[pair][l][c'] = s dE, R[pair][l][2C] (radial filter values),
+//          dR[pair][l][2C], f[pair][32];  accumulates the radial scale / phase cotangents (per-thread, then atomics).
+// ------------------------------------------------------------------------------------------------------------
+struct EdgeScratch {
+  float* dpre;   // [pairs][5][C][2]
+  float* R;      // [pairs][5][2C]
+  float* dR;     // [pairs][5][2C]
+  float* f;      // [pairs][32]
+};
+
+template <int NLIN>
+__global__ void __launch_bounds__(kPairThreads)
+k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ pos,
+                 const int* __restrict__ n_atoms, const int* __restrict__ pair_off, const float* __restrict__ dE,
+                 float* __restrict__ dE_prev, float* __restrict__ dD, EdgeScratch sc, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, C2 = 2 * C;
+  const int total = pair_off[B];
+  if ((int)(blockIdx.x * blockDim.x) >= total) return;
+  MGB_DYN_SMEM(float2, smem);
+  float2* sW = smem;                                              // [sumCatE][kEdgeC]: WE in the REFERENCE layout per ell, [k][c'] padded
+  float* sRad = reinterpret_cast<float*>(sW + L.sumCatE * kEdgeC);   // [5][2C][32] + [5][2C]
+  {
+    int off = 0;
+    for (int l = 0; l < kNL; ++l) {
+      const float2* src = reinterpret_cast<const float2*>(P + L.p_edgeW) + L.offE[l];   // [c'][k]
+      const int K = L.catE[l];
+      for (int idx = threadIdx.x; idx < K * kEdgeC; idx += blockDim.x) {
+        const int k = idx / kEdgeC, c = idx - k * kEdgeC;
+        sW[off * kEdgeC + idx] = c < C ? src[c * K + k] : make_float2(0.f, 0.f);
+      }
+      off += K;
+    }
+    for (int idx = threadIdx.x; idx < kNL * C2 * kRadFeat; idx += blockDim.x) sRad[idx] = P[L.p_radW + idx];
+    for (int idx = threadIdx.x; idx < kNL * C2; idx += blockDim.x) sRad[kNL * C2 * kRadFeat + idx] = P[L.p_radb + idx];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float dsc[kTrig], dph[kTrig];
+  MGB_UNROLL
+  for (int t = 0; t < kTrig; ++t) { dsc[t] = 0.f; dph[t] = 0.f; }
+  if (p < total) {
+    const PairId id = decode_pair(p, B, pair_off, n_atoms);
+    const PairGeom g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
+    const long long pair = ((long long)id.b * N + id.i) * N + id.j;
+    float f[kRadFeat], df[kRadFeat];
+    rad_features_all(g, P + L.p_scales, P + L.p_phases, f, nullptr);
+    MGB_UNROLL
+    for (int t = 0; t < kRadFeat; ++t) { df[t] = 0.f; sc.f[(long long)p * kRadFeat + t] = f[t]; }
+    float2 dDacc[NLIN * kEdgeC];
+    MGB_UNROLL
+    for (int k = 0; k < NLIN * kEdgeC; ++k) dDacc[k] = make_float2(0.f, 0.f);
+    int off = 0;
+    for (int l = 0; l < kNL; ++l) {
+      float2 dpre[kEdgeC];
+      const float2* g_in = reinterpret_cast<const float2*>(dE) + pair * kNL * C + l * C;
+      MGB_UNROLL
+      for (int c = 0; c < kEdgeC; ++c) {
+        dpre[c] = c < C ? make_float2(g_in[c].x * g.s, g_in[c].y * g.s) : make_float2(0.f, 0.f);
+        if (c < C) reinterpret_cast<float2*>(sc.dpre)[((long long)p * kNL + l) * C + c] = dpre[c];
+      }
+      const float2* Wl = sW + off * kEdgeC;
+      int kk = 0;
+      if (L.has_prev) {
+        float2* o = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C + l * C;
+        for (int k = 0; k < C; ++k) {
+          float2 a = make_float2(0.f, 0.f);
+          MGB_UNROLL
+          for (int c = 0; c < kEdgeC; ++c) cfmacl(a, Wl[(kk + k) * kEdgeC + c], dpre[c]);
+          o[k] = a;
+        }
+        kk += C;
+      }
+      if (l < NLIN) {
+        MGB_UNROLL
+        for (int lp = 0; lp < NLIN; ++lp)
+          MGB_UNROLL
+          for (int cc = 0; cc < kEdgeC; ++cc) {
+            if (cc < C) {
+              MGB_UNROLL
+              for (int c = 0; c < kEdgeC; ++c) cfmacl(dDacc[lp * kEdgeC + cc], Wl[(kk + lp * C + cc) * kEdgeC + c], dpre[c]);
+            }
+          }
+        kk += NLIN * C;
+      }
+      // radial part: R_l (forward value, recomputed) and its cotangent
+      for (int k = 0; k < C; ++k) {
+        float2 a = make_float2(0.f, 0.f);
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) cfmacl(a, Wl[(kk + k) * kEdgeC + c], dpre[c]);
+        const float* wr = sRad + ((l * C2) + 2 * k) * kRadFeat;
+        float re = sRad[kNL * C2 * kRadFeat + l * C2 + 2 * k], im = sRad[kNL * C2 * kRadFeat + l * C2 + 2 * k + 1];
+        MGB_UNROLL
+        for (int t = 0; t < kRadFeat; ++t) {
+          re = fmaf(wr[t], f[t], re);
+          im = fmaf(wr[kRadFeat + t], f[t], im);
+          df[t] = fmaf(wr[t], a.x, fmaf(wr[kRadFeat + t], a.y, df[t]));
+        }
+        sc.R[((long long)p * kNL + l) * C2 + 2 * k] = re;
+        sc.R[((long long)p * kNL + l) * C2 + 2 * k + 1] = im;
+        sc.dR[((long long)p * kNL + l) * C2 + 2 * k] = a.x;
+        sc.dR[((long long)p * kNL + l) * C2 + 2 * k + 1] = a.y;
+      }
+      off += L.catE[l];
+    }
+    float2* od = reinterpret_cast<float2*>(dD) + pair * kNL * C;
+    MGB_UNROLL
+    for (int lp = 0; lp < NLIN; ++lp)
+      MGB_UNROLL
+      for (int cc = 0; cc < kEdgeC; ++cc)
+        if (cc < C) od[lp * C + cc] = dDacc[lp * kEdgeC + cc];
+    {   // f is no longer needed: reuse its registers for d f[t] / d arg_t = cos(arg) r^-p
+      float tmp[kRadFeat];
+      rad_features_all(g, P + L.p_scales, P + L.p_phases, tmp, f);
+    }
+    MGB_UNROLL
+    for (int t = 0; t < kRadFeat; ++t) {
+      const float gv = df[t] * f[t];
+      dph[t >> 2] += gv;
+      dsc[t >> 2] = fmaf(gv, kTwoPi * g.r, dsc[t >> 2]);
+    }
+  }
+  // scale / phase cotangents: warp reduction, one atomic per warp and parameter
+  MGB_UNROLL
+  for (int t = 0; t < kTrig; ++t) {
+    const float a = warp_sum(dsc[t]), b2 = warp_sum(dph[t]);
+    if ((threadIdx.x & 31) == 0) {
+      if (a != 0.f) atomicAdd(grad + L.p_scales + t, a);
+      if (b2 != 0.f) atomicAdd(grad + L.p_phases + t, b2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward, weight cotangents (reductions over pairs).  grid = (pair chunks, 5 ells), 128 threads:
+//   threads 0 .. K_l-1     : dWE_l[c'][k] += sum_p conj(cat_l[p][k]) dpre_l[p][c']     (10 complex accumulators each)
+//   threads K_l .. 127     : dWrad_l[o][t] += sum_p dR_l[p][o] f[p][t], db_l[o] += sum_p dR_l[p][o]
+// cat_l[p] = [E_prev[p][l] | D[p] | R[p][l]] is read straight from HBM (coalesced over k); dpre / dR / f of a sub-chunk of
+// pairs are staged in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kEdgeDwThreads = 128;
+constexpr int kEdgeDwSub = 32;
+constexpr int kEdgeDwRadSlots = 12;   // ceil(2*10*33 / (128 - 70))
+
+template <int NLIN>
+__global__ void __launch_bounds__(kEdgeDwThreads)
+k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
+          const float* __restrict__ E_prev, const float* __restrict__ D, EdgeScratch sc, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
+  const int total = pair_off[B];
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int p_begin = per * blockIdx.x, p_end = min(total, p_begin + per);
+  if (p_begin >= p_end) return;
+  __shared__ float2 s_dpre[kEdgeDwSub][kEdgeC];
+  __shared__ float s_dR[kEdgeDwSub][2 * kEdgeC];
+  __shared__ float s_f[kEdgeDwSub][kRadFeat];
+  __shared__ long long s_pair[kEdgeDwSub];
+  const int tid = threadIdx.x;
+  const bool edge_thread = tid < K;
+  // which segment of cat_l does this thread's k live in?
+  const int kprev = L.has_prev ? C : 0, kdot = (l < NLIN) ? NLIN * C : 0;
+  float2 acc[kEdgeC];
+  MGB_UNROLL
+  for (int c = 0; c < kEdgeC; ++c) acc[c] = make_float2(0.f, 0.f);
+  // radial entries owned by the non-edge threads: e = (tid - K) + s * n_rad_threads over [2C][33] (column 32 = bias)
+  const int n_rad_threads = kEdgeDwThreads - K, n_rad = C2 * (kRadFeat + 1);
+  float racc[kEdgeDwRadSlots];
+  MGB_UNROLL
+  for (int s = 0; s < kEdgeDwRadSlots; ++s) racc[s] = 0.f;
+  for (int p0 = p_begin; p0 < p_end; p0 += kEdgeDwSub) {
+    const int np = min(kEdgeDwSub, p_end - p0);
+    __syncthreads();
+    if (tid < np) {
+      const PairId id = decode_pair(p0 + tid, B, pair_off, n_atoms);
+      s_pair[tid] = ((long long)id.b * N + id.i) * N + id.j;
+    }
+    for (int idx = tid; idx < np * C; idx += blockDim.x) {
+      const int q = idx / C, c = idx - q * C;
+      s_dpre[q][c] = reinterpret_cast<const float2*>(sc.dpre)[((long long)(p0 + q) * kNL + l) * C + c];
+    }
+    for (int idx = tid; idx < np * C2; idx += blockDim.x) {
+      const int q = idx / C2, o = idx - q * C2;
+      s_dR[q][o] = sc.dR[((long long)(p0 + q) * kNL + l) * C2 + o];
+    }
+    for (int idx = tid; idx < np * kRadFeat; idx += blockDim.x) s_f[idx / kRadFeat][idx % kRadFeat] = sc.f[(long long)p0 * kRadFeat + idx];
+    __syncthreads();
+    if (edge_thread) {
+#pragma unroll 4
+      for (int q = 0; q < np; ++q) {
+        float2 x;
+        if (tid < kprev) x = reinterpret_cast<const float2*>(E_prev)[s_pair[q] * kNL * C + l * C + tid];
+        else if (tid < kprev + kdot) x = reinterpret_cast<const float2*>(D)[s_pair[q] * kNL * C + (tid - kprev)];
+        else {
+          const float* r = sc.R + ((long long)(p0 + q) * kNL + l) * C2 + 2 * (tid - kprev - kdot);
+          x = make_float2(r[0], r[1]);
+        }
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) cfmacl(acc[c], x, s_dpre[q][c]);
+      }
+    } else {
+      for (int q = 0; q < np; ++q) {
+        MGB_UNROLL
+        for (int s = 0; s < kEdgeDwRadSlots; ++s) {
+          const int e = (tid - K) + s * n_rad_threads;
+          if (e < n_rad) {
+            const int o = e / (kRadFeat + 1), t = e - o * (kRadFeat + 1);
+            racc[s] = fmaf(s_dR[q][o], t < kRadFeat ? s_f[q][t] : 1.f, racc[s]);
+          }
+        }
+      }
+    }
+  }
+  if (edge_thread) {
+    MGB_UNROLL
+    for (int c = 0; c < kEdgeC; ++c) {
+      if (c < C) {
+        float* dst = grad + L.p_edgeW + 2ll * (L.offE[l] + c * K + tid);
+        if (acc[c].x != 0.f) atomicAdd(dst, acc[c].x);
+        if (acc[c].y != 0.f) atomicAdd(dst + 1, acc[c].y);
+      }
+    }
+  } else {
+    MGB_UNROLL
+    for (int s = 0; s < kEdgeDwRadSlots; ++s) {
+      const int e = (tid - K) + s * n_rad_threads;
+      if (e < n_rad && racc[s] != 0.f) {
+        const int o = e / (kRadFeat + 1), t = e - o * (kRadFeat + 1);
+        if (t < kRadFeat) atomicAdd(grad + L.p_radW + ((long long)l * C2 + o) * kRadFeat + t, racc[s]);
+        else atomicAdd(grad + L.p_radb + l * C2 + o, racc[s]);
+      }
+    }
+  }
+}
+
+}  // namespace mgb

@@ -51,6 +51,7 @@ struct CovDesc {
   long long n_params;
   long long n_wt;                // floats of transposed-weight scratch
   long long wt_edge[kMaxLevels]; // float offset of transposed edge weights [l][k][c'][2] in the scratch
+  long long wt_atom[kMaxLevels]; // float offset of transposed atom-mix weights [l][k][c'][2] in the scratch
   int n_grid;                    // Lebedev points
   const float* leb_y;            // [25][n_grid][2]  Y_lm(x_g), 'qm' norm, no conjugation
   const float* leb_logw;         // [n_grid]

@@ -4,6 +4,7 @@
 #include <memory>
 
 #include "heads.cuh"
+#include "edge.cuh"
 
 struct mgb_cov_plan {
   mgb_cov_config cfg;
@@ -125,6 +126,9 @@ inline void fill_mlp(MlpDesc& m, int in, int hidden, int out, long long& p, long
 struct CovWs {
   int* n_atoms;
   int* pair_off;                  // [B+1] prefix of n_b^2 (flat list of valid pairs)
+  int* atom_off;                  // [B+1] prefix of n_b
+  int* atom_list;                 // [B*N] slot index b*N+i of every valid atom
+  float* dcat;                    // [B,N,max totA,2] cotangent of the cat vectors of the level being differentiated
   float* Wt;                      // transposed weights scratch
   float* X;                       // [B,N,S_in]
   float* A[kMaxLevels + 1];       // A[0] [B,N,1,C,2]; A[k] [B,N,25,C_k,2]
@@ -140,6 +144,8 @@ struct CovWs {
   float* dA[2];                   // ping-pong, each [B,N,25,Cmax,2]
   float* dE[2];                   // ping-pong, each [B,N,N,5,C,2]
   float* dD;                      // [B,N,N,5C,2]
+  float* D;                       // [B,N,N,5C,2] dot matrix of the level being processed
+  float* e_dpre, *e_R, *e_dR, *e_f;   // per-pair scratch of the edge backward (flat pair index)
   double* loss_acc;               // [16]
   float* mix_stage;               // [sum_l catM, 2] compact mixer-weight cotangent
   DwProblem* dw_probs;            // [16]
@@ -160,6 +166,13 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   int cmax = std::max(C, d.Cout);
   w.n_atoms = (int*)take(sizeof(int) * B);
   w.pair_off = (int*)take(sizeof(int) * (B + 1));
+  w.atom_off = (int*)take(sizeof(int) * (B + 1));
+  w.atom_list = (int*)take(sizeof(int) * BN);
+  {
+    int tmax = 0;
+    for (int k = 0; k < d.K; ++k) tmax = std::max(tmax, d.lv[k].totA);
+    w.dcat = (float*)take(sizeof(float) * BN * tmax * 2);
+  }
   w.Wt = (float*)take(sizeof(float) * d.n_wt);
   w.X = (float*)take(sizeof(float) * BN * d.S_in);
   w.A[0] = (float*)take(sizeof(float) * BN * C * 2);
@@ -195,6 +208,11 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   for (int q = 0; q < 2; ++q) w.dA[q] = (float*)take(sizeof(float) * BN * kM * cmax * 2);
   for (int q = 0; q < 2; ++q) w.dE[q] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.D = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.e_dpre = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.e_R = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.e_dR = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.e_f = (float*)take(sizeof(float) * BNN * kRadFeat);
   w.loss_acc = (double*)take(sizeof(double) * 16);
   w.mix_stage = (float*)take(sizeof(float) * 2 * d.totWM);
   w.dw_probs = (DwProblem*)take(sizeof(DwProblem) * 32);
@@ -206,6 +224,11 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
 inline int pick_co(int cout) {
   for (int co : {10, 8, 6, 5, 4}) if (cout % co == 0) return co;
   return 4;
+}
+// smallest instantiated register tile that holds all output channels of the row-parallel mix kernels
+inline int pick_co_rows(int cout) {
+  for (int co : {4, 8, 10, 12, 16, 20, 32}) if (cout <= co) return co;
+  return 32;
 }
 
 }  // namespace mgb
