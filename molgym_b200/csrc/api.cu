@@ -21,7 +21,8 @@ static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const 
   const size_t smem = sizeof(float2) * (size_t)kmax * CO;
   MGB_CUDA_OK(cudaFuncSetAttribute((k_mix_rows<CO, BACKWARD, KS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long rows_per_cta = kMixThreads / KS;
-  dim3 grid((unsigned)(((long long)B * d.N * 9 + rows_per_cta - 1) / rows_per_cta), kNL);
+  const long long groups = ((long long)B * d.N * 9 + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid((unsigned)std::min<long long>(groups, 148 * 2), kNL);   // ~10 CTAs per SM over the five ells; each loops over row groups
   MGB_LAUNCH((k_mix_rows<CO, BACKWARD, KS>), grid, kMixThreads, smem, st, plan->d_desc, level, w.Wt, w.atom_off, w.atom_list, B,
              w.cat[level], A_out, out);
   MGB_LAUNCH_OK("k_mix_rows");
@@ -29,10 +30,8 @@ static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const 
 }
 template <int CO, bool BACKWARD>
 static int launch_mix_rows_co(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
-  // small minibatches: split every row over 8 lanes so that the GPU has enough warps; large ones: one thread per row
-  const long long slots = (long long)B * plan->desc.N;
-  if (slots * 25 < 148ll * 2048 * 2) return launch_mix_rows_ks<CO, BACKWARD, 8>(plan, level, B, w, A_out, out, st);
-  return launch_mix_rows_ks<CO, BACKWARD, 1>(plan, level, B, w, A_out, out, st);
+  // 8 adjacent lanes share a row: its cat entries are read / written as contiguous 64-byte pieces
+  return launch_mix_rows_ks<CO, BACKWARD, 8>(plan, level, B, w, A_out, out, st);
 }
 template <bool BACKWARD>
 static int launch_mix_rows(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {

@@ -138,29 +138,32 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       EdgeScratch sc{w.e_dpre, w.e_R, w.e_dR, w.e_f};
       const int dw_chunks = (int)std::max<size_t>(1, std::min<size_t>((BN * N + kEdgeDwSub - 1) / kEdgeDwSub, 148 * 4));
       dim3 dwgrid(dw_chunks, kNL);
+      const bool split = edge_bwd_split(B, N);
+      const long long slice = (long long)BN * N * kNL * L.C;
+      dim3 pgrid(pair_blocks, split ? kNL : 1);
+#define MGB_EDGE_BWD(NL, EPREV, DEPREV, DOTTHREADS)                                                                              \
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));                          \
+  MGB_LAUNCH(k_dot_fwd<NL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);                                              \
+  MGB_LAUNCH_OK("k_dot_fwd");                                                                                                       \
+  if (split) {                                                                                                                      \
+    MGB_CUDA_OK(cudaFuncSetAttribute((k_edge_pairs_bwd<NL, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));         \
+    MGB_LAUNCH((k_edge_pairs_bwd<NL, true>), pgrid, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,       \
+               w.dE[k & 1], DEPREV, w.dD, slice, sc, grad);                                                                         \
+  } else {                                                                                                                          \
+    MGB_CUDA_OK(cudaFuncSetAttribute((k_edge_pairs_bwd<NL, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));        \
+    MGB_LAUNCH((k_edge_pairs_bwd<NL, false>), pgrid, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,      \
+               w.dE[k & 1], DEPREV, w.dD, slice, sc, grad);                                                                         \
+  }                                                                                                                                 \
+  MGB_LAUNCH_OK("k_edge_pairs_bwd");                                                                                                \
+  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 0, st, plan->d_desc, k, B, w.n_atoms, w.pair_off, EPREV, w.D, sc, grad);        \
+  MGB_LAUNCH_OK("k_edge_dw");                                                                                                       \
+  MGB_LAUNCH(k_dot_bwd<NL>, B * N, DOTTHREADS, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, split ? NL : 1, slice, w.dA[k & 1]);
       if (k == 0) {
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-        MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
-        MGB_LAUNCH_OK("k_dot_fwd");
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_pairs_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-        MGB_LAUNCH(k_edge_pairs_bwd<1>, pair_blocks, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,
-                   w.dE[k & 1], (float*)nullptr, w.dD, sc, grad);
-        MGB_LAUNCH_OK("k_edge_pairs_bwd");
-        MGB_LAUNCH(k_edge_dw<1>, dwgrid, kEdgeDwThreads, 0, st, plan->d_desc, k, B, w.n_atoms, w.pair_off, (const float*)nullptr, w.D, sc, grad);
-        MGB_LAUNCH_OK("k_edge_dw");
-        MGB_LAUNCH(k_dot_bwd<1>, B * N, 64, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
+        MGB_EDGE_BWD(1, (const float*)nullptr, (float*)nullptr, 64)
       } else {
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-        MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
-        MGB_LAUNCH_OK("k_dot_fwd");
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_pairs_bwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-        MGB_LAUNCH(k_edge_pairs_bwd<kNL>, pair_blocks, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,
-                   w.dE[k & 1], w.dE[(k - 1) & 1], w.dD, sc, grad);
-        MGB_LAUNCH_OK("k_edge_pairs_bwd");
-        MGB_LAUNCH(k_edge_dw<kNL>, dwgrid, kEdgeDwThreads, 0, st, plan->d_desc, k, B, w.n_atoms, w.pair_off, w.E[k - 1], w.D, sc, grad);
-        MGB_LAUNCH_OK("k_edge_dw");
-        MGB_LAUNCH(k_dot_bwd<kNL>, B * N, 256, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, w.dA[k & 1]);
+        MGB_EDGE_BWD(kNL, w.E[k - 1], w.dE[(k - 1) & 1], 256)
       }
+#undef MGB_EDGE_BWD
       MGB_LAUNCH_OK("k_dot_bwd");
     }
   }

@@ -551,10 +551,10 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   }
 }
 
-// dA_k[b,i,l',m,c] += sum_j (dD_ij + dD_ji)[l',c] (-1)^m conj(A_j[l',-m,c])
+// dA_k[b,i,l',m,c] += sum_j (dD_ij + dD_ji)[l',c] (-1)^m conj(A_j[l',-m,c]);  dD may come in n_slices partial slices
 template <int NLIN>
 __global__ void k_dot_bwd(const CovDesc* __restrict__ dp, int level, const int* __restrict__ n_atoms, const float* __restrict__ A_in,
-                          const float* __restrict__ dD, float* __restrict__ dA_in) {
+                          const float* __restrict__ dD, int n_slices, long long slice_stride /* complex */, float* __restrict__ dA_in) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C;
@@ -569,8 +569,12 @@ __global__ void k_dot_bwd(const CovDesc* __restrict__ dp, int level, const int* 
     const int lm = idx / C, c = idx % C, l = ell_of_lm(lm), m = lm - l * l - l;
     float2 acc = make_float2(0.f, 0.f);
     for (int j = 0; j < n; ++j) {
-      const float2 g1 = dDb[((long long)i * N + j) * kNL * C + l * C + c], g2 = dDb[((long long)j * N + i) * kNL * C + l * C + c];
-      const float2 g = make_float2(g1.x + g2.x, g1.y + g2.y);
+      float2 g = make_float2(0.f, 0.f);
+      for (int s = 0; s < n_slices; ++s) {
+        const float2 g1 = dDb[s * slice_stride + ((long long)i * N + j) * kNL * C + l * C + c];
+        const float2 g2 = dDb[s * slice_stride + ((long long)j * N + i) * kNL * C + l * C + c];
+        g.x += g1.x + g2.x; g.y += g1.y + g2.y;
+      }
       cfmacl(acc, Ab[(long long)j * NLM * C + lm_index(l, -m) * C + c], g);
     }
     const float sg = (m & 1) ? -1.f : 1.f;

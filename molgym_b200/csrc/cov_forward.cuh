@@ -383,7 +383,7 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const int l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1, Cout = L.Cout;
   const int rows = atom_off[B] * nm;
   constexpr int kRowsPerCta = kMixThreads / KS;
-  if ((int)(blockIdx.x * kRowsPerCta) >= rows) return;
+  if ((int)(blockIdx.x * kRowsPerCta) >= rows) return;   // uniform per CTA: the whole CTA leaves before any barrier
   MGB_DYN_SMEM(float2, sW);   // [K][CO]
   {
     const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_atom[level]) + L.offWA[l];   // [k][c'] (transposed by k_prep_params)
@@ -394,7 +394,8 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   }
   __syncthreads();
   const int ks = threadIdx.x % KS;
-  const int row_raw = blockIdx.x * kRowsPerCta + threadIdx.x / KS;
+  for (int rg = blockIdx.x; rg * kRowsPerCta < rows; rg += gridDim.x) {   // a CTA keeps its weights for several row groups
+  const int row_raw = rg * kRowsPerCta + threadIdx.x / KS;
   const bool valid = row_raw < rows;
   const int row = valid ? row_raw : rows - 1;   // clamp: every lane takes part in the shuffles
   const int a = row / nm, m = row - a * nm;
@@ -448,6 +449,7 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
         o[k] = acc;
       }
     }
+  }
   }
 }
 

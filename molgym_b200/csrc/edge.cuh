@@ -151,11 +151,12 @@ struct EdgeScratch {
   float* f;      // [pairs][32]
 };
 
-template <int NLIN>
+template <int NLIN, bool SPLIT>   // SPLIT: grid.y = 5, one thread per (pair, ell); dD goes to slice ell (summed by k_dot_bwd)
 __global__ void __launch_bounds__(kPairThreads)
 k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ pos,
                  const int* __restrict__ n_atoms, const int* __restrict__ pair_off, const float* __restrict__ dE,
-                 float* __restrict__ dE_prev, float* __restrict__ dD, EdgeScratch sc, float* __restrict__ grad) {
+                 float* __restrict__ dE_prev, float* __restrict__ dD, long long slice_stride /* complex */, EdgeScratch sc,
+                 float* __restrict__ grad) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C, C2 = 2 * C;
@@ -189,13 +190,18 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
     const long long pair = ((long long)id.b * N + id.i) * N + id.j;
     float f[kRadFeat], df[kRadFeat];
     rad_features_all(g, P + L.p_scales, P + L.p_phases, f, nullptr);
+    const int l_begin = SPLIT ? (int)blockIdx.y : 0, l_end = SPLIT ? (int)blockIdx.y + 1 : kNL;
     MGB_UNROLL
-    for (int t = 0; t < kRadFeat; ++t) { df[t] = 0.f; sc.f[(long long)p * kRadFeat + t] = f[t]; }
+    for (int t = 0; t < kRadFeat; ++t) {
+      df[t] = 0.f;
+      if (l_begin == 0) sc.f[(long long)p * kRadFeat + t] = f[t];
+    }
     float2 dDacc[NLIN * kEdgeC];
     MGB_UNROLL
     for (int k = 0; k < NLIN * kEdgeC; ++k) dDacc[k] = make_float2(0.f, 0.f);
     int off = 0;
-    for (int l = 0; l < kNL; ++l) {
+    for (int l = 0; l < l_begin; ++l) off += L.catE[l];
+    for (int l = l_begin; l < l_end; ++l) {
       float2 dpre[kEdgeC];
       const float2* g_in = reinterpret_cast<const float2*>(dE) + pair * kNL * C + l * C;
       MGB_UNROLL
@@ -247,7 +253,8 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
       }
       off += L.catE[l];
     }
-    float2* od = reinterpret_cast<float2*>(dD) + pair * kNL * C;
+    float2* od = reinterpret_cast<float2*>(dD) + (SPLIT ? (long long)blockIdx.y * slice_stride : 0ll) + pair * kNL * C;
+    if (!SPLIT || l_begin < NLIN)
     MGB_UNROLL
     for (int lp = 0; lp < NLIN; ++lp)
       MGB_UNROLL
@@ -311,8 +318,15 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
   // radial entries owned by the non-edge threads: e = (tid - K) + s * n_rad_threads over [2C][33] (column 32 = bias)
   const int n_rad_threads = kEdgeDwThreads - K, n_rad = C2 * (kRadFeat + 1);
   float racc[kEdgeDwRadSlots];
+  int r_o[kEdgeDwRadSlots], r_t[kEdgeDwRadSlots];   // (output, feature) of every owned entry; r_o < 0: none
   MGB_UNROLL
-  for (int s = 0; s < kEdgeDwRadSlots; ++s) racc[s] = 0.f;
+  for (int s = 0; s < kEdgeDwRadSlots; ++s) {
+    racc[s] = 0.f;
+    const int e = (tid - K) + s * n_rad_threads;
+    const bool on = !edge_thread && e < n_rad;
+    r_o[s] = on ? e / (kRadFeat + 1) : -1;
+    r_t[s] = on ? e - r_o[s] * (kRadFeat + 1) : 0;
+  }
   for (int p0 = p_begin; p0 < p_end; p0 += kEdgeDwSub) {
     const int np = min(kEdgeDwSub, p_end - p0);
     __syncthreads();
@@ -346,13 +360,8 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
     } else {
       for (int q = 0; q < np; ++q) {
         MGB_UNROLL
-        for (int s = 0; s < kEdgeDwRadSlots; ++s) {
-          const int e = (tid - K) + s * n_rad_threads;
-          if (e < n_rad) {
-            const int o = e / (kRadFeat + 1), t = e - o * (kRadFeat + 1);
-            racc[s] = fmaf(s_dR[q][o], t < kRadFeat ? s_f[q][t] : 1.f, racc[s]);
-          }
-        }
+        for (int s = 0; s < kEdgeDwRadSlots; ++s)
+          if (r_o[s] >= 0) racc[s] = fmaf(s_dR[q][r_o[s]], r_t[s] < kRadFeat ? s_f[q][r_t[s]] : 1.f, racc[s]);
       }
     }
   }
@@ -368,9 +377,8 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
   } else {
     MGB_UNROLL
     for (int s = 0; s < kEdgeDwRadSlots; ++s) {
-      const int e = (tid - K) + s * n_rad_threads;
-      if (e < n_rad && racc[s] != 0.f) {
-        const int o = e / (kRadFeat + 1), t = e - o * (kRadFeat + 1);
+      if (r_o[s] >= 0 && racc[s] != 0.f) {
+        const int o = r_o[s], t = r_t[s];
         if (t < kRadFeat) atomicAdd(grad + L.p_radW + ((long long)l * C2 + o) * kRadFeat + t, racc[s]);
         else atomicAdd(grad + L.p_radb + l * C2 + o, racc[s]);
       }

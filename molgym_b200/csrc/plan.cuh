@@ -153,6 +153,9 @@ struct CovWs {
   size_t bytes;
 };
 
+// small minibatches: the per-pair edge backward is split over the five ells (one thread per (pair, ell))
+inline bool edge_bwd_split(int B, int N) { return (long long)B * N * N < 148ll * 2048; }
+
 inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   CovWs w;
   size_t off = 0;
@@ -207,7 +210,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   w.dinv = (float*)take(sizeof(float) * BN * d.lat);
   for (int q = 0; q < 2; ++q) w.dA[q] = (float*)take(sizeof(float) * BN * kM * cmax * 2);
   for (int q = 0; q < 2; ++q) w.dE[q] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
-  w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2 * (edge_bwd_split(B, d.N) ? kNL : 1));
   w.D = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.e_dpre = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.e_R = (float*)take(sizeof(float) * BNN * kNL * C * 2);
