@@ -60,6 +60,59 @@ static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const flo
   return launch_mix_rows<false>(plan, level, B, w, nullptr, w.A[level + 1], st);
 }
 
+// Row MLPs (focus head, value transform): shared-memory resident weights when they fit, else the generic kernels.
+constexpr size_t kMaxDynSmem = 227 * 1024;
+static bool rows_mlp_smem_ok(const CovDesc& d) {
+  return d.lat % 4 == 0 && d.Wd % 4 == 0 && d.focus.in == d.trans.in && d.focus.hidden == d.trans.hidden &&
+         rows_mlp_fwd_smem_bytes<32>(d.lat, d.Wd, d.Wd) <= kMaxDynSmem && rows_mlp_bwd_smem_bytes<32>(d.lat, d.Wd) <= kMaxDynSmem;
+}
+template <int RT>
+static int launch_rows_mlp_fwd_rt(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const long long rows = (long long)B * d.N;
+  const size_t sm = rows_mlp_fwd_smem_bytes<RT>(d.lat, d.Wd, d.Wd);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_fwd_smem<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((unsigned)((rows + RT - 1) / RT), 2);
+  MGB_LAUNCH(k_rows_mlp_fwd_smem<RT>, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, B, w.act_off, w.act_list, w.atom_off, w.atom_list,
+             w.inv, w.hf, w.flogit, w.ht0, w.trans);
+  MGB_LAUNCH_OK("k_rows_mlp_fwd_smem");
+  return MGB_OK;
+}
+static int launch_rows_mlp_fwd(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const long long rows = (long long)B * d.N;
+  if (rows_mlp_smem_ok(d)) return rows <= 8ll * 148 * 4 ? launch_rows_mlp_fwd_rt<8>(plan, B, P, w, st) : launch_rows_mlp_fwd_rt<32>(plan, B, P, w, st);
+  dim3 grid((unsigned)((rows + kRowTile - 1) / kRowTile), 2);
+  const size_t sm = sizeof(float) * kRowTile * (d.lat + d.Wd);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  MGB_LAUNCH(k_rows_mlp_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, w.n_atoms, rows, w.inv, w.hf, w.flogit, w.ht0, w.trans);
+  MGB_LAUNCH_OK("k_rows_mlp_fwd");
+  return MGB_OK;
+}
+template <int RT>
+static int launch_rows_mlp_bwd_rt(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const long long rows = (long long)B * d.N;
+  const size_t sm = rows_mlp_bwd_smem_bytes<RT>(d.lat, d.Wd);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_bwd_smem<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((unsigned)((rows + RT - 1) / RT), 2);
+  MGB_LAUNCH(k_rows_mlp_bwd_smem<RT>, grid, kHeadThreads, sm, st, plan->d_desc, P, B, w.act_off, w.act_list, w.atom_off, w.atom_list, w.hf,
+             w.dflogit, w.dhf, w.ht0, w.dvf, w.dtrans, w.dht0, w.dinv);
+  MGB_LAUNCH_OK("k_rows_mlp_bwd_smem");
+  return MGB_OK;
+}
+static int launch_rows_mlp_bwd(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const long long rows = (long long)B * d.N;
+  if (rows_mlp_smem_ok(d)) return rows <= 8ll * 148 * 4 ? launch_rows_mlp_bwd_rt<8>(plan, B, P, w, st) : launch_rows_mlp_bwd_rt<32>(plan, B, P, w, st);
+  const size_t sm = sizeof(float) * kRowTile * d.Wd * 3;
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  MGB_LAUNCH(k_rows_mlp_bwd, (unsigned)((rows + kRowTile - 1) / kRowTile), kHeadThreads, sm, st, plan->d_desc, P, w.n_atoms, rows, w.hf,
+             w.dflogit, w.dhf, w.ht0, w.dvf, w.dtrans, w.dht0, w.dinv);
+  MGB_LAUNCH_OK("k_rows_mlp_bwd");
+  return MGB_OK;
+}
+
 static int launch_policy_fwd(const mgb_cov_plan* plan, int B, const float* bags, const float* actions, const float* P,
                              const CovWs& w, const mgb_cov_outputs* out, cudaStream_t st) {
   const CovDesc& d = plan->desc;
@@ -67,7 +120,7 @@ static int launch_policy_fwd(const mgb_cov_plan* plan, int B, const float* bags,
   MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int grid = std::min(B, 148 * 4);
   MGB_LAUNCH(k_policy_fwd, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
-             w.flogit, w.trans, reinterpret_cast<float2*>(w.lse), *out);
+             w.flogit, w.trans, reinterpret_cast<float2*>(w.lse), w.pol_state, *out);
   MGB_LAUNCH_OK("k_policy_fwd");
   return MGB_OK;
 }
@@ -253,9 +306,12 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   MGB_CUDA_OK(cudaMalloc((void**)&plan->d_segs, sizeof(TransposeSeg) * plan->segs.size()));
   MGB_CUDA_OK(cudaMemcpy(plan->d_segs, plan->segs.data(), sizeof(TransposeSeg) * plan->segs.size(), cudaMemcpyHostToDevice));
   MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
+  MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side2, cudaStreamNonBlocking));
   for (int q = 0; q <= kMaxLevels; ++q) {
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork[q], cudaEventDisableTiming));
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join[q], cudaEventDisableTiming));
+    MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork2[q], cudaEventDisableTiming));
+    MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join2[q], cudaEventDisableTiming));
   }
   *out = plan.release();
   return MGB_OK;
@@ -264,9 +320,12 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
 void mgb_cov_plan_destroy(mgb_cov_plan* plan) {
   if (!plan) return;
   if (plan->side) cudaStreamDestroy(plan->side);
+  if (plan->side2) cudaStreamDestroy(plan->side2);
   for (int q = 0; q <= kMaxLevels; ++q) {
     if (plan->ev_fork[q]) cudaEventDestroy(plan->ev_fork[q]);
     if (plan->ev_join[q]) cudaEventDestroy(plan->ev_join[q]);
+    if (plan->ev_fork2[q]) cudaEventDestroy(plan->ev_fork2[q]);
+    if (plan->ev_join2[q]) cudaEventDestroy(plan->ev_join2[q]);
   }
   cudaFree(plan->d_tables);
   cudaFree(plan->d_desc);
@@ -319,7 +378,7 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   MGB_LAUNCH_OK("k_input_fwd");
   if (out->covariats)   // padded atoms carry zero representations in the reference; the level kernels skip them
     MGB_CUDA_OK(cudaMemsetAsync(w.A[d.K], 0, sizeof(float) * (size_t)B * N * kM * d.Cout * 2, st));
-  MGB_LAUNCH(k_pair_offsets, 1, 1024, 0, st, B, N, w.n_atoms, w.pair_off, w.atom_off, w.atom_list);
+  MGB_LAUNCH(k_pair_offsets, 1, 1024, 0, st, B, N, w.n_atoms, w.pair_off, w.atom_off, w.atom_list, w.act_off, w.act_list);
   MGB_LAUNCH_OK("k_pair_offsets");
   const unsigned pair_blocks = (unsigned)(((long long)B * N * N + kPairThreads - 1) / kPairThreads);
   for (int k = 0; k < d.K; ++k) {
@@ -329,15 +388,15 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
     dim3 egrid(pair_blocks, kNL);
     if (k == 0) {
       MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
+      MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);
       MGB_LAUNCH_OK("k_dot_fwd");
-      MGB_LAUNCH(k_edge_pairs_fwd<1>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D,
+      MGB_LAUNCH(k_edge_pairs_fwd<1>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
                  (const float*)nullptr, w.E[k]);
     } else {
       MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);
+      MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);
       MGB_LAUNCH_OK("k_dot_fwd");
-      MGB_LAUNCH(k_edge_pairs_fwd<kNL>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D,
+      MGB_LAUNCH(k_edge_pairs_fwd<kNL>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
                  w.E[k - 1], w.E[k]);
     }
     MGB_LAUNCH_OK("k_edge_pairs_fwd");
@@ -347,12 +406,8 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   MGB_LAUNCH(k_scalars_fwd, B * N, 64, 0, st, plan->d_desc, w.n_atoms, w.A[d.K], w.inv);
   MGB_LAUNCH_OK("k_scalars_fwd");
   {
-    const long long rows = (long long)B * N;
-    dim3 grid((unsigned)((rows + kRowTile - 1) / kRowTile), 2);
-    const size_t sm = sizeof(float) * kRowTile * (d.lat + d.Wd);
-    MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    MGB_LAUNCH(k_rows_mlp_fwd, grid, kHeadThreads, sm, st, plan->d_desc, P, w.Wt, w.n_atoms, rows, w.inv, w.hf, w.flogit, w.ht0, w.trans);
-    MGB_LAUNCH_OK("k_rows_mlp_fwd");
+    int rc = launch_rows_mlp_fwd(plan, B, P, w, st);
+    if (rc != MGB_OK) return rc;
   }
   {
     int rc = launch_policy_fwd(plan, B, bags, actions, P, w, out, st);

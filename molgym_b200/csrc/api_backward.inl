@@ -1,17 +1,5 @@
 // api_backward.inl — backward launch sequence + PPO loss + host packer (part of api.cu).
 
-namespace mgb {
-struct DwProblemList {
-  DwProblem p[32];
-  DwWork w[96];
-  int n, nw;
-};
-__global__ void k_store_dw_problems(DwProblemList list, DwProblem* __restrict__ dst, DwWork* __restrict__ wdst) {
-  if ((int)threadIdx.x < list.n) dst[threadIdx.x] = list.p[threadIdx.x];
-  if ((int)threadIdx.x < list.nw) wdst[threadIdx.x] = list.w[threadIdx.x];
-}
-}  // namespace mgb
-
 template <int NLM2>
 static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
                            int accumulate_dE, cudaStream_t st) {
@@ -53,19 +41,15 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     const size_t sm = sizeof(float) * (policy_smem_floats(d) + policy_bwd_extra_floats(d));
     MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int grid = std::min(B, 148 * 2);
-    MGB_LAUNCH(k_policy_bwd, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
-               w.trans, d.has_beta ? reinterpret_cast<const float2*>(w.lse) : (const float2*)nullptr, g_logp, g_ent, g_v, o, w.mix_stage, grad);
+    MGB_LAUNCH(k_policy_bwd, grid, kPolicyBwdThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
+               w.trans, w.pol_state, g_logp, g_ent, g_v, o, w.mix_stage, grad);
     MGB_LAUNCH_OK("k_policy_bwd");
     MGB_LAUNCH(k_mixer_dw_finish, 2, 256, 0, st, plan->d_desc, w.mix_stage, grad);
     MGB_LAUNCH_OK("k_mixer_dw_finish");
   }
   {
-    const long long rows = (long long)BN;
-    const size_t sm = sizeof(float) * kRowTile * d.Wd * 3;
-    MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    MGB_LAUNCH(k_rows_mlp_bwd, (unsigned)((rows + kRowTile - 1) / kRowTile), kHeadThreads, sm, st, plan->d_desc, P, w.n_atoms, rows,
-               w.hf, w.dflogit, w.dhf, w.ht0, w.dvf, w.dtrans, w.dht0, w.dinv);
-    MGB_LAUNCH_OK("k_rows_mlp_bwd");
+    int rc = launch_rows_mlp_bwd(plan, B, P, w, st);
+    if (rc != MGB_OK) return rc;
   }
   MGB_LAUNCH(k_scalars_bwd, B * N, 64, 0, st, plan->d_desc, w.n_atoms, w.A[K], w.dinv, w.dA[K & 1]);
   MGB_LAUNCH_OK("k_scalars_bwd");
@@ -95,11 +79,9 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     for (int pi = 0; pi < q; ++pi)
       for (int o0 = 0; o0 < list.p[pi].No; o0 += kDwTileO) list.w[nw++] = DwWork{pi, o0};
     list.nw = nw;
-    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, side, list, w.dw_probs, w.dw_work);
-    MGB_LAUNCH_OK("k_store_dw_problems");
     const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
     dim3 grid(chunks, nw);
-    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, side, w.dw_probs, w.dw_work, w.n_atoms, N, grad);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, side, list, w.n_atoms, N, grad);
     MGB_LAUNCH_OK("k_dw_grouped");
   }
   for (int k = K - 1; k >= 0; --k) {
@@ -133,7 +115,6 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     }
     {
       const unsigned pair_blocks = (unsigned)((BN * N + kPairThreads - 1) / kPairThreads);
-      const size_t dsm = sizeof(float2) * (size_t)N * L.nlm_in * L.C;
       const size_t esm = sizeof(float2) * (size_t)L.sumCatE * kEdgeC + sizeof(float) * (kNL * 2 * L.C * (kRadFeat + 1));
       EdgeScratch sc{w.e_dpre, w.e_R, w.e_dR, w.e_f};
       const int dw_chunks = (int)std::max<size_t>(1, std::min<size_t>((BN * N + kEdgeDwSub - 1) / kEdgeDwSub, 148 * 4));
@@ -141,10 +122,9 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       const bool split = edge_bwd_split(B, N);
       const long long slice = (long long)BN * N * kNL * L.C;
       dim3 pgrid(pair_blocks, split ? kNL : 1);
+      // the scratch of the previous (higher) level's edge backward is still being reduced by k_edge_dw on side2
+      if (k < K - 1) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join2[k + 1], 0));
 #define MGB_EDGE_BWD(NL, EPREV, DEPREV, DOTTHREADS)                                                                              \
-  MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));                          \
-  MGB_LAUNCH(k_dot_fwd<NL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D);                                              \
-  MGB_LAUNCH_OK("k_dot_fwd");                                                                                                       \
   if (split) {                                                                                                                      \
     MGB_CUDA_OK(cudaFuncSetAttribute((k_edge_pairs_bwd<NL, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));         \
     MGB_LAUNCH((k_edge_pairs_bwd<NL, true>), pgrid, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,       \
@@ -155,8 +135,12 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
                w.dE[k & 1], DEPREV, w.dD, slice, sc, grad);                                                                         \
   }                                                                                                                                 \
   MGB_LAUNCH_OK("k_edge_pairs_bwd");                                                                                                \
-  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 0, st, plan->d_desc, k, B, w.n_atoms, w.pair_off, EPREV, w.D, sc, grad);        \
+  /* fork: the edge weight gradients (reductions over pairs of the scratch just written) run on side2 */                            \
+  MGB_CUDA_OK(cudaEventRecord(plan->ev_fork2[k], st));                                                                              \
+  MGB_CUDA_OK(cudaStreamWaitEvent(plan->side2, plan->ev_fork2[k], 0));                                                              \
+  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 0, plan->side2, plan->d_desc, k, B, w.n_atoms, w.pair_off, EPREV, w.D[k], sc, grad); \
   MGB_LAUNCH_OK("k_edge_dw");                                                                                                       \
+  MGB_CUDA_OK(cudaEventRecord(plan->ev_join2[k], plan->side2));                                                                     \
   MGB_LAUNCH(k_dot_bwd<NL>, B * N, DOTTHREADS, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, split ? NL : 1, slice, w.dA[k & 1]);
       if (k == 0) {
         MGB_EDGE_BWD(1, (const float*)nullptr, (float*)nullptr, 64)
@@ -175,14 +159,13 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     int nw = 0;
     for (int o0 = 0; o0 < list.p[0].No; o0 += kDwTileO) list.w[nw++] = DwWork{0, o0};
     list.nw = nw;
-    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, st, list, w.dw_probs + 16, w.dw_work + 64);
-    MGB_LAUNCH_OK("k_store_dw_problems");
     const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
     dim3 grid(chunks, nw);
-    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, w.dw_probs + 16, w.dw_work + 64, w.n_atoms, N, grad);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, list, w.n_atoms, N, grad);
     MGB_LAUNCH_OK("k_dw_grouped");
   }
-  MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[0], 0));   // join the side stream (its last work is mix_dw(0))
+  MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[0], 0));    // join the side streams (their last work is mix_dw(0), edge_dw(0))
+  MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join2[0], 0));
   return MGB_OK;
 }
 

@@ -208,11 +208,9 @@ int mgb_int_backward(mgb_int_plan* plan, int32_t B, const int32_t* numbers, cons
     for (int pi = 0; pi < q; ++pi)
       for (int o0 = 0; o0 < list.p[pi].No; o0 += kDwTileO) list.w[nw++] = DwWork{pi, o0};
     list.nw = nw;
-    MGB_LAUNCH(k_store_dw_problems, 1, 96, 0, st, list, w.dw_probs, w.dw_work);
-    MGB_LAUNCH_OK("k_store_dw_problems");
     const int chunks = (int)std::max<long long>(1, std::min<long long>((Pn + 255) / 256, 64));
     dim3 grid(chunks, nw);
-    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, w.dw_probs, w.dw_work, (const int*)nullptr, d.N, grad);
+    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, list, (const int*)nullptr, d.N, grad);
     MGB_LAUNCH_OK("k_dw_grouped");
   }
   return MGB_OK;

@@ -118,6 +118,66 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
   return r;
 }
 
+// ---- TMA bulk copies global -> shared memory (cp.async.bulk + mbarrier; SASS UBLKCP) ---------------------------
+// Used to stage weight matrices: one thread issues the copy, the whole tile is in flight at once, and everybody waits on
+// the mbarrier.  Source / destination must be 16-byte aligned and the size a multiple of 16 (smem_fill_ok); callers fall
+// back to cooperative loads otherwise.  The CPU emulator build copies synchronously.
+struct SmemBarrier { unsigned long long word; };
+__device__ __forceinline__ bool smem_fill_ok(const void* src, long long bytes) {
+  return ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0ull) && (bytes % 16 == 0) && bytes > 0;
+}
+#ifndef MGB_CUSIM
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(SmemBarrier* bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the init visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_expect(SmemBarrier* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, SmemBarrier* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(SmemBarrier* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MGB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MGB_DONE;\n"
+      "bra MGB_WAIT;\n"
+      "MGB_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+#else
+__device__ inline void mbar_init(SmemBarrier*, int) {}
+__device__ inline void mbar_expect(SmemBarrier*, unsigned) {}
+__device__ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, SmemBarrier*) { std::memcpy(dst, src, bytes); }
+__device__ inline void mbar_wait(SmemBarrier*, unsigned) { __syncthreads(); }   // every thread of the CTA waits in our kernels
+#endif
+// Whole-CTA helper: start filling dst[0..n) (floats) from src.  Returns true when the copy is asynchronous (wait with
+// mbar_wait(bar, parity) before reading); false when it was done with plain loads (a __syncthreads() is still needed).
+// `bar` must have been initialised (mbar_init(bar, 1) + __syncthreads()) by the caller; one fill per barrier phase.
+__device__ __forceinline__ bool smem_fill_begin(float* dst, const float* __restrict__ src, int n, SmemBarrier* bar) {
+  const long long bytes = 4ll * n;
+  if (smem_fill_ok(src, bytes) && smem_fill_ok(dst, bytes)) {
+    if (threadIdx.x == 0) {
+      mbar_expect(bar, (unsigned)bytes);
+      bulk_g2s(dst, src, (unsigned)bytes, bar);
+    }
+    return true;
+  }
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) dst[idx] = src[idx];
+  return false;
+}
+__device__ __forceinline__ void smem_fill_end(bool async, SmemBarrier* bar, unsigned parity) {
+  if (async) mbar_wait(bar, parity); else __syncthreads();
+}
+
 // ---- Clebsch-Gordan term tables (device pointers; built on the host in plan.cuh) --------------------------------
 struct CgTable {
   int n_out;               // number of (path, m) outputs

@@ -81,11 +81,11 @@ __device__ __forceinline__ void gemv_n(const float* __restrict__ W, const float*
   }
 }
 
-__global__ void __launch_bounds__(kPolicyThreads)
+__global__ void __launch_bounds__(kPolicyBwdThreads)
 k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
-             const float* __restrict__ trans, const float2* __restrict__ lse_saved, const float* __restrict__ g_logp,
+             const float* __restrict__ trans, const float* __restrict__ state, const float* __restrict__ g_logp,
              const float* __restrict__ g_ent, const float* __restrict__ g_v, PolicyBwdOut o, float* __restrict__ mix_stage,
              float* __restrict__ grad) {
   const CovDesc& d = *dp;
@@ -108,7 +108,13 @@ k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     PolicyScalars ps;
     __syncthreads();
-    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps, lse_saved);
+    {   // the forward's intermediates (PolicySmem block + scalars), saved by k_policy_fwd
+      const float* src = state + (long long)b * policy_state_floats(d);
+      const int nf = policy_smem_floats(d);
+      for (int idx = threadIdx.x; idx < nf; idx += blockDim.x) sm[idx] = src[idx];
+      ps = *reinterpret_cast<const PolicyScalars*>(src + ((nf + 3) & ~3));
+    }
+    __syncthreads();
     const float gl = g_logp[b], ge = g_ent[b], gv = g_v[b];
     const int nact = ps.n > 1 ? ps.n : 1;
     // ---- value head

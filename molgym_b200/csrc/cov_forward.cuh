@@ -135,33 +135,51 @@ __device__ __forceinline__ float rad_feature(int t, const PairGeom& g, const flo
 // Flat list of valid (b, i, j) pairs: pair_off[b] = sum_{b' < b} n_b'^2, pair_off[B] = total.  One CTA.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_pair_offsets(int B, int N, const int* __restrict__ n_atoms, int* __restrict__ pair_off, int* __restrict__ atom_off,
-                               int* __restrict__ atom_list) {
-  __shared__ int part[1024], parta[1024];
+                               int* __restrict__ atom_list, int* __restrict__ act_off, int* __restrict__ act_list) {
+  // three exclusive prefix sums over the canvases: n^2 (pairs), n (valid atoms), max(n, 1) (rows the focus head looks at)
+  __shared__ int wsum[3][32];
   const int per = (B + blockDim.x - 1) / blockDim.x;
   const int lo = threadIdx.x * per, hi = min(B, lo + per);
-  int sum = 0, suma = 0;
-  for (int b = lo; b < hi; ++b) { sum += n_atoms[b] * n_atoms[b]; suma += n_atoms[b]; }
-  part[threadIdx.x] = sum;
-  parta[threadIdx.x] = suma;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0, runa = 0;
-    for (int t = 0; t < (int)blockDim.x; ++t) {
-      const int v = part[t], va = parta[t];
-      part[t] = run; parta[t] = runa;
-      run += v; runa += va;
+  int own[3] = {0, 0, 0};
+  for (int b = lo; b < hi; ++b) {
+    const int n = n_atoms[b];
+    own[0] += n * n; own[1] += n; own[2] += n > 1 ? n : 1;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc[3];
+  for (int q = 0; q < 3; ++q) {
+    inc[q] = own[q];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc[q], o);
+      if (lane >= o) inc[q] += t;
     }
-    pair_off[B] = run;
-    atom_off[B] = runa;
+    if (lane == 31) wsum[q][wid] = inc[q];
   }
   __syncthreads();
-  int run = part[threadIdx.x], runa = parta[threadIdx.x];
+  if (wid == 0) {
+    for (int q = 0; q < 3; ++q) {
+      const int v = lane < nw ? wsum[q][lane] : 0;
+      int s = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+      }
+      wsum[q][lane] = s - v;   // exclusive prefix of the warp totals
+      if (lane == 31) (q == 0 ? pair_off : (q == 1 ? atom_off : act_off))[B] = s;
+    }
+  }
+  __syncthreads();
+  int run = wsum[0][wid] + inc[0] - own[0], runa = wsum[1][wid] + inc[1] - own[1], runc = wsum[2][wid] + inc[2] - own[2];
   for (int b = lo; b < hi; ++b) {
+    const int n = n_atoms[b], nact = n > 1 ? n : 1;
     pair_off[b] = run;
     atom_off[b] = runa;
-    for (int i = 0; i < n_atoms[b]; ++i) atom_list[runa + i] = b * N + i;   // flat list of valid atoms (slot index b*N + i)
-    run += n_atoms[b] * n_atoms[b];
-    runa += n_atoms[b];
+    act_off[b] = runc;
+    for (int i = 0; i < n; ++i) atom_list[runa + i] = b * N + i;       // flat list of valid atoms (slot index b*N + i)
+    for (int i = 0; i < nact; ++i) act_list[runc + i] = b * N + i;     // flat list of active rows
+    run += n * n;
+    runa += n;
+    runc += nact;
   }
 }
 

@@ -11,7 +11,8 @@ namespace mgb {
 
 constexpr int kRowTile = 8;
 constexpr int kHeadThreads = 128;     // row-MLP kernels
-constexpr int kPolicyThreads = 256;   // per-canvas policy kernels
+constexpr int kPolicyThreads = 512;   // per-canvas policy forward (one CTA per canvas; the GEMV phases are latency-bound)
+constexpr int kPolicyBwdThreads = 256;
 constexpr float kF32Eps = 1.1920928955078125e-07f;
 constexpr float kLogSqrt2Pi = 0.9189385332046727f;
 constexpr float kLog4Pi = 2.5310242469692907f;
@@ -176,6 +177,206 @@ k_rows_mlp_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// The same two MLPs with the weight matrices resident in shared memory (TMA bulk copies, everything in flight at once)
+// and only the rows that matter: tiles of RT rows taken from the compact lists of active rows (focus head) / valid atoms
+// (value transform).  grid = (ceil(B*N / RT), 2); CTAs beyond the end of their list leave at once.
+// Needs K % 4 == 0, Wd % 4 == 0 and the matrices to fit (rows_mlp_smem_bytes); the generic kernels above are the fallback.
+// ------------------------------------------------------------------------------------------------------------
+template <int RT>
+__host__ __device__ inline size_t rows_mlp_fwd_smem_bytes(int K, int Wd, int No_max) {
+  return sizeof(float) * ((size_t)K * Wd + (size_t)Wd * No_max + (size_t)RT * (K + Wd) + 16 + RT);
+}
+template <int RT>
+__global__ void __launch_bounds__(kHeadThreads)
+k_rows_mlp_fwd_smem(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
+                    const int* __restrict__ act_off, const int* __restrict__ act_list, const int* __restrict__ atom_off,
+                    const int* __restrict__ atom_list, const float* __restrict__ X, float* __restrict__ H0, float* __restrict__ Y0,
+                    float* __restrict__ H1, float* __restrict__ Y1) {
+  const CovDesc& d = *dp;
+  const bool focus = blockIdx.y == 0;
+  const MlpDesc& M = focus ? d.focus : d.trans;
+  const int n_rows = focus ? act_off[B] : atom_off[B];
+  const int r0 = blockIdx.x * RT;
+  if (r0 >= n_rows) return;
+  const int* list = focus ? act_list : atom_list;
+  float* H = focus ? H0 : H1;
+  float* Y = focus ? Y0 : Y1;
+  const int K = M.in, Wd = M.hidden, No = M.out;
+  MGB_DYN_SMEM(float, sm);
+  SmemBarrier* bar = reinterpret_cast<SmemBarrier*>(sm);     // [2]
+  int* s_row = reinterpret_cast<int*>(sm + 16);              // [RT]
+  float* sW0 = sm + 16 + RT;                                 // [K][Wd]   (16-byte aligned: RT is a multiple of 4)
+  float* sW1 = sW0 + (size_t)K * Wd;                         // [Wd][No]
+  float* sx = sW1 + (size_t)Wd * No;                         // [RT][K]
+  float* sh = sx + RT * K;                                   // [RT][Wd]
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  if ((int)threadIdx.x < RT) s_row[threadIdx.x] = r0 + (int)threadIdx.x < n_rows ? list[r0 + threadIdx.x] : -1;
+  __syncthreads();
+  const bool a0 = smem_fill_begin(sW0, Wt + M.W0t, K * Wd, &bar[0]);
+  const bool a1 = smem_fill_begin(sW1, Wt + M.W1t, Wd * No, &bar[1]);
+  for (int idx = threadIdx.x; idx < RT * (K / 4); idx += blockDim.x) {
+    const int q = idx / (K / 4), k4 = idx - q * (K / 4);
+    const int row = s_row[q];
+    reinterpret_cast<float4*>(sx)[idx] = row >= 0 ? reinterpret_cast<const float4*>(X + (long long)row * K)[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  smem_fill_end(a0, &bar[0], 0);
+  for (int o = threadIdx.x; o < Wd; o += blockDim.x) {
+    float acc[RT];
+    const float bias = P[M.b0 + o];
+    MGB_UNROLL
+    for (int q = 0; q < RT; ++q) acc[q] = bias;
+    for (int k = 0; k < K; k += 4) {
+      const float w0 = sW0[(k + 0) * Wd + o], w1 = sW0[(k + 1) * Wd + o], w2 = sW0[(k + 2) * Wd + o], w3 = sW0[(k + 3) * Wd + o];
+      MGB_UNROLL
+      for (int q = 0; q < RT; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(sx + q * K + k);
+        acc[q] = fmaf(w3, x.w, fmaf(w2, x.z, fmaf(w1, x.y, fmaf(w0, x.x, acc[q]))));
+      }
+    }
+    MGB_UNROLL
+    for (int q = 0; q < RT; ++q) {
+      const float h = fmaxf(acc[q], 0.f);
+      sh[q * Wd + o] = h;
+      if (s_row[q] >= 0) H[(long long)s_row[q] * Wd + o] = h;
+    }
+  }
+  __syncthreads();
+  smem_fill_end(a1, &bar[1], 0);
+  if (No >= 32) {
+    for (int o = threadIdx.x; o < No; o += blockDim.x) {
+      float acc[RT];
+      const float bias = P[M.b1 + o];
+      MGB_UNROLL
+      for (int q = 0; q < RT; ++q) acc[q] = bias;
+      for (int k = 0; k < Wd; k += 4) {
+        const float w0 = sW1[(k + 0) * No + o], w1 = sW1[(k + 1) * No + o], w2 = sW1[(k + 2) * No + o], w3 = sW1[(k + 3) * No + o];
+        MGB_UNROLL
+        for (int q = 0; q < RT; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(sh + q * Wd + k);
+          acc[q] = fmaf(w3, x.w, fmaf(w2, x.z, fmaf(w1, x.y, fmaf(w0, x.x, acc[q]))));
+        }
+      }
+      MGB_UNROLL
+      for (int q = 0; q < RT; ++q)
+        if (s_row[q] >= 0) Y[(long long)s_row[q] * No + o] = acc[q];
+    }
+  } else {
+    // few outputs (the focus logit): a warp per (row, output), lanes over k, shuffle reduction
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int pr = warp; pr < RT * No; pr += nwarps) {
+      const int q = pr / No, o = pr - q * No;
+      float acc = 0.f;
+      for (int k = lane; k < Wd; k += 32) acc = fmaf(sW1[k * No + o], sh[q * Wd + k], acc);
+      acc = warp_sum(acc);
+      if (lane == 0 && s_row[q] >= 0) Y[(long long)s_row[q] * No + o] = acc + P[M.b1 + o];
+    }
+  }
+}
+
+// Backward of the same.  blockIdx.y = 0: focus head on the active rows (dY0 [rows]); 1: value transform on the valid atoms
+// (dY = dvf[b,:] for every atom of canvas b, also written to dY1 for the weight gradient).  Both add into dX (atomics).
+template <int RT>
+__host__ __device__ inline size_t rows_mlp_bwd_smem_bytes(int K, int Wd) {
+  return sizeof(float) * ((size_t)K * Wd + (size_t)Wd * Wd + (size_t)RT * 2 * Wd + 16 + RT);
+}
+template <int RT>
+__global__ void __launch_bounds__(kHeadThreads)
+k_rows_mlp_bwd_smem(const CovDesc* __restrict__ dp, const float* __restrict__ P, int B, const int* __restrict__ act_off,
+                    const int* __restrict__ act_list, const int* __restrict__ atom_off, const int* __restrict__ atom_list,
+                    const float* __restrict__ H0, const float* __restrict__ dY0, float* __restrict__ dH0,
+                    const float* __restrict__ H1, const float* __restrict__ dvf, float* __restrict__ dY1, float* __restrict__ dH1,
+                    float* __restrict__ dX) {
+  const CovDesc& d = *dp;
+  const bool focus = blockIdx.y == 0;
+  const MlpDesc& M = focus ? d.focus : d.trans;
+  const int n_rows = focus ? act_off[B] : atom_off[B];
+  const int r0 = blockIdx.x * RT;
+  if (r0 >= n_rows) return;
+  const int* list = focus ? act_list : atom_list;
+  const int K = M.in, Wd = M.hidden, N = d.N;
+  MGB_DYN_SMEM(float, sm);
+  SmemBarrier* bar = reinterpret_cast<SmemBarrier*>(sm);     // [2]
+  int* s_row = reinterpret_cast<int*>(sm + 16);              // [RT]
+  float* sW0 = sm + 16 + RT;                                 // [Wd][K]   reference layout of W0
+  float* sW1 = sW0 + (size_t)K * Wd;                         // [Wd][Wd]  reference layout of W1 (trans only)
+  float* sdy = sW1 + (focus ? 0 : (size_t)Wd * Wd);          // [RT][Wd]
+  float* sdh = sdy + RT * Wd;                                // [RT][Wd]
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  if ((int)threadIdx.x < RT) s_row[threadIdx.x] = r0 + (int)threadIdx.x < n_rows ? list[r0 + threadIdx.x] : -1;
+  __syncthreads();
+  const bool a0 = smem_fill_begin(sW0, P + M.W0, K * Wd, &bar[0]);
+  bool a1 = false;
+  if (!focus) a1 = smem_fill_begin(sW1, P + M.W1, Wd * Wd, &bar[1]);
+  if (focus) {
+    for (int idx = threadIdx.x; idx < RT * Wd; idx += blockDim.x) {
+      const int q = idx / Wd, h = idx - q * Wd;
+      const int row = s_row[q];
+      float g = 0.f;
+      if (row >= 0) {
+        g = H0[(long long)row * Wd + h] > 0.f ? P[M.W1 + h] * dY0[row] : 0.f;
+        dH0[(long long)row * Wd + h] = g;
+      }
+      sdh[idx] = g;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < RT * Wd; idx += blockDim.x) {
+      const int q = idx / Wd, o = idx - q * Wd;
+      const int row = s_row[q];
+      float v = 0.f;
+      if (row >= 0) {
+        v = dvf[(long long)(row / N) * Wd + o];
+        dY1[(long long)row * Wd + o] = v;
+      }
+      sdy[idx] = v;
+    }
+    __syncthreads();
+    smem_fill_end(a1, &bar[1], 0);
+    for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+      float acc[RT];
+      MGB_UNROLL
+      for (int q = 0; q < RT; ++q) acc[q] = 0.f;
+      for (int o = 0; o < Wd; o += 4) {
+        const float w0 = sW1[(o + 0) * Wd + h], w1 = sW1[(o + 1) * Wd + h], w2 = sW1[(o + 2) * Wd + h], w3 = sW1[(o + 3) * Wd + h];
+        MGB_UNROLL
+        for (int q = 0; q < RT; ++q) {
+          const float4 g = *reinterpret_cast<const float4*>(sdy + q * Wd + o);
+          acc[q] = fmaf(w3, g.w, fmaf(w2, g.z, fmaf(w1, g.y, fmaf(w0, g.x, acc[q]))));
+        }
+      }
+      MGB_UNROLL
+      for (int q = 0; q < RT; ++q) {
+        const int row = s_row[q];
+        float g = 0.f;
+        if (row >= 0) {
+          g = H1[(long long)row * Wd + h] > 0.f ? acc[q] : 0.f;
+          dH1[(long long)row * Wd + h] = g;
+        }
+        sdh[q * Wd + h] = g;
+      }
+    }
+  }
+  __syncthreads();
+  smem_fill_end(a0, &bar[0], 0);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc[RT];
+    MGB_UNROLL
+    for (int q = 0; q < RT; ++q) acc[q] = 0.f;
+    for (int h = 0; h < Wd; h += 4) {
+      const float w0 = sW0[(h + 0) * K + k], w1 = sW0[(h + 1) * K + k], w2 = sW0[(h + 2) * K + k], w3 = sW0[(h + 3) * K + k];
+      MGB_UNROLL
+      for (int q = 0; q < RT; ++q) {
+        const float4 g = *reinterpret_cast<const float4*>(sdh + q * Wd + h);
+        acc[q] = fmaf(w3, g.w, fmaf(w2, g.z, fmaf(w1, g.y, fmaf(w0, g.x, acc[q]))));
+      }
+    }
+    MGB_UNROLL
+    for (int q = 0; q < RT; ++q)
+      if (s_row[q] >= 0 && acc[q] != 0.f) atomicAdd(dX + (long long)s_row[q] * K + k, acc[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Grouped weight gradient: for each problem p, dW[o][k] += sum_rows dY[r][o] X[r][k], db[o] += sum_rows dY[r][o].
 // grid = (row chunks, work items); a work item is (problem, tile of 32 outputs); threads over k (k == K is the bias
 // column), 32 accumulators in registers, dY tile staged in shared memory, X rows streamed coalesced from HBM.
@@ -188,15 +389,20 @@ struct DwProblem {
   long long dW, db;  // float offsets into the gradient buffer
 };
 struct DwWork { int prob, o0; };
+// the whole problem list travels as a kernel parameter (2.6 KB of the 4 KB parameter space): no staging launch
+struct DwProblemList {
+  DwProblem p[32];
+  DwWork w[96];
+  int n, nw;
+};
 constexpr int kDwThreads = 256;
 constexpr int kDwTileO = 32;
 constexpr int kDwRowChunk = 32;
 
 __global__ void __launch_bounds__(kDwThreads)
-k_dw_grouped(const DwProblem* __restrict__ probs, const DwWork* __restrict__ work, const int* __restrict__ n_atoms, int N,
-             float* __restrict__ grad) {
-  const DwWork wk = work[blockIdx.y];
-  const DwProblem pr = probs[wk.prob];
+k_dw_grouped(const MGB_GRID_CONSTANT DwProblemList list, const int* __restrict__ n_atoms, int N, float* __restrict__ grad) {
+  const DwWork wk = list.w[blockIdx.y];
+  const DwProblem pr = list.p[wk.prob];
   const long long per = (pr.rows + gridDim.x - 1) / gridDim.x;
   const long long r_begin = per * blockIdx.x, r_end = (r_begin + per < pr.rows) ? r_begin + per : pr.rows;
   if (r_begin >= r_end) return;
@@ -265,6 +471,9 @@ __host__ __device__ inline int policy_smem_floats(const CovDesc& d) {
   return 2 * d.N + d.lat + d.Wd + 2 * d.Z + 2 * kM * d.CPE + d.latE + d.Wd + 2 * d.G + 2 * d.totM + 2 * kM * d.CPE + 2 * kM +
          2 * d.Wd + 64 + 32 + 16;
 }
+// saved per canvas by k_policy_fwd for k_policy_bwd: the PolicySmem block followed by PolicyScalars (padded to 16 bytes)
+#define MGB_POLICY_SCALARS_FLOATS 32
+__host__ __device__ inline int policy_state_floats(const CovDesc& d) { return ((policy_smem_floats(d) + 3) & ~3) + MGB_POLICY_SCALARS_FLOATS + 4; }
 __device__ __forceinline__ PolicySmem policy_smem_carve(const CovDesc& d, float* base) {
   PolicySmem s;
   float* p = base;
@@ -373,13 +582,14 @@ __device__ __forceinline__ void gemv_rows(const float* __restrict__ W, const flo
 
 struct PolicyScalars {
   int n, focus, element;
-  bool focus_valid;
+  int focus_valid;
   float dist;
   float ent_f, ent_e, logp_f, logp_e, logp_d, logp_o, v;
   float k_raw, inv_sqrt_k, log_z, lse_max, lse_sum;  // spherical
   float2 s_o;                                          // s(orientation)
   SoftmaxAux aux_f, aux_e;
 };
+static_assert(sizeof(PolicyScalars) <= sizeof(float) * MGB_POLICY_SCALARS_FLOATS, "PolicyScalars outgrew its slot in the saved state");
 
 // s(x) = sum_lm a_lm Y_lm(x)
 __device__ __forceinline__ float2 sph_sum(const float2* a, const float2* y) {
@@ -566,7 +776,7 @@ __global__ void __launch_bounds__(kPolicyThreads)
 k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
-             const float* __restrict__ trans, float2* __restrict__ lse_out, mgb_cov_outputs out) {
+             const float* __restrict__ trans, float2* __restrict__ lse_out, float* __restrict__ state, mgb_cov_outputs out) {
   const CovDesc& d = *dp;
   MGB_DYN_SMEM(float, sm);
   PolicySmem s = policy_smem_carve(d, sm);
@@ -574,6 +784,13 @@ k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
     PolicyScalars ps;
     __syncthreads();
     policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps, nullptr);
+    if (state) {   // everything the backward needs: the shared-memory intermediates and the per-canvas scalars
+      __syncthreads();
+      float* dst = state + (long long)b * policy_state_floats(d);
+      const int nf = policy_smem_floats(d);
+      for (int idx = threadIdx.x; idx < nf; idx += blockDim.x) dst[idx] = sm[idx];
+      if (threadIdx.x == 0) *reinterpret_cast<PolicyScalars*>(dst + ((nf + 3) & ~3)) = ps;
+    }
     if (threadIdx.x == 0) {
       lse_out[b] = make_float2(ps.lse_max, ps.lse_sum);
       out.logp[b] = ((ps.logp_f + ps.logp_e) + ps.logp_d) + ps.logp_o;

@@ -16,8 +16,9 @@ struct mgb_cov_plan {
   mgb::TransposeSeg* d_segs = nullptr;
   std::vector<long long> p_offsets, p_numels;
   // fork/join of independent backward kernels (weight-gradient reductions next to the edge level)
-  cudaStream_t side = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr;
   cudaEvent_t ev_fork[mgb::kMaxLevels + 1] = {}, ev_join[mgb::kMaxLevels + 1] = {};
+  cudaEvent_t ev_fork2[mgb::kMaxLevels + 1] = {}, ev_join2[mgb::kMaxLevels + 1] = {};   // edge weight gradients (side2)
 };
 
 namespace mgb {
@@ -128,6 +129,8 @@ struct CovWs {
   int* pair_off;                  // [B+1] prefix of n_b^2 (flat list of valid pairs)
   int* atom_off;                  // [B+1] prefix of n_b
   int* atom_list;                 // [B*N] slot index b*N+i of every valid atom
+  int* act_off;                   // [B+1] prefix of max(n_b, 1)
+  int* act_list;                  // [B*N] slot index of every active row (i < max(n_b, 1): what the focus head sees)
   float* dcat;                    // [B,N,max totA,2] cotangent of the cat vectors of the level being differentiated
   float* Wt;                      // transposed weights scratch
   float* X;                       // [B,N,S_in]
@@ -135,7 +138,8 @@ struct CovWs {
   float* E[kMaxLevels];           // [B,N,N,5,C,2]
   float* cat[kMaxLevels];         // [B,N,totA_k,2]
   float* inv;                     // [B,N,lat]
-  float* lse;                     // [B,2] running max / sum of the log Z quadrature (saved for backward)
+  float* lse;                     // [B,2] running max / sum of the log Z quadrature
+  float* pol_state;               // [B, policy_state_floats] intermediates of k_policy_fwd, read by k_policy_bwd
   float* hf, *flogit, *ht0, *trans;       // rows
   // backward
   float* finv, *he, *einv, *hd, *vf, *hv;  // per canvas activations saved by policy_bwd for the weight gradients
@@ -144,7 +148,7 @@ struct CovWs {
   float* dA[2];                   // ping-pong, each [B,N,25,Cmax,2]
   float* dE[2];                   // ping-pong, each [B,N,N,5,C,2]
   float* dD;                      // [B,N,N,5C,2]
-  float* D;                       // [B,N,N,5C,2] dot matrix of the level being processed
+  float* D[kMaxLevels];           // [B,N,N,5C,2] dot matrix of every level (saved by the forward for the edge backward)
   float* e_dpre, *e_R, *e_dR, *e_f;   // per-pair scratch of the edge backward (flat pair index)
   double* loss_acc;               // [16]
   float* mix_stage;               // [sum_l catM, 2] compact mixer-weight cotangent
@@ -171,6 +175,8 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   w.pair_off = (int*)take(sizeof(int) * (B + 1));
   w.atom_off = (int*)take(sizeof(int) * (B + 1));
   w.atom_list = (int*)take(sizeof(int) * BN);
+  w.act_off = (int*)take(sizeof(int) * (B + 1));
+  w.act_list = (int*)take(sizeof(int) * BN);
   {
     int tmax = 0;
     for (int k = 0; k < d.K; ++k) tmax = std::max(tmax, d.lv[k].totA);
@@ -186,6 +192,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   }
   w.inv = (float*)take(sizeof(float) * BN * d.lat);
   w.lse = (float*)take(sizeof(float) * B * 2);
+  w.pol_state = (float*)take(sizeof(float) * (size_t)B * policy_state_floats(d));
   w.hf = (float*)take(sizeof(float) * BN * d.Wd);
   w.flogit = (float*)take(sizeof(float) * BN);
   w.ht0 = (float*)take(sizeof(float) * BN * d.Wd);
@@ -211,7 +218,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   for (int q = 0; q < 2; ++q) w.dA[q] = (float*)take(sizeof(float) * BN * kM * cmax * 2);
   for (int q = 0; q < 2; ++q) w.dE[q] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.dD = (float*)take(sizeof(float) * BNN * kNL * C * 2 * (edge_bwd_split(B, d.N) ? kNL : 1));
-  w.D = (float*)take(sizeof(float) * BNN * kNL * C * 2);
+  for (int k = 0; k < d.K; ++k) w.D[k] = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.e_dpre = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.e_R = (float*)take(sizeof(float) * BNN * kNL * C * 2);
   w.e_dR = (float*)take(sizeof(float) * BNN * kNL * C * 2);

@@ -3,6 +3,7 @@
 #ifdef MGB_CUSIM
 #include "cusim.h"  // tests/cusim/cusim.h — test infrastructure only
 #define MGB_UNROLL
+#define MGB_GRID_CONSTANT
 #else
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -45,4 +46,5 @@ inline void prof_end(cudaStream_t st) {
   extern __shared__ __align__(16) unsigned char _mgb_dyn_smem[];        \
   type* name = reinterpret_cast<type*>(_mgb_dyn_smem)
 #define MGB_UNROLL _Pragma("unroll")
+#define MGB_GRID_CONSTANT __grid_constant__
 #endif

@@ -246,6 +246,13 @@ template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d,
   return cusim::shfl_idx(m, v, src);
 }
 
+template <class T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d, int = 32) {
+  int lane = cusim::g_block->current % 32;
+  int src = lane - (int)d;
+  if (src < 0) src = lane;
+  return cusim::shfl_idx(m, v, src);
+}
+
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float atomicAdd(float* p, float v) {
   uint32_t* ip = (uint32_t*)p;
