@@ -325,6 +325,7 @@ def run_ours(args):
     lib.mgb_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
     lib.mgb_profile_kernel(None)
     total_ms, mode = eager_ms, 'eager launches'
+    graph_ms = None
     if graph is not None:
         sampler2 = ClockSampler(local_rank) if rank == 0 else None
         graph_ms, wall_g, clocks_g = timed(graph_step, args.steps, max(3, args.warmup), sampler2)
@@ -382,6 +383,7 @@ def run_ours(args):
                      'fp32_achieved_tflops': alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
                      'note': 'kernel is FP32-FMA/latency bound at this size (arithmetic intensity >> ridge); see DESIGN.md'},
         'wall_ms_per_step': wall / args.steps * 1e3, 'launch_mode': mode, 'eager_ms_per_step': eager_ms / args.steps,
+        'graph_ms_per_step': graph_ms / args.steps if graph_ms is not None else None,
     }
     if not args.no_cpu_baseline and world == 1:
         cpu = run_cpu(cfg, steps=5, warmup=1, budget_s=20.0)

@@ -180,6 +180,9 @@ int mgb_int_backward(mgb_int_plan* plan, int32_t batch, const int32_t* d_numbers
 int64_t mgb_launch_count(void);
 int mgb_profile_kernel(const char* substr);
 int mgb_profile_read(double* total_ms, int64_t* launches);
+/* Per-launch report of the timed launches since the last read, one "<kernel> <milliseconds>\n" line each in launch order
+ * (truncated at cap); clears the list like mgb_profile_read. */
+int mgb_profile_report(char* buf, int64_t cap);
 
 /* Host-side observation packer (no device work).  labels[B,N] are indices into zs, xyz[B,N,3] float64 canvas
  * coordinates, as found in ObservationType tuples.  Null-symbol items are dropped and the rest compacted to the

@@ -18,7 +18,7 @@ static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const 
   const LevelDesc& L = d.lv[level];
   int kmax = 0;
   for (int l = 0; l < kNL; ++l) kmax = std::max(kmax, L.catA[l]);
-  const size_t smem = sizeof(float2) * (size_t)kmax * CO;
+  const size_t smem = sizeof(float2) * (size_t)kmax * kMixStride<CO>;
   MGB_CUDA_OK(cudaFuncSetAttribute((k_mix_rows<CO, BACKWARD, KS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long rows_per_cta = kMixThreads / KS;
   const long long groups = ((long long)B * d.N * 9 + rows_per_cta - 1) / rows_per_cta;
@@ -391,13 +391,13 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
       MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);
       MGB_LAUNCH_OK("k_dot_fwd");
       MGB_LAUNCH(k_edge_pairs_fwd<1>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
-                 (const float*)nullptr, w.E[k]);
+                 (const float*)nullptr, w.E[k], w.pair_slot);
     } else {
       MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);
       MGB_LAUNCH_OK("k_dot_fwd");
       MGB_LAUNCH(k_edge_pairs_fwd<kNL>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
-                 w.E[k - 1], w.E[k]);
+                 w.E[k - 1], w.E[k], (int*)nullptr);
     }
     MGB_LAUNCH_OK("k_edge_pairs_fwd");
     int rc = k == 0 ? launch_atom_fwd<1>(plan, k, B, P, pos, w, st) : launch_atom_fwd<kM>(plan, k, B, P, pos, w, st);

@@ -97,17 +97,22 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[k], 0));
       const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + kMixDwAtoms - 1) / kMixDwAtoms, 148 * 2));
       dim3 grid(chunks, kNL);
-      const size_t sm = sizeof(float2) * kMixDwAtoms * 9 * L.Cout;
-#define MGB_MIXDW_CASE(CO)                                                                                              \
-  case CO:                                                                                                              \
-    MGB_LAUNCH(k_mix_dw<CO>, grid, kMixDwThreads, sm, side, plan->d_desc, k, B, w.n_atoms, w.cat[k], w.dA[(k + 1) & 1], grad); \
+      const int co = std::min(pick_co_rows(L.Cout), 16 + 4 * (L.Cout == 20));   // more than 20 channels: passes of 16
+      const size_t sm = sizeof(float2) * kMixDwAtoms * 9 * co;
+#define MGB_MIXDW_CASE(CO)                                                                                                        \
+  case CO:                                                                                                                        \
+    for (int cb = 0; cb < L.Cout; cb += CO) {                                                                                     \
+      MGB_LAUNCH(k_mix_dw<CO>, grid, kMixDwThreads, sm, side, plan->d_desc, k, B, w.atom_off, w.atom_list, w.cat[k],              \
+                 w.dA[(k + 1) & 1], cb, grad);                                                                                    \
+    }                                                                                                                             \
     break;
-      switch (pick_co(L.Cout)) {
-        MGB_MIXDW_CASE(10)
-        MGB_MIXDW_CASE(8)
-        MGB_MIXDW_CASE(6)
-        MGB_MIXDW_CASE(5)
+      switch (co) {
         MGB_MIXDW_CASE(4)
+        MGB_MIXDW_CASE(8)
+        MGB_MIXDW_CASE(10)
+        MGB_MIXDW_CASE(12)
+        MGB_MIXDW_CASE(16)
+        MGB_MIXDW_CASE(20)
       }
 #undef MGB_MIXDW_CASE
       MGB_LAUNCH_OK("k_mix_dw");
@@ -117,7 +122,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       const unsigned pair_blocks = (unsigned)((BN * N + kPairThreads - 1) / kPairThreads);
       const size_t esm = sizeof(float2) * (size_t)L.sumCatE * kEdgeC + sizeof(float) * (kNL * 2 * L.C * (kRadFeat + 1));
       EdgeScratch sc{w.e_dpre, w.e_R, w.e_dR, w.e_f};
-      const int dw_chunks = (int)std::max<size_t>(1, std::min<size_t>((BN * N + kEdgeDwSub - 1) / kEdgeDwSub, 148 * 4));
+      const int dw_chunks = (int)std::max<size_t>(1, std::min<size_t>((BN * N + kEdgeDwTile - 1) / kEdgeDwTile, 148 * 2));
       dim3 dwgrid(dw_chunks, kNL);
       const bool split = edge_bwd_split(B, N);
       const long long slice = (long long)BN * N * kNL * L.C;
@@ -138,7 +143,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   /* fork: the edge weight gradients (reductions over pairs of the scratch just written) run on side2 */                            \
   MGB_CUDA_OK(cudaEventRecord(plan->ev_fork2[k], st));                                                                              \
   MGB_CUDA_OK(cudaStreamWaitEvent(plan->side2, plan->ev_fork2[k], 0));                                                              \
-  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 0, plan->side2, plan->d_desc, k, B, w.n_atoms, w.pair_off, EPREV, w.D[k], sc, grad); \
+  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 0, plan->side2, plan->d_desc, k, B, w.pair_off, w.pair_slot, EPREV, w.D[k], sc, grad); \
   MGB_LAUNCH_OK("k_edge_dw");                                                                                                       \
   MGB_CUDA_OK(cudaEventRecord(plan->ev_join2[k], plan->side2));                                                                     \
   MGB_LAUNCH(k_dot_bwd<NL>, B * N, DOTTHREADS, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, split ? NL : 1, slice, w.dA[k & 1]);
@@ -187,6 +192,7 @@ int mgb_profile_kernel(const char* substr) {
 #ifndef MGB_CUSIM
   for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
   g_prof.ev.clear();
+  g_prof.names.clear();
   g_prof.active = substr && substr[0];
   std::snprintf(g_prof.pattern, sizeof(g_prof.pattern), "%s", substr ? substr : "");
 #endif
@@ -206,9 +212,31 @@ int mgb_profile_read(double* total_ms, int64_t* launches) {
   }
   for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
   g_prof.ev.clear();
+  g_prof.names.clear();
 #endif
   if (total_ms) *total_ms = tot;
   if (launches) *launches = n;
+  return MGB_OK;
+}
+
+int mgb_profile_report(char* buf, int64_t cap) {
+  if (!buf || cap <= 0) return fail(MGB_ERR_INVALID, "null buffer");
+  buf[0] = 0;
+#ifndef MGB_CUSIM
+  // one line per timed launch, in launch order: "<kernel> <milliseconds>"
+  int64_t used = 0;
+  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
+    MGB_CUDA_OK(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float ms = 0.f;
+    MGB_CUDA_OK(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+    const int n = std::snprintf(buf + used, (size_t)(cap - used), "%s %.6f\n", g_prof.names[i / 2], ms);
+    if (n < 0 || used + n >= cap) break;
+    used += n;
+  }
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.names.clear();
+#endif
   return MGB_OK;
 }
 

@@ -478,7 +478,9 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------------------
 // Atom-mix weight gradient: dW_l[c'][k] += sum_{atoms, m} conj(cat[a][l][m][k]) dOut[a][lm][c'].
-// grid = (atom chunks, 5 ells); lanes over k straight out of HBM (the forward saved cat), register tile over c'.
+// grid = (chunks of the compact valid-atom list, 5 ells); lanes over k straight out of HBM (the forward saved cat,
+// every row is one coalesced run), all output channels of a k in registers (one pass over cat), dOut rows of a group of
+// atoms staged in shared memory and read as broadcasts.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMixDwThreads = 128;
 constexpr int kMixDwSlots = 3;   // catA_l <= 3 * 128
@@ -486,71 +488,62 @@ constexpr int kMixDwAtoms = 8;   // atoms per CTA pass (their dOut rows are stag
 
 template <int CO>
 __global__ void __launch_bounds__(kMixDwThreads)
-k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ n_atoms, const float* __restrict__ cat,
-         const float* __restrict__ dA_out, float* __restrict__ grad) {
+k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ atom_off, const int* __restrict__ atom_list,
+         const float* __restrict__ cat, const float* __restrict__ dA_out, int c_base, float* __restrict__ grad) {
+  // this launch covers the output channels [c_base, min(c_base + CO, Cout))
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
-  const int N = d.N, Cout = L.Cout, l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1;
-  const long long rows = (long long)B * N;
-  const long long per = (rows + gridDim.x - 1) / gridDim.x;
-  const long long r0 = per * blockIdx.x, r1 = (r0 + per < rows) ? r0 + per : rows;
-  MGB_DYN_SMEM(float2, sd);   // [kMixDwAtoms][9][Cout]
-  __shared__ long long s_row[kMixDwAtoms];
-  __shared__ int s_cnt;
-  for (int c0 = 0; c0 < Cout; c0 += CO) {
-    float2 acc[kMixDwSlots][CO];
+  const int Cout = L.Cout, l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1;
+  const int n_at = atom_off[B];
+  const int per = (n_at + gridDim.x - 1) / gridDim.x;
+  const int a0 = per * blockIdx.x, a1 = min(n_at, a0 + per);
+  if (a0 >= a1) return;
+  MGB_DYN_SMEM(float2, sd);   // [kMixDwAtoms][nm][CO], zero beyond Cout
+  float2 acc[kMixDwSlots][CO];
+  MGB_UNROLL
+  for (int s = 0; s < kMixDwSlots; ++s)
     MGB_UNROLL
-    for (int s = 0; s < kMixDwSlots; ++s)
-      MGB_UNROLL
-      for (int c = 0; c < CO; ++c) acc[s][c] = make_float2(0.f, 0.f);
-    for (long long rb = r0; rb < r1; rb += kMixDwAtoms) {
-      __syncthreads();
-      if (threadIdx.x == 0) {   // compact the valid atoms of this group
-        int cnt = 0;
-        for (long long r = rb; r < r1 && r < rb + kMixDwAtoms; ++r)
-          if ((int)(r % N) < n_atoms[r / N]) s_row[cnt++] = r;
-        s_cnt = cnt;
-      }
-      __syncthreads();
-      const int cnt = s_cnt;
-      for (int idx = threadIdx.x; idx < cnt * nm * Cout; idx += blockDim.x) {
-        const int a = idx / (nm * Cout), rem = idx - a * nm * Cout;
-        sd[idx] = reinterpret_cast<const float2*>(dA_out)[(s_row[a] * kM + l * l) * Cout + rem];
-      }
-      __syncthreads();
-      for (int a = 0; a < cnt; ++a) {
-        const float2* cr = reinterpret_cast<const float2*>(cat) + s_row[a] * L.totA + L.offA[l];
-        const float2* ga = sd + a * nm * Cout + c0;
+    for (int c = 0; c < CO; ++c) acc[s][c] = make_float2(0.f, 0.f);
+  const float2* dO = reinterpret_cast<const float2*>(dA_out);
+  for (int ab = a0; ab < a1; ab += kMixDwAtoms) {
+    const int cnt = min(kMixDwAtoms, a1 - ab);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cnt * nm * CO; idx += blockDim.x) {
+      const int a = idx / (nm * CO), rem = idx - a * nm * CO, m = rem / CO, c = rem - m * CO;
+      sd[idx] = c_base + c < Cout ? dO[((long long)atom_list[ab + a] * kM + l * l + m) * Cout + c_base + c] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int a = 0; a < cnt; ++a) {
+      const float2* cr = reinterpret_cast<const float2*>(cat) + (long long)atom_list[ab + a] * L.totA + L.offA[l];
+      const float2* ga = sd + a * nm * CO;
 #pragma unroll 3
-        for (int m = 0; m < nm; ++m) {
-          float2 xv[kMixDwSlots];
+      for (int m = 0; m < nm; ++m) {
+        float2 xv[kMixDwSlots];
+        MGB_UNROLL
+        for (int s = 0; s < kMixDwSlots; ++s) {
+          const int k = threadIdx.x + s * kMixDwThreads;
+          xv[s] = k < K ? cr[m * K + k] : make_float2(0.f, 0.f);
+        }
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) {
+          const float2 g = ga[m * CO + c];
           MGB_UNROLL
-          for (int s = 0; s < kMixDwSlots; ++s) {
-            const int k = threadIdx.x + s * kMixDwThreads;
-            xv[s] = k < K ? cr[m * K + k] : make_float2(0.f, 0.f);
-          }
-          MGB_UNROLL
-          for (int c = 0; c < CO; ++c) {
-            if (c0 + c < Cout) {
-              const float2 g = ga[m * Cout + c];
-              MGB_UNROLL
-              for (int s = 0; s < kMixDwSlots; ++s) cfmacl(acc[s][c], xv[s], g);
-            }
-          }
+          for (int s = 0; s < kMixDwSlots; ++s)
+            if (s * kMixDwThreads < K) cfmacl(acc[s][c], xv[s], g);
         }
       }
     }
-    MGB_UNROLL
-    for (int s = 0; s < kMixDwSlots; ++s) {
-      const int k = threadIdx.x + s * kMixDwThreads;
-      if (k < K) {
-        MGB_UNROLL
-        for (int c = 0; c < CO; ++c) {
-          if (c0 + c < Cout) {
-            float* dst = grad + L.p_atomW + 2ll * (L.offWA[l] + (long long)(c0 + c) * K + k);
-            if (acc[s][c].x != 0.f) atomicAdd(dst, acc[s][c].x);
-            if (acc[s][c].y != 0.f) atomicAdd(dst + 1, acc[s][c].y);
-          }
+  }
+  MGB_UNROLL
+  for (int s = 0; s < kMixDwSlots; ++s) {
+    const int k = threadIdx.x + s * kMixDwThreads;
+    if (k < K) {
+      MGB_UNROLL
+      for (int c = 0; c < CO; ++c) {
+        if (c_base + c < Cout) {
+          float* dst = grad + L.p_atomW + 2ll * (L.offWA[l] + (long long)(c_base + c) * K + k);
+          if (acc[s][c].x != 0.f) atomicAdd(dst, acc[s][c].x);
+          if (acc[s][c].y != 0.f) atomicAdd(dst + 1, acc[s][c].y);
         }
       }
     }

@@ -388,6 +388,7 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
 // are registers; no cross-lane reduction.  grid = (row blocks, 5 ells).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMixThreads = 128;
+template <int CO> constexpr int kMixStride = (CO % 4 == 2) ? CO : ((CO % 2 == 0) ? CO + 2 : CO);
 
 template <int CO, bool BACKWARD, int KS>
 __global__ void __launch_bounds__(kMixThreads)
@@ -402,12 +403,16 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const int rows = atom_off[B] * nm;
   constexpr int kRowsPerCta = kMixThreads / KS;
   if ((int)(blockIdx.x * kRowsPerCta) >= rows) return;   // uniform per CTA: the whole CTA leaves before any barrier
-  MGB_DYN_SMEM(float2, sW);   // [K][CO]
+  // row stride of the staged weights: KS lanes of a quarter-warp read KS different k at once, so the stride (in float2) is
+  // kept = 2 mod 4 — 16-byte aligned rows whose 16-byte slots fall into different bank groups (CO = 16 would otherwise put
+  // all eight k of a request on the same banks)
+  constexpr int CS = kMixStride<CO>;
+  MGB_DYN_SMEM(float2, sW);   // [K][CS]
   {
     const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_atom[level]) + L.offWA[l];   // [k][c'] (transposed by k_prep_params)
     for (int idx = threadIdx.x; idx < K * CO; idx += blockDim.x) {
       const int k = idx / CO, c = idx - k * CO;
-      sW[idx] = c < Cout ? src[k * Cout + c] : make_float2(0.f, 0.f);
+      sW[k * CS + c] = c < Cout ? src[k * Cout + c] : make_float2(0.f, 0.f);
     }
   }
   __syncthreads();
@@ -432,12 +437,12 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       MGB_UNROLL
       for (int q = 0; q < 4; ++q)
         MGB_UNROLL
-        for (int c = 0; c < CO; ++c) cfma(acc[c], sW[(k + q * KS) * CO + c], x[q]);
+        for (int c = 0; c < CO; ++c) cfma(acc[c], sW[(k + q * KS) * CS + c], x[q]);
     }
     for (; k < K; k += KS) {
       const float2 x = crow[k];
       MGB_UNROLL
-      for (int c = 0; c < CO; ++c) cfma(acc[c], sW[k * CO + c], x);
+      for (int c = 0; c < CO; ++c) cfma(acc[c], sW[k * CS + c], x);
     }
     MGB_UNROLL
     for (int c = 0; c < CO; ++c) {
@@ -463,7 +468,7 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       for (int k = ks; k < K; k += KS) {
         float2 acc = make_float2(0.f, 0.f);
         MGB_UNROLL
-        for (int c = 0; c < CO; ++c) cfmacl(acc, sW[k * CO + c], g[c]);
+        for (int c = 0; c < CO; ++c) cfmacl(acc, sW[k * CS + c], g[c]);
         o[k] = acc;
       }
     }

@@ -71,7 +71,8 @@ template <int NLIN>
 __global__ void __launch_bounds__(kPairThreads)
 k_edge_pairs_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
                  const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
-                 const float* __restrict__ D, const float* __restrict__ E_prev, float* __restrict__ E_out) {
+                 const float* __restrict__ D, const float* __restrict__ E_prev, float* __restrict__ E_out,
+                 int* __restrict__ pair_slot /* level 0 only: [pairs] dense slot (b*N+i)*N+j of every flat pair, else NULL */) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
@@ -95,6 +96,7 @@ k_edge_pairs_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
   const PairId id = decode_pair(p, B, pair_off, n_atoms);
   const PairGeom g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
   const long long pair = ((long long)id.b * N + id.i) * N + id.j;
+  if (pair_slot && l == 0) pair_slot[p] = (int)pair;
   float2 acc[kEdgeC];
   MGB_UNROLL
   for (int c = 0; c < kEdgeC; ++c) acc[c] = make_float2(0.f, 0.f);
@@ -283,85 +285,88 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Backward, weight cotangents (reductions over pairs).  grid = (pair chunks, 5 ells), 128 threads:
-//   threads 0 .. K_l-1     : dWE_l[c'][k] += sum_p conj(cat_l[p][k]) dpre_l[p][c']     (10 complex accumulators each)
-//   threads K_l .. 127     : dWrad_l[o][t] += sum_p dR_l[p][o] f[p][t], db_l[o] += sum_p dR_l[p][o]
-// cat_l[p] = [E_prev[p][l] | D[p] | R[p][l]] is read straight from HBM (coalesced over k); dpre / dR / f of a sub-chunk of
-// pairs are staged in shared memory.
+// Backward, weight cotangents: reductions over pairs, run as small GEMMs out of shared memory.
+//   dWE_l[c'][k]   += sum_p conj(cat_l[p][k]) dpre_l[p][c']       cat_l[p] = [E_prev[p][l] | D[p] | R[p][l]]
+//   dWrad_l[o][t]  += sum_p dR_l[p][o] f[p][t],   db_l[o] += sum_p dR_l[p][o]
+// grid = (pair chunks, 5 ells), 128 threads.  A CTA walks its chunk in tiles of kEdgeDwTile pairs: the tile's cat rows
+// (gathered through pair_slot, coalesced over k), dpre, dR and f are staged in shared memory, then
+//   threads 0 .. K_l-1 (warps 0-2) own one k: 10 complex accumulators, x from shared memory (lanes over k), dpre as broadcasts;
+//   warp 3 owns the radial features, lane = t: 2C real accumulators (+ the bias of output o = lane).
+// One flush of atomics per CTA at the end.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kEdgeDwThreads = 128;
-constexpr int kEdgeDwSub = 32;
-constexpr int kEdgeDwRadSlots = 12;   // ceil(2*10*33 / (128 - 70))
+constexpr int kEdgeDwTile = 32;
+constexpr int kEdgeKMax = 7 * kEdgeC;   // [E_prev (C) | dot (5 C) | radial (C)]
+static_assert(kRadFeat == 32, "warp 3 of k_edge_dw maps one lane to one radial feature");
 
 template <int NLIN>
 __global__ void __launch_bounds__(kEdgeDwThreads)
-k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
+k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ pair_off, const int* __restrict__ pair_slot,
           const float* __restrict__ E_prev, const float* __restrict__ D, EdgeScratch sc, float* __restrict__ grad) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
-  const int N = d.N, C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
+  const int C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
   const int total = pair_off[B];
   const int per = (total + gridDim.x - 1) / gridDim.x;
   const int p_begin = per * blockIdx.x, p_end = min(total, p_begin + per);
   if (p_begin >= p_end) return;
-  __shared__ float2 s_dpre[kEdgeDwSub][kEdgeC];
-  __shared__ float s_dR[kEdgeDwSub][2 * kEdgeC];
-  __shared__ float s_f[kEdgeDwSub][kRadFeat];
-  __shared__ long long s_pair[kEdgeDwSub];
+  __shared__ __align__(16) float2 s_cat[kEdgeDwTile][kEdgeKMax];
+  __shared__ __align__(16) float2 s_dpre[kEdgeDwTile][kEdgeC];
+  __shared__ __align__(16) float s_dR[kEdgeDwTile][2 * kEdgeC];
+  __shared__ float s_f[kEdgeDwTile][kRadFeat];
   const int tid = threadIdx.x;
-  const bool edge_thread = tid < K;
-  // which segment of cat_l does this thread's k live in?
+  const bool edge_thread = tid < K, rad_thread = tid >= 96;
   const int kprev = L.has_prev ? C : 0, kdot = (l < NLIN) ? NLIN * C : 0;
+  // channels beyond C stay zero for the whole kernel
+  for (int idx = tid; idx < kEdgeDwTile * kEdgeC; idx += blockDim.x) {
+    s_dpre[idx / kEdgeC][idx % kEdgeC] = make_float2(0.f, 0.f);
+    s_dR[idx / kEdgeC][2 * (idx % kEdgeC)] = 0.f;
+    s_dR[idx / kEdgeC][2 * (idx % kEdgeC) + 1] = 0.f;
+  }
   float2 acc[kEdgeC];
   MGB_UNROLL
   for (int c = 0; c < kEdgeC; ++c) acc[c] = make_float2(0.f, 0.f);
-  // radial entries owned by the non-edge threads: e = (tid - K) + s * n_rad_threads over [2C][33] (column 32 = bias)
-  const int n_rad_threads = kEdgeDwThreads - K, n_rad = C2 * (kRadFeat + 1);
-  float racc[kEdgeDwRadSlots];
-  int r_o[kEdgeDwRadSlots], r_t[kEdgeDwRadSlots];   // (output, feature) of every owned entry; r_o < 0: none
+  float racc[2 * kEdgeC], bacc = 0.f;
   MGB_UNROLL
-  for (int s = 0; s < kEdgeDwRadSlots; ++s) {
-    racc[s] = 0.f;
-    const int e = (tid - K) + s * n_rad_threads;
-    const bool on = !edge_thread && e < n_rad;
-    r_o[s] = on ? e / (kRadFeat + 1) : -1;
-    r_t[s] = on ? e - r_o[s] * (kRadFeat + 1) : 0;
-  }
-  for (int p0 = p_begin; p0 < p_end; p0 += kEdgeDwSub) {
-    const int np = min(kEdgeDwSub, p_end - p0);
+  for (int o = 0; o < 2 * kEdgeC; ++o) racc[o] = 0.f;
+  const float2* Ep = reinterpret_cast<const float2*>(E_prev);
+  const float2* Dp = reinterpret_cast<const float2*>(D);
+  const float2* Rp = reinterpret_cast<const float2*>(sc.R);
+  for (int p0 = p_begin; p0 < p_end; p0 += kEdgeDwTile) {
+    const int np = min(kEdgeDwTile, p_end - p0);
     __syncthreads();
-    if (tid < np) {
-      const PairId id = decode_pair(p0 + tid, B, pair_off, n_atoms);
-      s_pair[tid] = ((long long)id.b * N + id.i) * N + id.j;
+    for (int idx = tid; idx < np * K; idx += blockDim.x) {
+      const int q = idx / K, k = idx - q * K;
+      float2 x;
+      if (k < kprev) x = Ep[(long long)pair_slot[p0 + q] * kNL * C + l * C + k];
+      else if (k < kprev + kdot) x = Dp[(long long)pair_slot[p0 + q] * kNL * C + (k - kprev)];
+      else x = Rp[((long long)(p0 + q) * kNL + l) * C + (k - kprev - kdot)];
+      s_cat[q][k] = x;
     }
     for (int idx = tid; idx < np * C; idx += blockDim.x) {
       const int q = idx / C, c = idx - q * C;
       s_dpre[q][c] = reinterpret_cast<const float2*>(sc.dpre)[((long long)(p0 + q) * kNL + l) * C + c];
-    }
-    for (int idx = tid; idx < np * C2; idx += blockDim.x) {
-      const int q = idx / C2, o = idx - q * C2;
-      s_dR[q][o] = sc.dR[((long long)(p0 + q) * kNL + l) * C2 + o];
+      const float2 r = reinterpret_cast<const float2*>(sc.dR)[((long long)(p0 + q) * kNL + l) * C + c];
+      s_dR[q][2 * c] = r.x;
+      s_dR[q][2 * c + 1] = r.y;
     }
     for (int idx = tid; idx < np * kRadFeat; idx += blockDim.x) s_f[idx / kRadFeat][idx % kRadFeat] = sc.f[(long long)p0 * kRadFeat + idx];
     __syncthreads();
     if (edge_thread) {
-#pragma unroll 4
+#pragma unroll 2
       for (int q = 0; q < np; ++q) {
-        float2 x;
-        if (tid < kprev) x = reinterpret_cast<const float2*>(E_prev)[s_pair[q] * kNL * C + l * C + tid];
-        else if (tid < kprev + kdot) x = reinterpret_cast<const float2*>(D)[s_pair[q] * kNL * C + (tid - kprev)];
-        else {
-          const float* r = sc.R + ((long long)(p0 + q) * kNL + l) * C2 + 2 * (tid - kprev - kdot);
-          x = make_float2(r[0], r[1]);
-        }
+        const float2 x = s_cat[q][tid];
         MGB_UNROLL
         for (int c = 0; c < kEdgeC; ++c) cfmacl(acc[c], x, s_dpre[q][c]);
       }
-    } else {
+    } else if (rad_thread) {
+      const int t = tid - 96;
+#pragma unroll 2
       for (int q = 0; q < np; ++q) {
+        const float f = s_f[q][t];
         MGB_UNROLL
-        for (int s = 0; s < kEdgeDwRadSlots; ++s)
-          if (r_o[s] >= 0) racc[s] = fmaf(s_dR[q][r_o[s]], r_t[s] < kRadFeat ? s_f[q][r_t[s]] : 1.f, racc[s]);
+        for (int o = 0; o < 2 * kEdgeC; ++o) racc[o] = fmaf(s_dR[q][o], f, racc[o]);
+        if (t < 2 * kEdgeC) bacc += s_dR[q][t];
       }
     }
   }
@@ -374,15 +379,12 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
         if (acc[c].y != 0.f) atomicAdd(dst + 1, acc[c].y);
       }
     }
-  } else {
+  } else if (rad_thread) {
+    const int t = tid - 96;
     MGB_UNROLL
-    for (int s = 0; s < kEdgeDwRadSlots; ++s) {
-      if (r_o[s] >= 0 && racc[s] != 0.f) {
-        const int o = r_o[s], t = r_t[s];
-        if (t < kRadFeat) atomicAdd(grad + L.p_radW + ((long long)l * C2 + o) * kRadFeat + t, racc[s]);
-        else atomicAdd(grad + L.p_radb + l * C2 + o, racc[s]);
-      }
-    }
+    for (int o = 0; o < 2 * kEdgeC; ++o)
+      if (o < C2 && racc[o] != 0.f) atomicAdd(grad + L.p_radW + ((long long)l * C2 + o) * kRadFeat + t, racc[o]);
+    if (t < C2 && bacc != 0.f) atomicAdd(grad + L.p_radb + l * C2 + t, bacc);
   }
 }
 

@@ -113,10 +113,13 @@ inline void host_sph_harm(double x, double y, double z, double* out /* [25][2] *
 
 inline void fill_mlp(MlpDesc& m, int in, int hidden, int out, long long& p, long long& wt) {
   m.in = in; m.hidden = hidden; m.out = out;
-  m.W0 = p; p += (long long)hidden * in;
-  m.b0 = p; p += hidden;
-  m.W1 = p; p += (long long)out * hidden;
-  m.b1 = p; p += out;
+  // every tensor starts on a 16-byte boundary of the flat buffer (bulk copies into shared memory need it)
+  auto al = [](long long v) { return (v + 3) & ~3ll; };
+  p = al(p); m.W0 = p; p += (long long)hidden * in;
+  p = al(p); m.b0 = p; p += hidden;
+  p = al(p); m.W1 = p; p += (long long)out * hidden;
+  p = al(p); m.b1 = p; p += out;
+  p = al(p);
   m.W0t = wt; wt += (long long)hidden * in;
   m.W1t = wt; wt += (long long)out * hidden;
 }
@@ -127,6 +130,7 @@ inline void fill_mlp(MlpDesc& m, int in, int hidden, int out, long long& p, long
 struct CovWs {
   int* n_atoms;
   int* pair_off;                  // [B+1] prefix of n_b^2 (flat list of valid pairs)
+  int* pair_slot;                 // [B*N*N] dense slot (b*N+i)*N+j of every flat pair (written by the level-0 edge kernel)
   int* atom_off;                  // [B+1] prefix of n_b
   int* atom_list;                 // [B*N] slot index b*N+i of every valid atom
   int* act_off;                   // [B+1] prefix of max(n_b, 1)
@@ -173,6 +177,7 @@ inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   int cmax = std::max(C, d.Cout);
   w.n_atoms = (int*)take(sizeof(int) * B);
   w.pair_off = (int*)take(sizeof(int) * (B + 1));
+  w.pair_slot = (int*)take(sizeof(int) * BNN);
   w.atom_off = (int*)take(sizeof(int) * (B + 1));
   w.atom_list = (int*)take(sizeof(int) * BN);
   w.act_off = (int*)take(sizeof(int) * (B + 1));

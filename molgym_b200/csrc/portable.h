@@ -20,6 +20,7 @@ struct Profiler {
   char pattern[64] = "";
   bool active = false, hit = false;
   std::vector<cudaEvent_t> ev;   // start/stop pairs not yet read
+  std::vector<const char*> names;   // kernel name (string literal) of every pair
 };
 inline Profiler g_prof;
 inline void prof_begin(const char* name, cudaStream_t st) {
@@ -30,6 +31,7 @@ inline void prof_begin(const char* name, cudaStream_t st) {
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, st);
     g_prof.ev.push_back(a); g_prof.ev.push_back(b);
+    g_prof.names.push_back(name);
   }
 }
 inline void prof_end(cudaStream_t st) {

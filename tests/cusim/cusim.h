@@ -25,6 +25,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static thread_local
 #define __constant__ static
 
