@@ -22,7 +22,7 @@ static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const 
   MGB_CUDA_OK(cudaFuncSetAttribute((k_mix_rows<CO, BACKWARD, KS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long rows_per_cta = kMixThreads / KS;
   const long long groups = ((long long)B * d.N * 9 + rows_per_cta - 1) / rows_per_cta;
-  dim3 grid((unsigned)std::min<long long>(groups, 148 * 2), kNL);   // ~10 CTAs per SM over the five ells; each loops over row groups
+  dim3 grid((unsigned)std::min<long long>(groups, 148 * (KS == 32 ? 3 : 2)), kNL);   // ~10-15 CTAs per SM over the five ells; each loops over row groups
   MGB_LAUNCH((k_mix_rows<CO, BACKWARD, KS>), grid, kMixThreads, smem, st, plan->d_desc, level, w.Wt, w.atom_off, w.atom_list, B,
              w.cat[level], A_out, out);
   MGB_LAUNCH_OK("k_mix_rows");
@@ -30,7 +30,8 @@ static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const 
 }
 template <int CO, bool BACKWARD>
 static int launch_mix_rows_co(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
-  // 8 adjacent lanes share a row: its cat entries are read / written as contiguous 64-byte pieces
+  // 8 adjacent lanes share a row: its cat entries are read / written as contiguous 64-byte pieces (a whole warp per row was
+  // measured slower at C2: every CTA stages the ell's weights for fewer rows)
   return launch_mix_rows_ks<CO, BACKWARD, 8>(plan, level, B, w, A_out, out, st);
 }
 template <bool BACKWARD>
@@ -54,8 +55,9 @@ static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const flo
   const size_t smem = sizeof(float) * atom_smem_floats(L, d.N);
   MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MGB_LAUNCH(k_atom_cat<NLM2>, B * d.N, kAtomThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
-             w.A[level], w.E[level], w.cat[level]);
+             w.A[level], w.E[level], w.cat[level], small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB);
   MGB_LAUNCH_OK("k_atom_cat");
+  if (small_atoms(B, d.N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[level], 0));   // the square / pass-through blocks (side3)
   (void)P;
   return launch_mix_rows<false>(plan, level, B, w, nullptr, w.A[level + 1], st);
 }
@@ -307,11 +309,14 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   MGB_CUDA_OK(cudaMemcpy(plan->d_segs, plan->segs.data(), sizeof(TransposeSeg) * plan->segs.size(), cudaMemcpyHostToDevice));
   MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
   MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side2, cudaStreamNonBlocking));
+  MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side3, cudaStreamNonBlocking));
   for (int q = 0; q <= kMaxLevels; ++q) {
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork[q], cudaEventDisableTiming));
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join[q], cudaEventDisableTiming));
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork2[q], cudaEventDisableTiming));
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join2[q], cudaEventDisableTiming));
+    MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork3[q], cudaEventDisableTiming));
+    MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join3[q], cudaEventDisableTiming));
   }
   *out = plan.release();
   return MGB_OK;
@@ -321,11 +326,14 @@ void mgb_cov_plan_destroy(mgb_cov_plan* plan) {
   if (!plan) return;
   if (plan->side) cudaStreamDestroy(plan->side);
   if (plan->side2) cudaStreamDestroy(plan->side2);
+  if (plan->side3) cudaStreamDestroy(plan->side3);
   for (int q = 0; q <= kMaxLevels; ++q) {
     if (plan->ev_fork[q]) cudaEventDestroy(plan->ev_fork[q]);
     if (plan->ev_join[q]) cudaEventDestroy(plan->ev_join[q]);
     if (plan->ev_fork2[q]) cudaEventDestroy(plan->ev_fork2[q]);
     if (plan->ev_join2[q]) cudaEventDestroy(plan->ev_join2[q]);
+    if (plan->ev_fork3[q]) cudaEventDestroy(plan->ev_fork3[q]);
+    if (plan->ev_join3[q]) cudaEventDestroy(plan->ev_join3[q]);
   }
   cudaFree(plan->d_tables);
   cudaFree(plan->d_desc);
@@ -371,9 +379,14 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = d.N;
-  MGB_LAUNCH(k_prep_params, (int)((d.n_wt + 255) / 256), 256, 0, st, plan->d_segs, (int)plan->segs.size(), (long long)d.n_wt, P, w.Wt,
-             (long long)d.n_params, (const char*)plan->d_tables, (long long)plan->table_bytes);
+  // the weight transposes (+ L2 prefetch of parameters and tables) run on the side stream beside the input kernels; the first
+  // reader of Wt is the level-0 edge kernel
+  MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[0], st));
+  MGB_CUDA_OK(cudaStreamWaitEvent(plan->side, plan->ev_fork[0], 0));
+  MGB_LAUNCH(k_prep_params, (int)((d.n_wt + 255) / 256), 256, 0, plan->side, plan->d_segs, (int)plan->segs.size(), (long long)d.n_wt, P,
+             w.Wt, (long long)d.n_params, (const char*)plan->d_tables, (long long)plan->table_bytes);
   MGB_LAUNCH_OK("k_prep_params");
+  MGB_CUDA_OK(cudaEventRecord(plan->ev_join[0], plan->side));
   MGB_LAUNCH(k_input_fwd, B, 128, sizeof(float) * N * d.S_in, st, plan->d_desc, P, charges, bags, w.n_atoms, w.X, w.A[0]);
   MGB_LAUNCH_OK("k_input_fwd");
   if (out->covariats)   // padded atoms carry zero representations in the reference; the level kernels skip them
@@ -383,21 +396,52 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   const unsigned pair_blocks = (unsigned)(((long long)B * N * N + kPairThreads - 1) / kPairThreads);
   for (int k = 0; k < d.K; ++k) {
     const LevelDesc& L = d.lv[k];
+    if (small_atoms(B, N)) {
+      // the CG-square and pass-through blocks of cat_k only need A_k: side3, beside the dot matrix and the edge kernel
+      const size_t asm_ = sizeof(float) * atom_smem_floats(L, N);
+      MGB_CUDA_OK(cudaEventRecord(plan->ev_fork3[k], st));
+      MGB_CUDA_OK(cudaStreamWaitEvent(plan->side3, plan->ev_fork3[k], 0));
+      if (k == 0) {
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_));
+        MGB_LAUNCH(k_atom_cat<1>, B * N, kAtomThreads, asm_, plan->side3, plan->d_desc, k, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+                   w.A[k], w.E[k], w.cat[k], kAtomPhaseB);
+      } else {
+        MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<kM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_));
+        MGB_LAUNCH(k_atom_cat<kM>, B * N, kAtomThreads, asm_, plan->side3, plan->d_desc, k, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+                   w.A[k], w.E[k], w.cat[k], kAtomPhaseB);
+      }
+      MGB_LAUNCH_OK("k_atom_cat");
+      MGB_CUDA_OK(cudaEventRecord(plan->ev_join3[k], plan->side3));
+    }
     const size_t dsm = sizeof(float2) * (size_t)N * L.nlm_in * L.C;
     const size_t esm = sizeof(float2) * 70 * kEdgeC + sizeof(float) * (2 * L.C * (kRadFeat + 1));
     dim3 egrid(pair_blocks, kNL);
+    const bool small = edge_small(B, N);   // few pairs: five threads per (pair, ell)
+    dim3 sgrid((unsigned)(((long long)B * N * N + kPairCsPairs - 1) / kPairCsPairs), kNL);
+    const size_t ssm = esm + sizeof(float2) * kPairCsPairs * kEdgeC;
     if (k == 0) {
       MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);
       MGB_LAUNCH_OK("k_dot_fwd");
-      MGB_LAUNCH(k_edge_pairs_fwd<1>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
-                 (const float*)nullptr, w.E[k], w.pair_slot);
+      MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[0], 0));   // Wt is ready
+      if (small) {
+        MGB_LAUNCH(k_edge_pairs_fwd_cs<1>, sgrid, kPairCsThreads, ssm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off,
+                   w.D[k], (const float*)nullptr, w.E[k], w.pair_slot);
+      } else {
+        MGB_LAUNCH(k_edge_pairs_fwd<1>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
+                   (const float*)nullptr, w.E[k], w.pair_slot);
+      }
     } else {
       MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<kNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       MGB_LAUNCH(k_dot_fwd<kNL>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);
       MGB_LAUNCH_OK("k_dot_fwd");
-      MGB_LAUNCH(k_edge_pairs_fwd<kNL>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
-                 w.E[k - 1], w.E[k], (int*)nullptr);
+      if (small) {
+        MGB_LAUNCH(k_edge_pairs_fwd_cs<kNL>, sgrid, kPairCsThreads, ssm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off,
+                   w.D[k], w.E[k - 1], w.E[k], (int*)nullptr);
+      } else {
+        MGB_LAUNCH(k_edge_pairs_fwd<kNL>, egrid, kPairThreads, esm, st, plan->d_desc, k, B, P, w.Wt, pos, w.n_atoms, w.pair_off, w.D[k],
+                   w.E[k - 1], w.E[k], (int*)nullptr);
+      }
     }
     MGB_LAUNCH_OK("k_edge_pairs_fwd");
     int rc = k == 0 ? launch_atom_fwd<1>(plan, k, B, P, pos, w, st) : launch_atom_fwd<kM>(plan, k, B, P, pos, w, st);

@@ -11,8 +11,18 @@ static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const flo
   if (rc != MGB_OK) return rc;
   const size_t smem = sizeof(float) * atom_bwd_smem_floats(L, d.N);
   MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (small_atoms(B, d.N)) {
+    // column pass + own-atom terms on side3, beside the row pass -> edge backward -> dot backward chain of the main stream
+    MGB_CUDA_OK(cudaEventRecord(plan->ev_fork3[level], st));
+    MGB_CUDA_OK(cudaStreamWaitEvent(plan->side3, plan->ev_fork3[level], 0));
+    MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomBwdThreads, smem, plan->side3, plan->d_desc, level, pos, w.n_atoms, w.atom_off,
+               w.atom_list, B, w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE, kAtomPhaseB);
+    MGB_LAUNCH_OK("k_atom_bwd");
+    MGB_CUDA_OK(cudaEventRecord(plan->ev_join3[level], plan->side3));
+  }
   MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
-             w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE);
+             w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE,
+             small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB);
   MGB_LAUNCH_OK("k_atom_bwd");
   return MGB_OK;
 }
@@ -44,8 +54,6 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     MGB_LAUNCH(k_policy_bwd, grid, kPolicyBwdThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
                w.trans, w.pol_state, g_logp, g_ent, g_v, o, w.mix_stage, grad);
     MGB_LAUNCH_OK("k_policy_bwd");
-    MGB_LAUNCH(k_mixer_dw_finish, 2, 256, 0, st, plan->d_desc, w.mix_stage, grad);
-    MGB_LAUNCH_OK("k_mixer_dw_finish");
   }
   {
     int rc = launch_rows_mlp_bwd(plan, B, P, w, st);
@@ -57,6 +65,8 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   // fork: the MLP weight gradients only need the head kernels' outputs; they run beside the CG levels
   MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[K], st));
   MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[K], 0));
+  MGB_LAUNCH(k_mixer_dw_finish, 2, 256, 0, side, plan->d_desc, w.mix_stage, grad);   // expands the compact mixer cotangent
+  MGB_LAUNCH_OK("k_mixer_dw_finish");
   {
     DwProblemList list;
     int q = 0;
@@ -87,12 +97,10 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   for (int k = K - 1; k >= 0; --k) {
     const LevelDesc& L = d.lv[k];
     if (k < K - 1) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[k + 1], 0));   // mix_dw(k+1) still reads dA[(k+2)&1] == dA[k&1]
+    if (k < K - 1 && small_atoms(B, N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[k + 1], 0));   // column pass of level k+1: dA_{k+1} complete, dcat free
     MGB_CUDA_OK(cudaMemsetAsync(w.dA[k & 1], 0, sizeof(float) * BN * kM * cmax * 2, st));
-    const int acc_dE = (k < K - 1) ? 1 : 0;
-    int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, st);
-    if (rc != MGB_OK) return rc;
     {
-      // fork: the atom-mix weight gradient (reads cat_k and dA_{k+1}) runs beside the edge level of the same k
+      // fork: the atom-mix weight gradient (reads cat_k and dA_{k+1}, both complete here) runs beside the whole level
       MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[k], st));
       MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[k], 0));
       const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + kMixDwAtoms - 1) / kMixDwAtoms, 148 * 2));
@@ -118,19 +126,27 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       MGB_LAUNCH_OK("k_mix_dw");
       MGB_CUDA_OK(cudaEventRecord(plan->ev_join[k], side));
     }
+    const int acc_dE = (k < K - 1) ? 1 : 0;
+    int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, st);
+    if (rc != MGB_OK) return rc;
     {
       const unsigned pair_blocks = (unsigned)((BN * N + kPairThreads - 1) / kPairThreads);
       const size_t esm = sizeof(float2) * (size_t)L.sumCatE * kEdgeC + sizeof(float) * (kNL * 2 * L.C * (kRadFeat + 1));
       EdgeScratch sc{w.e_dpre, w.e_R, w.e_dR, w.e_f};
       const int dw_chunks = (int)std::max<size_t>(1, std::min<size_t>((BN * N + kEdgeDwTile - 1) / kEdgeDwTile, 148 * 2));
       dim3 dwgrid(dw_chunks, kNL);
-      const bool split = edge_bwd_split(B, N);
+      const bool split = edge_bwd_split(B, N), small = edge_small(B, N);
+      dim3 sgrid((unsigned)((BN * N + kPairCsPairs - 1) / kPairCsPairs), kNL);
+      const size_t ssm = sizeof(float2) * 70 * kEdgeC + sizeof(float) * (2 * L.C * (kRadFeat + 1));
       const long long slice = (long long)BN * N * kNL * L.C;
       dim3 pgrid(pair_blocks, split ? kNL : 1);
       // the scratch of the previous (higher) level's edge backward is still being reduced by k_edge_dw on side2
       if (k < K - 1) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join2[k + 1], 0));
 #define MGB_EDGE_BWD(NL, EPREV, DEPREV, DOTTHREADS)                                                                              \
-  if (split) {                                                                                                                      \
+  if (small) {                                                                                                                      \
+    MGB_LAUNCH(k_edge_pairs_bwd_cs<NL>, sgrid, kPairCsThreads, ssm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,          \
+               w.dE[k & 1], DEPREV, w.dD, slice, sc, grad);                                                                         \
+  } else if (split) {                                                                                                                    \
     MGB_CUDA_OK(cudaFuncSetAttribute((k_edge_pairs_bwd<NL, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));         \
     MGB_LAUNCH((k_edge_pairs_bwd<NL, true>), pgrid, kPairThreads, esm, st, plan->d_desc, k, B, P, pos, w.n_atoms, w.pair_off,       \
                w.dE[k & 1], DEPREV, w.dD, slice, sc, grad);                                                                         \
@@ -157,17 +173,11 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     }
   }
   {
-    // InputLinear weight gradient (needs dA_0) on the main stream; its problem descriptor sits after the head problems
-    DwProblemList list;
-    list.p[0] = DwProblem{w.X, w.dA[0], (long long)BN, d.S_in, 2 * d.C, kRowsValid, d.p_inW, d.p_inb};
-    list.n = 1;
-    int nw = 0;
-    for (int o0 = 0; o0 < list.p[0].No; o0 += kDwTileO) list.w[nw++] = DwWork{0, o0};
-    list.nw = nw;
-    const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
-    dim3 grid(chunks, nw);
-    MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, list, w.n_atoms, N, grad);
-    MGB_LAUNCH_OK("k_dw_grouped");
+    // InputLinear weight gradient (needs the complete dA_0): the tail of the main stream
+    if (small_atoms(B, N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[0], 0));
+    const int per_cta = (B + 147) / 148;
+    MGB_LAUNCH(k_input_dw, (B + per_cta - 1) / per_cta, 256, 0, st, plan->d_desc, B, per_cta, w.n_atoms, w.X, w.dA[0], grad);
+    MGB_LAUNCH_OK("k_input_dw");
   }
   MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[0], 0));    // join the side streams (their last work is mix_dw(0), edge_dw(0))
   MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join2[0], 0));

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kAtomBwdThreads, 2)
 k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ pos, const int* __restrict__ n_atoms,
            const int* __restrict__ atom_off, const int* __restrict__ atom_list, int B, const float* __restrict__ A_in,
            const float* __restrict__ E, const float* __restrict__ dcat, float* __restrict__ dA_in, float* __restrict__ dE,
-           int accumulate_dE) {
+           int accumulate_dE, int phases) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C;
@@ -398,8 +398,11 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const int x = owner ? threadIdx.x / C : 0, c = owner ? threadIdx.x % C : 0;
   const int l1 = ell_of_lm(x);
   const bool col_owner = owner && x < NLM2;
+  // small minibatches launch the two passes as separate kernels (kAtomPhaseA / kAtomPhaseB): the edge backward only waits
+  // for the row pass, the column pass runs beside it on a side stream
+  const bool do_rows = (phases & kAtomPhaseA) != 0, do_cols = (phases & kAtomPhaseB) != 0;
   // ---- (B) row pass
-  {
+  if (do_rows) {
     float2 dTrow[NLM2];   // dT[x][y], y < NLM2
     if (owner) {
       MGB_UNROLL
@@ -438,7 +441,7 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     }
   }
   // ---- (C) column pass + own-atom terms
-  {
+  if (do_cols) {
     float2 dTcol[kM];     // dT[y][x], y < 25   (threads x < NLM2)
     if (col_owner) {
       MGB_UNROLL
@@ -495,7 +498,7 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   const LevelDesc& L = d.lv[level];
   const int Cout = L.Cout, l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1;
   const int n_at = atom_off[B];
-  const int per = (n_at + gridDim.x - 1) / gridDim.x;
+  const int per = max((int)((n_at + gridDim.x - 1) / gridDim.x), 2 * kMixDwAtoms);   // every CTA flushes K * Cout atomics: not too few atoms
   const int a0 = per * blockIdx.x, a1 = min(n_at, a0 + per);
   if (a0 >= a1) return;
   MGB_DYN_SMEM(float2, sd);   // [kMixDwAtoms][nm][CO], zero beyond Cout
@@ -577,8 +580,33 @@ __global__ void k_dot_bwd(const CovDesc* __restrict__ dp, int level, const int* 
       cfmacl(acc, Ab[(long long)j * NLM * C + lm_index(l, -m) * C + c], g);
     }
     const float sg = (m & 1) ? -1.f : 1.f;
-    dst[idx].x += sg * acc.x;
-    dst[idx].y += sg * acc.y;
+    atomic_add2(dst + idx, make_float2(sg * acc.x, sg * acc.y));   // the atom level's column pass may still be adding to dA_k
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// InputLinear weight gradient (cormorant InputLinear, covariant/modules.py:106): dW[o][s] += sum_rows dA0[r][o] X[r][s],
+// db[o] += sum_rows dA0[r][o] over the valid atoms.  The last kernel of the backward: thread = one (o, s) entry
+// (s == S_in is the bias), a CTA walks the atoms of a few canvases and flushes one atomic per entry.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_input_dw(const CovDesc* __restrict__ dp, int B, int per_cta, const int* __restrict__ n_atoms, const float* __restrict__ X,
+           const float* __restrict__ dA0, float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  const int N = d.N, S = d.S_in, C2 = 2 * d.C;
+  const int b0 = blockIdx.x * per_cta, b1 = min(B, b0 + per_cta);
+  for (int e = threadIdx.x; e < C2 * (S + 1); e += blockDim.x) {
+    const int o = e / (S + 1), sidx = e - o * (S + 1);
+    float acc = 0.f;
+    for (int b = b0; b < b1; ++b) {
+      const int n = n_atoms[b];
+      for (int i = 0; i < n; ++i) {
+        const long long r = (long long)b * N + i;
+        const float x = sidx < S ? X[r * S + sidx] : 1.f;
+        acc = fmaf(dA0[r * C2 + o], x, acc);
+      }
+    }
+    if (acc != 0.f) atomicAdd(sidx < S ? grad + d.p_inW + (long long)o * S + sidx : grad + d.p_inb + o, acc);
   }
 }
 

@@ -290,6 +290,8 @@ __device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2*
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kAtomThreads = 256;
 constexpr int kJChunk = 8;
+constexpr int kAtomPhaseA = 1;   // forward: CG aggregate over the neighbours (needs E_k)   backward: row pass -> dE
+constexpr int kAtomPhaseB = 2;   // forward: CG square + pass-through (needs A_k only)       backward: column pass + own atom -> dA
 
 __host__ __device__ inline int atom_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
@@ -324,7 +326,7 @@ template <int NLM2>
 __global__ void __launch_bounds__(kAtomThreads)
 k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ pos, const int* __restrict__ n_atoms,
            const int* __restrict__ atom_off, const int* __restrict__ atom_list, int B, const float* __restrict__ A_in,
-           const float* __restrict__ E, float* __restrict__ cat_out) {
+           const float* __restrict__ E, float* __restrict__ cat_out, int phases) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = L.C;
@@ -344,6 +346,15 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const float* pos_b = pos + (long long)b * N * 3;
   float2* co = reinterpret_cast<float2*>(cat_out) + (long long)slot * L.totA;
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
+  if (!(phases & kAtomPhaseA)) {   // only the blocks that depend on A_i alone
+    __syncthreads();
+    cg_gather<true>(L.sq, C, sAi, co);
+    for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) {
+      const int lm = idx / C, cc = idx % C, l = ell_of_lm(lm);
+      co[L.offA[l] + (lm - l * l) * L.catA[l] + L.in_block[l] * C + cc] = sAi[idx];
+    }
+    return;
+  }
   neighbour_harmonics(pos_b, i, n, sYall);
 
   const bool owner = (int)threadIdx.x < kM * C;
@@ -373,6 +384,7 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   }
   __syncthreads();
   cg_gather<false>(L.ag, C, sT, co);
+  if (!(phases & kAtomPhaseB)) return;
   cg_gather<true>(L.sq, C, sAi, co);
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) {
     const int lm = idx / C, cc = idx % C, l = ell_of_lm(lm);

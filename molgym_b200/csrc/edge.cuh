@@ -139,6 +139,28 @@ k_edge_pairs_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
     if (c < C) Eo[c] = make_float2(acc[c].x * g.s, acc[c].y * g.s);
 }
 
+// scale / phase cotangents of a CTA: warp reduction, shared-memory reduction over the warps, then ONE global atomic per CTA
+// and parameter (all CTAs of all ells hit the same 16 floats: per-warp atomics serialise in L2)
+__device__ __forceinline__ void edge_flush_scale_phase(const float* dsc, const float* dph, float* __restrict__ g_scales,
+                                                       float* __restrict__ g_phases) {
+  __shared__ float s_red[2 * kTrig];
+  if (threadIdx.x < 2 * kTrig) s_red[threadIdx.x] = 0.f;
+  __syncthreads();
+  MGB_UNROLL
+  for (int t = 0; t < kTrig; ++t) {
+    const float a = warp_sum(dsc[t]), b2 = warp_sum(dph[t]);
+    if ((threadIdx.x & 31) == 0) {
+      if (a != 0.f) atomicAdd(&s_red[t], a);
+      if (b2 != 0.f) atomicAdd(&s_red[kTrig + t], b2);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kTrig) {
+    const float v = s_red[threadIdx.x];
+    if (v != 0.f) atomicAdd(threadIdx.x < kTrig ? g_scales + threadIdx.x : g_phases + (threadIdx.x - kTrig), v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Backward, per-pair part: one thread per pair, loop over the five ells.
 //   reads  dE[pair][l][c']                      (cotangent of this level's edge scalars)
@@ -274,14 +296,216 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
     }
   }
   // scale / phase cotangents: warp reduction, one atomic per warp and parameter
-  MGB_UNROLL
-  for (int t = 0; t < kTrig; ++t) {
-    const float a = warp_sum(dsc[t]), b2 = warp_sum(dph[t]);
-    if ((threadIdx.x & 31) == 0) {
-      if (a != 0.f) atomicAdd(grad + L.p_scales + t, a);
-      if (b2 != 0.f) atomicAdd(grad + L.p_phases + t, b2);
+  edge_flush_scale_phase(dsc, dph, grad + L.p_scales, grad + L.p_phases);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Small minibatches (a few thousand pairs): the same two per-pair kernels with kEdgeCs threads per (pair, ell), so that
+// the work fills the machine and every thread's serial chain is 5x shorter.
+//   forward : thread (pair, ell, g) owns the output channels c' = g*kEdgeCg .. and the radial filters of the same indices
+//             (exchanged through shared memory);
+//   backward: thread (pair, ell, g) owns a fifth of every segment of dcat_l (previous edge / dot / radial) — the radial
+//             feature cotangent is linear in the owned radial outputs, so the scale / phase cotangents need no exchange.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kEdgeCs = 5;                        // threads per (pair, ell)
+constexpr int kEdgeCg = kEdgeC / kEdgeCs;         // channels per thread
+constexpr int kPairCsPairs = 32;                  // pairs per CTA
+constexpr int kPairCsThreads = kPairCsPairs * kEdgeCs;
+
+template <int NLIN>
+__global__ void __launch_bounds__(kPairCsThreads)
+k_edge_pairs_fwd_cs(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ Wt,
+                    const float* __restrict__ pos, const int* __restrict__ n_atoms, const int* __restrict__ pair_off,
+                    const float* __restrict__ D, const float* __restrict__ E_prev, float* __restrict__ E_out,
+                    int* __restrict__ pair_slot) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
+  const int total = pair_off[B];
+  if ((int)(blockIdx.x * kPairCsPairs) >= total) return;
+  MGB_DYN_SMEM(float2, smem);
+  float2* sW = smem;                                          // [K][kEdgeC]   WE_l transposed ([k][c'])
+  float2* sR = sW + K * kEdgeC;                               // [pairs][kEdgeC] radial filter values of this ell
+  float* sRad = reinterpret_cast<float*>(sR + kPairCsPairs * kEdgeC);   // [2C][32] radial linear of this ell + [2C] bias
+  {
+    const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_edge[level]) + L.offE[l];
+    for (int idx = threadIdx.x; idx < K * kEdgeC; idx += blockDim.x) {
+      const int k = idx / kEdgeC, c = idx - k * kEdgeC;
+      sW[idx] = c < C ? src[k * C + c] : make_float2(0.f, 0.f);
+    }
+    for (int idx = threadIdx.x; idx < C2 * kRadFeat; idx += blockDim.x) sRad[idx] = P[L.p_radW + (long long)l * C2 * kRadFeat + idx];
+    for (int idx = threadIdx.x; idx < C2; idx += blockDim.x) sRad[C2 * kRadFeat + idx] = P[L.p_radb + l * C2 + idx];
+  }
+  __syncthreads();
+  const int pl = threadIdx.x / kEdgeCs, g = threadIdx.x - pl * kEdgeCs;
+  const int p = blockIdx.x * kPairCsPairs + pl;
+  const bool valid = p < total;
+  PairGeom geo;
+  long long pair = 0;
+  if (valid) {
+    const PairId id = decode_pair(p, B, pair_off, n_atoms);
+    geo = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
+    pair = ((long long)id.b * N + id.i) * N + id.j;
+    if (pair_slot && l == 0 && g == 0) pair_slot[p] = (int)pair;
+    float f[kRadFeat];
+    rad_features_all(geo, P + L.p_scales, P + L.p_phases, f, nullptr);
+    MGB_UNROLL
+    for (int q = 0; q < kEdgeCg; ++q) {
+      const int k = g * kEdgeCg + q;
+      float re = 0.f, im = 0.f;
+      if (k < C) {
+        re = sRad[C2 * kRadFeat + 2 * k]; im = sRad[C2 * kRadFeat + 2 * k + 1];
+        const float* wr = sRad + (2 * k) * kRadFeat;
+        MGB_UNROLL
+        for (int t = 0; t < kRadFeat; ++t) { re = fmaf(wr[t], f[t], re); im = fmaf(wr[kRadFeat + t], f[t], im); }
+      }
+      sR[pl * kEdgeC + k] = make_float2(re, im);
     }
   }
+  __syncthreads();
+  if (!valid) return;
+  float2 acc[kEdgeCg];
+  MGB_UNROLL
+  for (int q = 0; q < kEdgeCg; ++q) acc[q] = make_float2(0.f, 0.f);
+  const float2* w = sW + g * kEdgeCg;
+  int kk = 0;
+  if (L.has_prev) {
+    const float2* x = reinterpret_cast<const float2*>(E_prev) + pair * kNL * C + l * C;
+    for (int k = 0; k < C; ++k) {
+      const float2 xv = x[k];
+      MGB_UNROLL
+      for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[(kk + k) * kEdgeC + q], xv);
+    }
+    kk += C;
+  }
+  if (l < NLIN) {
+    const float2* x = reinterpret_cast<const float2*>(D) + pair * kNL * C;
+#pragma unroll 5
+    for (int k = 0; k < NLIN * C; ++k) {
+      const float2 xv = x[k];
+      MGB_UNROLL
+      for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[(kk + k) * kEdgeC + q], xv);
+    }
+    kk += NLIN * C;
+  }
+  for (int k = 0; k < C; ++k) {
+    const float2 xv = sR[pl * kEdgeC + k];
+    MGB_UNROLL
+    for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[(kk + k) * kEdgeC + q], xv);
+  }
+  float2* Eo = reinterpret_cast<float2*>(E_out) + pair * kNL * C + l * C;
+  MGB_UNROLL
+  for (int q = 0; q < kEdgeCg; ++q)
+    if (g * kEdgeCg + q < C) Eo[g * kEdgeCg + q] = make_float2(acc[q].x * geo.s, acc[q].y * geo.s);
+}
+
+template <int NLIN>
+__global__ void __launch_bounds__(kPairCsThreads)
+k_edge_pairs_bwd_cs(const CovDesc* __restrict__ dp, int level, int B, const float* __restrict__ P, const float* __restrict__ pos,
+                    const int* __restrict__ n_atoms, const int* __restrict__ pair_off, const float* __restrict__ dE,
+                    float* __restrict__ dE_prev, float* __restrict__ dD, long long slice_stride /* complex */, EdgeScratch sc,
+                    float* __restrict__ grad) {
+  const CovDesc& d = *dp;
+  const LevelDesc& L = d.lv[level];
+  const int N = d.N, C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
+  const int total = pair_off[B];
+  if ((int)(blockIdx.x * kPairCsPairs) >= total) return;
+  MGB_DYN_SMEM(float2, smem);
+  float2* sW = smem;                                              // [K][kEdgeC]: WE_l of the REFERENCE layout read as [k][c'], padded
+  float* sRad = reinterpret_cast<float*>(sW + K * kEdgeC);        // [2C][32] + [2C]
+  {
+    const float2* src = reinterpret_cast<const float2*>(P + L.p_edgeW) + L.offE[l];   // [c'][k]
+    for (int idx = threadIdx.x; idx < K * kEdgeC; idx += blockDim.x) {
+      const int k = idx / kEdgeC, c = idx - k * kEdgeC;
+      sW[idx] = c < C ? src[c * K + k] : make_float2(0.f, 0.f);
+    }
+    for (int idx = threadIdx.x; idx < C2 * kRadFeat; idx += blockDim.x) sRad[idx] = P[L.p_radW + (long long)l * C2 * kRadFeat + idx];
+    for (int idx = threadIdx.x; idx < C2; idx += blockDim.x) sRad[C2 * kRadFeat + idx] = P[L.p_radb + l * C2 + idx];
+  }
+  __syncthreads();
+  const int pl = threadIdx.x / kEdgeCs, g = threadIdx.x - pl * kEdgeCs;
+  const int p = blockIdx.x * kPairCsPairs + pl;
+  float dsc[kTrig], dph[kTrig];
+  MGB_UNROLL
+  for (int t = 0; t < kTrig; ++t) { dsc[t] = 0.f; dph[t] = 0.f; }
+  if (p < total) {
+    const PairId id = decode_pair(p, B, pair_off, n_atoms);
+    const PairGeom geo = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
+    const long long pair = ((long long)id.b * N + id.i) * N + id.j;
+    float f[kRadFeat], df[kRadFeat];
+    rad_features_all(geo, P + L.p_scales, P + L.p_phases, f, nullptr);
+    MGB_UNROLL
+    for (int t = 0; t < kRadFeat; ++t) {
+      df[t] = 0.f;
+      if (l == 0 && g == 0) sc.f[(long long)p * kRadFeat + t] = f[t];
+    }
+    float2 dpre[kEdgeC];
+    const float2* g_in = reinterpret_cast<const float2*>(dE) + pair * kNL * C + l * C;
+    MGB_UNROLL
+    for (int c = 0; c < kEdgeC; ++c) {
+      dpre[c] = c < C ? make_float2(g_in[c].x * geo.s, g_in[c].y * geo.s) : make_float2(0.f, 0.f);
+      if (c < C && g == 0) reinterpret_cast<float2*>(sc.dpre)[((long long)p * kNL + l) * C + c] = dpre[c];
+    }
+    int kk = 0;
+    if (L.has_prev) {
+      float2* o = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C + l * C;
+      MGB_UNROLL
+      for (int q = 0; q < kEdgeCg; ++q) {
+        const int k = g * kEdgeCg + q;
+        if (k < C) {
+          float2 a = make_float2(0.f, 0.f);
+          MGB_UNROLL
+          for (int c = 0; c < kEdgeC; ++c) cfmacl(a, sW[(kk + k) * kEdgeC + c], dpre[c]);
+          o[k] = a;
+        }
+      }
+      kk += C;
+    }
+    if (l < NLIN) {
+      float2* od = reinterpret_cast<float2*>(dD) + (long long)l * slice_stride + pair * kNL * C;
+      const int per = (NLIN * C + kEdgeCs - 1) / kEdgeCs;
+      const int k0 = g * per, k1 = min(NLIN * C, k0 + per);
+      for (int k = k0; k < k1; ++k) {
+        float2 a = make_float2(0.f, 0.f);
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) cfmacl(a, sW[(kk + k) * kEdgeC + c], dpre[c]);
+        od[k] = a;
+      }
+      kk += NLIN * C;
+    }
+    MGB_UNROLL
+    for (int q = 0; q < kEdgeCg; ++q) {
+      const int k = g * kEdgeCg + q;
+      if (k < C) {
+        float2 a = make_float2(0.f, 0.f);
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) cfmacl(a, sW[(kk + k) * kEdgeC + c], dpre[c]);
+        const float* wr = sRad + (2 * k) * kRadFeat;
+        float re = sRad[C2 * kRadFeat + 2 * k], im = sRad[C2 * kRadFeat + 2 * k + 1];
+        MGB_UNROLL
+        for (int t = 0; t < kRadFeat; ++t) {
+          re = fmaf(wr[t], f[t], re);
+          im = fmaf(wr[kRadFeat + t], f[t], im);
+          df[t] = fmaf(wr[t], a.x, fmaf(wr[kRadFeat + t], a.y, df[t]));
+        }
+        sc.R[((long long)p * kNL + l) * C2 + 2 * k] = re;
+        sc.R[((long long)p * kNL + l) * C2 + 2 * k + 1] = im;
+        sc.dR[((long long)p * kNL + l) * C2 + 2 * k] = a.x;
+        sc.dR[((long long)p * kNL + l) * C2 + 2 * k + 1] = a.y;
+      }
+    }
+    {   // f is no longer needed: reuse its registers for d f[t] / d arg_t = cos(arg) r^-p
+      float tmp[kRadFeat];
+      rad_features_all(geo, P + L.p_scales, P + L.p_phases, tmp, f);
+    }
+    MGB_UNROLL
+    for (int t = 0; t < kRadFeat; ++t) {
+      const float gv = df[t] * f[t];
+      dph[t >> 2] += gv;
+      dsc[t >> 2] = fmaf(gv, kTwoPi * geo.r, dsc[t >> 2]);
+    }
+  }
+  edge_flush_scale_phase(dsc, dph, grad + L.p_scales, grad + L.p_phases);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -307,7 +531,7 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
   const LevelDesc& L = d.lv[level];
   const int C = L.C, C2 = 2 * C, l = blockIdx.y, K = L.catE[l];
   const int total = pair_off[B];
-  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int per = max((int)((total + gridDim.x - 1) / gridDim.x), kEdgeDwTile);   // at least one full tile per CTA: fewer atomics
   const int p_begin = per * blockIdx.x, p_end = min(total, p_begin + per);
   if (p_begin >= p_end) return;
   __shared__ __align__(16) float2 s_cat[kEdgeDwTile][kEdgeKMax];

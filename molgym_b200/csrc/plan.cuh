@@ -1,5 +1,6 @@
 // plan.cuh — host-side plan: descriptors, Clebsch-Gordan tables, parameter layout, workspace carving.
 #pragma once
+#include <cstdlib>
 #include <cstdarg>
 #include <memory>
 
@@ -16,9 +17,10 @@ struct mgb_cov_plan {
   mgb::TransposeSeg* d_segs = nullptr;
   std::vector<long long> p_offsets, p_numels;
   // fork/join of independent backward kernels (weight-gradient reductions next to the edge level)
-  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;
   cudaEvent_t ev_fork[mgb::kMaxLevels + 1] = {}, ev_join[mgb::kMaxLevels + 1] = {};
   cudaEvent_t ev_fork2[mgb::kMaxLevels + 1] = {}, ev_join2[mgb::kMaxLevels + 1] = {};   // edge weight gradients (side2)
+  cudaEvent_t ev_fork3[mgb::kMaxLevels + 1] = {}, ev_join3[mgb::kMaxLevels + 1] = {};   // small minibatches: half of the atom level (side3)
 };
 
 namespace mgb {
@@ -162,7 +164,25 @@ struct CovWs {
 };
 
 // small minibatches: the per-pair edge backward is split over the five ells (one thread per (pair, ell))
-inline bool edge_bwd_split(int B, int N) { return (long long)B * N * N < 148ll * 2048; }
+// MGB_EDGE_MODE=0|1|2 forces the decomposition of the per-pair edge kernels (tests): 0 thread per pair, 1 thread per
+// (pair, ell), 2 five threads per (pair, ell)
+inline int edge_mode_override() {
+  const char* e = std::getenv("MGB_EDGE_MODE");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
+}
+inline bool edge_bwd_split(int B, int N) {
+  const int m = edge_mode_override();
+  return m >= 0 ? m >= 1 : (long long)B * N * N < 148ll * 2048;
+}
+// small minibatches (the grid of one-atom CTAs is about one wave): the atom kernels are launched as two half kernels, the
+// half that is off the critical path on a side stream (forward: CG square + pass-through blocks of cat, which only need
+// A_k; backward: column pass + own-atom terms, which the edge backward does not wait for)
+inline bool small_atoms(int B, int N) { return (long long)B * N < 1536; }
+// a few thousand pairs only: five threads per (pair, ell) (k_edge_pairs_*_cs)
+inline bool edge_small(int B, int N) {
+  const int m = edge_mode_override();
+  return m >= 0 ? m == 2 : (long long)B * N * N * 5 < 148ll * 1024;
+}
 
 inline CovWs carve_workspace(const CovDesc& d, int B, void* base) {
   CovWs w;

@@ -85,6 +85,31 @@ def test_fresh_canvases_against_oracle(which, batch):
     assert_grads_close(grads_of(agent), ref_grads)
 
 
+@pytest.mark.parametrize('mode', ['0', '1', '2'])
+def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
+    """The per-pair edge kernels exist in three decompositions picked by minibatch size (thread per pair, per (pair, ell),
+    five threads per (pair, ell)); MGB_EDGE_MODE forces each of them on the same canvases."""
+    from oracle.molgym_oracle import CovariantOracle, ppo_loss
+    from molgym_b200 import ppo
+    monkeypatch.setenv('MGB_EDGE_MODE', mode)
+    cfg = synth.CONFIGS['C3']
+    torch.manual_seed(5)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle.load_state_dict({k: v.detach().cpu() for k, v in agent.state_dict().items()})
+    obs, n = synth.make_observations(cfg, batch=36)
+    act = synth.make_actions(cfg, obs, n)
+    ref = oracle.step(obs, act)
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, ref['logp'].detach().numpy())
+    loss, _ = ppo.compute_loss(agent, dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret), 0.2, 0.5, 0.01)
+    loss.backward()
+    ref_loss, _ = ppo_loss(ref['logp'], ref['ent'], ref['v'], old_logp, adv, ret, 0.2, 0.5, 0.01)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5
+    ref_grads = {k: (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k, p in oracle.named_parameters()}
+    assert_grads_close(grads_of(agent), ref_grads)
+
+
 def test_gradients_accumulate_over_minibatches_like_autograd():
     """ppo.train sums gradients over minibatches before one optimizer step (ppo.py:118-131)."""
     cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)

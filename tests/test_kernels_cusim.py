@@ -42,8 +42,11 @@ def test_golden_forward_backward(name):
     assert_grads_close(got, golden_grads(g))
 
 
-@pytest.mark.parametrize('levels,beta,zs,canvas', [(1, -10.0, [0, 9, 16], 7), (2, None, [0, 1, 6, 7, 8], 6)])
-def test_fresh_canvases_against_oracle(levels, beta, zs, canvas):
+@pytest.mark.parametrize('levels,beta,zs,canvas,edge_mode', [(1, -10.0, [0, 9, 16], 7, None), (2, None, [0, 1, 6, 7, 8], 6, '0'),
+                                                             (2, None, [0, 1, 6, 7, 8], 6, '1'), (2, None, [0, 1, 6, 7, 8], 6, '2')])
+def test_fresh_canvases_against_oracle(levels, beta, zs, canvas, edge_mode, monkeypatch):
+    if edge_mode is not None:   # the three decompositions of the per-pair edge kernels (plan.cuh: edge_mode_override)
+        monkeypatch.setenv('MGB_EDGE_MODE', edge_mode)
     cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=canvas, network_width=32, num_cg_levels=levels, beta=beta,
                               bag={z: 2 for z in zs if z}, bag_scale=4, seed=levels)
     torch.manual_seed(levels)
