@@ -60,6 +60,29 @@ class _CovEvaluate(torch.autograd.Function):
         return (None, ) * 6
 
 
+class _FusedPPOLoss(torch.autograd.Function):
+    """The scalar PPO loss of CovariantAC.fused_ppo_loss.  Its parameter gradient already sits in the step's scratch buffer
+    (the backward graph was enqueued right behind the forward); backward() scales it by the incoming cotangent into `.grad`."""
+
+    @staticmethod
+    def forward(ctx, anchor, agent, state, loss):
+        ctx.agent, ctx.state, ctx.generation = agent, state, state.generation
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.state.generation != ctx.generation:
+            raise RuntimeError('this PPO loss was superseded by a later compute_loss on the same minibatch size before it was '
+                               'differentiated; set agent.fused_ppo = False to keep several losses alive')
+        ctx.agent._fused_backward(ctx.state, g)
+        return None, None, None, None
+
+
+class _FusedState:
+    """Persistent buffers + captured CUDA graphs of the fused PPO step for one minibatch size."""
+    pass
+
+
 class CovariantAC(FlatParamMixin, AbstractActorCritic):
     def __init__(
         self,
@@ -93,6 +116,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         self.bag_scale = bag_scale
         self.canvas_size = self.observation_space.canvas_space.size
         self.data_parallel = False   # set by molgym_b200.parallel.shard_agent
+        self.fused_ppo = True        # molgym_b200.ppo.compute_loss may use fused_ppo_loss (CUDA-graph replay of the whole step)
         self._init_native()
         self._init_parameters()
 
@@ -126,6 +150,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         assert len(self._p_names) == n
         self._cat_sizes = list(cats)
         self._ws_cache: Dict[int, torch.Tensor] = {}
+        self._fused_cache: Dict[tuple, _FusedState] = {}
 
     def _param_shapes(self) -> Dict[str, tuple]:
         C, Z, cpe, W, G = self.num_channels_hidden, len(self.zs), self.num_channels_per_element, self.network_width, self.num_gaussians
@@ -208,7 +233,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ('_plan', '_cfg', '_ws_cache', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
+        for k in ('_plan', '_cfg', '_ws_cache', '_fused_cache', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
             state.pop(k, None)
         return state
 
@@ -284,6 +309,138 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                                                   g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), target.data_ptr(),
                                                   accumulate, stream))
             self._finish_grads(keep)
+
+    # ------------------------------------------------------------------------------------------------------
+    # fused PPO minibatch step: pack -> one H2D copy -> CUDA-graph replay of forward + PPO-clip loss, then of the backward
+    # ------------------------------------------------------------------------------------------------------
+    def _capture(self, fn):
+        dev = self.device
+        fn(torch.cuda.current_stream(dev).cuda_stream)   # eager warm-up: function attributes, lazy module loading
+        torch.cuda.current_stream(dev).synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                fn(torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return graph
+
+    def _fused_state(self, B: int, clip_ratio: float, vf_coef: float, entropy_coef: float) -> _FusedState:
+        key = (B, float(clip_ratio), float(vf_coef), float(entropy_coef), self._flat.data_ptr())
+        st = self._fused_cache.get(key)
+        if st is not None:
+            return st
+        lib = _lib.load()
+        dev, N, Z = self.device, self.canvas_size, len(self.zs)
+        st = _FusedState()
+        sizes = [B * N * 3 * 4, B * N * 4, B * Z * 4, B * 6 * 4, B * 4, B * 8, B * 8]   # pos, charges, bags, act, old_logp, adv, ret
+        offs = [0]
+        for sz in sizes:
+            offs.append((offs[-1] + sz + 255) // 256 * 256)
+        st.host = torch.empty(offs[-1], dtype=torch.uint8, pin_memory=True)
+        st.dev = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+        h = st.host.numpy()
+        seg = lambda buf, i: buf[offs[i]:offs[i] + sizes[i]]
+        st.h_pos = seg(h, 0).view(np.float32).reshape(B, N, 3)
+        st.h_charges = seg(h, 1).view(np.int32).reshape(B, N)
+        st.h_bags = seg(h, 2).view(np.float32).reshape(B, Z)
+        st.h_act = seg(h, 3).view(np.float32).reshape(B, 6)
+        st.h_old = seg(h, 4).view(np.float32)
+        st.h_adv = seg(h, 5).view(np.float64)
+        st.h_ret = seg(h, 6).view(np.float64)
+        st.pos = seg(st.dev, 0).view(torch.float32).view(B, N, 3)
+        st.charges = seg(st.dev, 1).view(torch.int32).view(B, N)
+        st.bags = seg(st.dev, 2).view(torch.float32).view(B, Z)
+        st.act = seg(st.dev, 3).view(torch.float32).view(B, 6)
+        st.old = seg(st.dev, 4).view(torch.float32)
+        st.adv = seg(st.dev, 5).view(torch.float64)
+        st.ret = seg(st.dev, 6).view(torch.float64)
+        f32 = dict(dtype=torch.float32, device=dev)
+        st.out = torch.empty(6, B, **f32)   # logp, ent, v, g_logp, g_ent, g_v
+        st.info = torch.zeros(8, dtype=torch.float64, device=dev)
+        st.info_host = torch.zeros(8, dtype=torch.float64, pin_memory=True)
+        st.grad = torch.zeros_like(self._flat_grad)
+        st.ws = torch.empty(lib.mgb_cov_workspace_bytes(self._plan, B), dtype=torch.uint8, device=dev)
+        st.event = torch.cuda.Event()
+        st.B = B
+        st.generation = 0
+        o = _cabi.CovOutputs()
+        o.logp, o.ent, o.v = st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr()
+        st.outputs = o
+        plan, flat = self._plan, self._flat
+
+        def forward_and_loss(stream):
+            _cabi.check(lib, lib.mgb_cov_forward(plan, B, st.pos.data_ptr(), st.charges.data_ptr(), st.bags.data_ptr(), st.act.data_ptr(),
+                                                 flat.data_ptr(), st.ws.data_ptr(), st.ws.numel(), ctypes.byref(o), stream))
+            _cabi.check(lib, lib.mgb_ppo_loss(B, st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr(), st.old.data_ptr(),
+                                              st.adv.data_ptr(), st.ret.data_ptr(), clip_ratio, vf_coef, entropy_coef, 1.0 / B,
+                                              st.info.data_ptr(), st.out[3].data_ptr(), st.out[4].data_ptr(), st.out[5].data_ptr(), stream))
+
+        def backward(stream):
+            _cabi.check(lib, lib.mgb_cov_backward(plan, B, st.pos.data_ptr(), st.charges.data_ptr(), st.bags.data_ptr(), st.act.data_ptr(),
+                                                  flat.data_ptr(), st.ws.data_ptr(), st.ws.numel(), st.out[3].data_ptr(),
+                                                  st.out[4].data_ptr(), st.out[5].data_ptr(), st.grad.data_ptr(), 0, stream))
+
+        with torch.cuda.device(dev):
+            st.h_pos[...] = 0
+            st.h_charges[...] = 0
+            st.h_bags[...] = 0
+            st.h_act[...] = 0
+            st.h_old[...] = 0
+            st.h_adv[...] = 0
+            st.h_ret[...] = 0
+            st.dev.copy_(st.host)
+            st.g_forward = self._capture(forward_and_loss)
+            st.g_backward = self._capture(backward)
+        if len(self._fused_cache) >= 4:   # minibatch size + remainder size (+ a change of coefficients): keep the cache small
+            self._fused_cache.pop(next(iter(self._fused_cache)))
+        self._fused_cache[key] = st
+        return st
+
+    def fused_ppo_loss(self, observations: List, actions, old_logp, adv, ret, clip_ratio: float, vf_coef: float,
+                       entropy_coef: float):
+        """The arithmetic of ppo.compute_loss (ppo.py:18-63) on this agent, as one pinned staging copy and two CUDA-graph
+        replays: forward + PPO-clip loss (float64, k_ppo_loss), then the backward into a scratch gradient, enqueued right away
+        (ppo.train always differentiates the loss it just computed, ppo.py:126-131).  Returns (loss, info) like compute_loss;
+        loss.backward() scales the scratch gradient into the parameters' .grad."""
+        B = len(observations)
+        if not self._params_aliased():
+            self._realias()
+        st = self._fused_state(B, clip_ratio, vf_coef, entropy_coef)
+        st.generation += 1
+        actions_np = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
+        assert actions_np.shape == (B, 6)
+        pack_observations(observations, self.zs, self.canvas_size, cfg=self._cfg, out=(st.h_pos, st.h_charges, st.h_bags))
+        st.h_act[...] = actions_np
+        st.h_old[...] = old_logp
+        st.h_adv[...] = adv
+        st.h_ret[...] = ret
+        with torch.cuda.device(self.device):
+            st.dev.copy_(st.host, non_blocking=True)
+            st.g_forward.replay()
+            if self._is_sharded():
+                pass   # every rank's loss is the mean over ITS slice, like the unfused path (bench / ppo divide by the world size)
+            st.info_host.copy_(st.info, non_blocking=True)
+            st.event.record()
+            st.g_backward.replay()
+            if self._is_sharded():
+                torch.distributed.all_reduce(st.grad, op=torch.distributed.ReduceOp.SUM)   # the path's one exchange step
+            loss_dev = st.info[0].clone()
+            st.event.synchronize()
+        vals = st.info_host.numpy()
+        info = dict(policy_loss=float(vals[1]), entropy_loss=float(vals[2]), vf_loss=float(vals[3]), total_loss=float(vals[0]),
+                    approx_kl=float(vals[4]), clip_fraction=float(vals[5]))
+        loss = _FusedPPOLoss.apply(self._param_list[-1], self, st, loss_dev)
+        return loss, info
+
+    def _fused_backward(self, st: _FusedState, g: torch.Tensor):
+        keep = self._attach_grads()
+        scale = g.detach().to(torch.float32)
+        if keep:
+            self._flat_grad.add_(st.grad * scale)
+        else:
+            torch.mul(st.grad, scale, out=self._flat_grad)
 
     # ------------------------------------------------------------------------------------------------------
     # the reference surface

@@ -17,7 +17,16 @@ def _to_device(x, device):
 
 
 def compute_loss(ac, data: dict, clip_ratio: float, vf_coef: float, entropy_coef: float, device=None) -> Tuple[torch.Tensor, Dict[str, float]]:
-    """ppo.py:18-63, same operations in the same order (adv / ret arrive as float64 numpy -> float64 loss)."""
+    """ppo.py:18-63, same operations in the same order (adv / ret arrive as float64 numpy -> float64 loss).
+
+    Agents that offer `fused_ppo_loss` (CovariantAC) take the whole step — packing, one H2D copy, forward, the same loss
+    arithmetic in float64 on the device (k_ppo_loss, checked against this function by the tests) and the backward — as CUDA-graph
+    replays when the buffers have the dtypes ppo.train hands over (buffer.py:106-116); set `ac.fused_ppo = False` for the
+    op-by-op path below."""
+    if (getattr(ac, 'fused_ppo', False) and device is None and torch.is_grad_enabled() and isinstance(data['adv'], np.ndarray)
+            and data['adv'].dtype == np.float64 and isinstance(data['ret'], np.ndarray) and data['ret'].dtype == np.float64
+            and isinstance(data['logp'], np.ndarray) and data['logp'].dtype == np.float32 and len(data['obs']) > 0):
+        return ac.fused_ppo_loss(data['obs'], data['act'], data['logp'], data['adv'], data['ret'], clip_ratio, vf_coef, entropy_coef)
     pred = ac.step(data['obs'], data['act'])
     device = device if device is not None else pred['logp'].device
     old_logp = _to_device(data['logp'], device)

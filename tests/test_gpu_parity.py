@@ -110,6 +110,55 @@ def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
     assert_grads_close(grads_of(agent), ref_grads)
 
 
+def test_fused_ppo_step_matches_the_op_by_op_path():
+    """ppo.compute_loss through CovariantAC.fused_ppo_loss (pinned staging copy + CUDA-graph replays of forward + k_ppo_loss and
+    of the backward) against the same function with agent.fused_ppo = False (agent.step + torch ops + autograd): loss, info and
+    every gradient; graphs are replayed on new canvases, after a parameter update, and with gradient accumulation."""
+    from molgym_b200 import ppo
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    torch.manual_seed(3)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+
+    def batch(seed, n_canvases=24):
+        obs, n = synth.make_observations(cfg, batch=n_canvases, seed=seed)
+        act = synth.make_actions(cfg, obs, n, seed=seed)
+        with torch.no_grad():
+            logp0 = agent.step(obs, act)['logp'].cpu().numpy()
+        old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0, seed=seed)
+        return dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret)
+
+    def run(data_list, fused):
+        agent.fused_ppo = fused
+        agent.zero_grad()
+        out = []
+        for data in data_list:
+            loss, info = ppo.compute_loss(agent, data, 0.2, 0.5, 0.01)
+            (loss * 0.5).backward()
+            out.append((loss.item(), info))
+        return out, {k: v.copy() for k, v in grads_of(agent).items()}
+
+    for round_ in range(2):   # second round: same graphs replayed after the parameters moved
+        data = [batch(100 + round_), batch(200 + round_)]
+        ref_out, ref_grads = run(data, fused=False)
+        got_out, got_grads = run(data, fused=True)
+        for (l0, i0), (l1, i1) in zip(ref_out, got_out):
+            assert abs(l0 - l1) <= 1e-6 * max(1.0, abs(l0))
+            for key in i0:
+                assert abs(i0[key] - i1[key]) <= 1e-6 * max(1.0, abs(i0[key])), key
+        assert_grads_close(got_grads, ref_grads)
+        with torch.no_grad():
+            for p in agent.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+    # a loss that was superseded before being differentiated must not silently use the newer step's gradient
+    agent.fused_ppo = True
+    d = batch(300)
+    first, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
+    second, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
+    with pytest.raises(RuntimeError):
+        first.backward()
+    second.backward()
+
+
 def test_gradients_accumulate_over_minibatches_like_autograd():
     """ppo.train sums gradients over minibatches before one optimizer step (ppo.py:118-131)."""
     cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
