@@ -47,16 +47,29 @@ static int launch_mix_rows(const mgb_cov_plan* plan, int level, int B, const Cov
   }
 }
 
+template <int NLM2, int CT>
+static int launch_atom_cat_ct(const mgb_cov_plan* plan, int level, int B, const float* pos, const CovWs& w, int phases, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const size_t smem = sizeof(float) * atom_smem_floats(d.lv[level], d.N);
+  MGB_CUDA_OK(cudaFuncSetAttribute((k_atom_cat<NLM2, CT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGB_LAUNCH((k_atom_cat<NLM2, CT>), B * d.N, kAtomThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+             w.A[level], w.E[level], w.cat[level], phases);
+  MGB_LAUNCH_OK("k_atom_cat");
+  return MGB_OK;
+}
+template <int NLM2>
+static int launch_atom_cat(const mgb_cov_plan* plan, int level, int B, const float* pos, const CovWs& w, int phases, cudaStream_t st) {
+  // the default hidden width gets compile-time channel strides
+  return plan->desc.lv[level].C == 10 ? launch_atom_cat_ct<NLM2, 10>(plan, level, B, pos, w, phases, st)
+                                      : launch_atom_cat_ct<NLM2, 0>(plan, level, B, pos, w, phases, st);
+}
+
 template <int NLM2>
 static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
                            cudaStream_t st) {
   const CovDesc& d = plan->desc;
-  const LevelDesc& L = d.lv[level];
-  const size_t smem = sizeof(float) * atom_smem_floats(L, d.N);
-  MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MGB_LAUNCH(k_atom_cat<NLM2>, B * d.N, kAtomThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
-             w.A[level], w.E[level], w.cat[level], small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB);
-  MGB_LAUNCH_OK("k_atom_cat");
+  int rc = launch_atom_cat<NLM2>(plan, level, B, pos, w, small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB, st);
+  if (rc != MGB_OK) return rc;
   if (small_atoms(B, d.N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[level], 0));   // the square / pass-through blocks (side3)
   (void)P;
   return launch_mix_rows<false>(plan, level, B, w, nullptr, w.A[level + 1], st);
@@ -398,19 +411,10 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
     const LevelDesc& L = d.lv[k];
     if (small_atoms(B, N)) {
       // the CG-square and pass-through blocks of cat_k only need A_k: side3, beside the dot matrix and the edge kernel
-      const size_t asm_ = sizeof(float) * atom_smem_floats(L, N);
       MGB_CUDA_OK(cudaEventRecord(plan->ev_fork3[k], st));
       MGB_CUDA_OK(cudaStreamWaitEvent(plan->side3, plan->ev_fork3[k], 0));
-      if (k == 0) {
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_));
-        MGB_LAUNCH(k_atom_cat<1>, B * N, kAtomThreads, asm_, plan->side3, plan->d_desc, k, pos, w.n_atoms, w.atom_off, w.atom_list, B,
-                   w.A[k], w.E[k], w.cat[k], kAtomPhaseB);
-      } else {
-        MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_cat<kM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_));
-        MGB_LAUNCH(k_atom_cat<kM>, B * N, kAtomThreads, asm_, plan->side3, plan->d_desc, k, pos, w.n_atoms, w.atom_off, w.atom_list, B,
-                   w.A[k], w.E[k], w.cat[k], kAtomPhaseB);
-      }
-      MGB_LAUNCH_OK("k_atom_cat");
+      int rc3 = k == 0 ? launch_atom_cat<1>(plan, k, B, pos, w, kAtomPhaseB, plan->side3) : launch_atom_cat<kM>(plan, k, B, pos, w, kAtomPhaseB, plan->side3);
+      if (rc3 != MGB_OK) return rc3;
       MGB_CUDA_OK(cudaEventRecord(plan->ev_join3[k], plan->side3));
     }
     const size_t dsm = sizeof(float2) * (size_t)N * L.nlm_in * L.C;

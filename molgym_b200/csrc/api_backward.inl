@@ -1,30 +1,37 @@
 // api_backward.inl — backward launch sequence + PPO loss + host packer (part of api.cu).
 
-template <int NLM2>
-static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
-                           int accumulate_dE, cudaStream_t st) {
+template <int NLM2, int CT>
+static int launch_atom_bwd_ct(const mgb_cov_plan* plan, int level, int B, const float* pos, const CovWs& w, int accumulate_dE,
+                              cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
-  (void)P;
-  // dcat = W^H dA_{level+1}, row-parallel, into HBM; the atom kernel stages its atom's slice in shared memory
-  int rc = launch_mix_rows<true>(plan, level, B, w, w.dA[(level + 1) & 1], w.dcat, st);
-  if (rc != MGB_OK) return rc;
   const size_t smem = sizeof(float) * atom_bwd_smem_floats(L, d.N);
-  MGB_CUDA_OK(cudaFuncSetAttribute(k_atom_bwd<NLM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGB_CUDA_OK(cudaFuncSetAttribute((k_atom_bwd<NLM2, CT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (small_atoms(B, d.N)) {
     // column pass + own-atom terms on side3, beside the row pass -> edge backward -> dot backward chain of the main stream
     MGB_CUDA_OK(cudaEventRecord(plan->ev_fork3[level], st));
     MGB_CUDA_OK(cudaStreamWaitEvent(plan->side3, plan->ev_fork3[level], 0));
-    MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomBwdThreads, smem, plan->side3, plan->d_desc, level, pos, w.n_atoms, w.atom_off,
+    MGB_LAUNCH((k_atom_bwd<NLM2, CT>), B * d.N, kAtomBwdThreads, smem, plan->side3, plan->d_desc, level, pos, w.n_atoms, w.atom_off,
                w.atom_list, B, w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE, kAtomPhaseB);
     MGB_LAUNCH_OK("k_atom_bwd");
     MGB_CUDA_OK(cudaEventRecord(plan->ev_join3[level], plan->side3));
   }
-  MGB_LAUNCH(k_atom_bwd<NLM2>, B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+  MGB_LAUNCH((k_atom_bwd<NLM2, CT>), B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
              w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE,
              small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB);
   MGB_LAUNCH_OK("k_atom_bwd");
   return MGB_OK;
+}
+
+template <int NLM2>
+static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
+                           int accumulate_dE, cudaStream_t st) {
+  (void)P;
+  // dcat = W^H dA_{level+1}, row-parallel, into HBM; the atom kernel stages its atom's slice in shared memory
+  int rc = launch_mix_rows<true>(plan, level, B, w, w.dA[(level + 1) & 1], w.dcat, st);
+  if (rc != MGB_OK) return rc;
+  return plan->desc.lv[level].C == 10 ? launch_atom_bwd_ct<NLM2, 10>(plan, level, B, pos, w, accumulate_dE, st)
+                                      : launch_atom_bwd_ct<NLM2, 0>(plan, level, B, pos, w, accumulate_dE, st);
 }
 
 extern "C" {
@@ -175,9 +182,22 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   {
     // InputLinear weight gradient (needs the complete dA_0): the tail of the main stream
     if (small_atoms(B, N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[0], 0));
-    const int per_cta = (B + 147) / 148;
-    MGB_LAUNCH(k_input_dw, (B + per_cta - 1) / per_cta, 256, 0, st, plan->d_desc, B, per_cta, w.n_atoms, w.X, w.dA[0], grad);
-    MGB_LAUNCH_OK("k_input_dw");
+    if (small_atoms(B, N)) {
+      const int per_cta = (B + 147) / 148;
+      MGB_LAUNCH(k_input_dw, (B + per_cta - 1) / per_cta, 256, 0, st, plan->d_desc, B, per_cta, w.n_atoms, w.X, w.dA[0], grad);
+      MGB_LAUNCH_OK("k_input_dw");
+    } else {   // many rows: the tiled grouped weight-gradient kernel
+      DwProblemList list;
+      list.p[0] = DwProblem{w.X, w.dA[0], (long long)BN, d.S_in, 2 * d.C, kRowsValid, d.p_inW, d.p_inb};
+      list.n = 1;
+      int nw = 0;
+      for (int o0 = 0; o0 < list.p[0].No; o0 += kDwTileO) list.w[nw++] = DwWork{0, o0};
+      list.nw = nw;
+      const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + 63) / 64, 148));
+      dim3 grid(chunks, nw);
+      MGB_LAUNCH(k_dw_grouped, grid, kDwThreads, 0, st, list, w.n_atoms, N, grad);
+      MGB_LAUNCH_OK("k_dw_grouped");
+    }
   }
   MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[0], 0));    // join the side streams (their last work is mix_dw(0), edge_dw(0))
   MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join2[0], 0));

@@ -34,6 +34,26 @@ __device__ __forceinline__ void cfmacl(float2& acc, float2 a, float2 b) {  // ac
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
 }
 
+// ---- asynchronous 8-byte global -> shared copies (LDGSTS); the emulator build copies synchronously ----------------
+__device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* __restrict__ gmem_src) {
+#ifndef MGB_CUSIM
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+#else
+  *smem_dst = *gmem_src;
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef MGB_CUSIM
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef MGB_CUSIM
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // ---- spherical harmonics -------------------------------------------------------------------------------------
 // Complex Y_lm(v) for l <= 4, Condon-Shortley phase, m = -l..l stored at lm = l*l+l+m, evaluated as solid
 // harmonics (|v|^l Y_lm(v/|v|)) so that an un-normalised argument reproduces Cormorant's recursion

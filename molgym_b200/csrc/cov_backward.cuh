@@ -347,7 +347,11 @@ __host__ __device__ inline int policy_bwd_extra_floats(const CovDesc& d) {
 // dT[.][x] in registers -> dA_j.  The neighbours are staged twice so that only one 25-vector of dT lives in registers.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kAtomBwdThreads = 256;
-constexpr int kJChunkBwd = 4;
+constexpr int kEdgeCMax = 10;   // hidden channels <= 10 (checked at plan creation)
+constexpr int kJChunkBwd = 8;
+// The neighbour chunks are software-pipelined through registers: while a chunk is consumed out of shared memory the next one
+// is already in flight from L2 (kAtomPre float2 per thread cover a chunk of E_ij and A_j rows for C <= 10).
+constexpr int kAtomPre = (kJChunkBwd * (kNL + kM) * kEdgeCMax + kAtomBwdThreads - 1) / kAtomBwdThreads;
 
 __host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
@@ -355,7 +359,31 @@ __host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L, int N) {
   return L.totA * 2 + stage + nlm2 * L.C * 2 + N * kM * 2;
 }
 
+// register-staged copy of one neighbour chunk: E_ij rows [nj][5][C] and (NLM2 > 0) A_j rows [nj][NLM2][C] are contiguous in
+// HBM (neighbours j0 .. j0+nj-1 of atom i), so element e of the chunk is either E_i[j0*5C + e] or Ab[j0*NLM2*C + (e - nE)].
 template <int NLM2>
+__device__ __forceinline__ void chunk_fetch(const float2* __restrict__ Ab, const float2* __restrict__ E_i, int C, int j0, int nj,
+                                            float2* pre) {
+  const int nE = nj * kNL * C, nA = nj * NLM2 * C;
+  MGB_UNROLL
+  for (int q = 0; q < kAtomPre; ++q) {
+    const int e = threadIdx.x + q * kAtomBwdThreads;
+    if (e < nE) pre[q] = E_i[(long long)j0 * kNL * C + e];
+    else if (e < nE + nA) pre[q] = Ab[(long long)j0 * NLM2 * C + (e - nE)];
+  }
+}
+template <int NLM2>
+__device__ __forceinline__ void chunk_commit(int C, int nj, const float2* pre, float2* sE, float2* sAj) {
+  const int nE = nj * kNL * C, nA = nj * NLM2 * C;
+  MGB_UNROLL
+  for (int q = 0; q < kAtomPre; ++q) {
+    const int e = threadIdx.x + q * kAtomBwdThreads;
+    if (e < nE) sE[e] = pre[q];
+    else if (e < nE + nA) sAj[e - nE] = pre[q];
+  }
+}
+
+template <int NLM2, int CT>   // CT: compile-time channel count (0: read it from the level descriptor)
 __global__ void __launch_bounds__(kAtomBwdThreads, 2)
 k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ pos, const int* __restrict__ n_atoms,
            const int* __restrict__ atom_off, const int* __restrict__ atom_list, int B, const float* __restrict__ A_in,
@@ -363,7 +391,7 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
            int accumulate_dE, int phases) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
-  const int N = d.N, C = L.C;
+  const int N = d.N, C = CT ? CT : L.C;
   if ((int)blockIdx.x >= atom_off[B]) return;
   const int slot = atom_list[blockIdx.x];
   const int b = slot / N, i = slot - b * N;
@@ -408,11 +436,14 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       MGB_UNROLL
       for (int y = 0; y < NLM2; ++y) dTrow[y] = pair_scatter<kCgPad>(L.ag.pad_pair, x * NLM2 + y, sDcat, c);
     }
+    float2 pre[kAtomPre];
+    chunk_fetch<NLM2>(Ab, E_i, C, 0, min(kJChunkBwd, n), pre);
     for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
       const int nj = min(kJChunkBwd, n - j0);
       __syncthreads();
-      stage_neighbours<NLM2>(L, Ab, E_i, j0, nj, sE, sAj);
+      chunk_commit<NLM2>(C, nj, pre, sE, sAj);
       __syncthreads();
+      if (j0 + kJChunkBwd < n) chunk_fetch<NLM2>(Ab, E_i, C, j0 + kJChunkBwd, min(kJChunkBwd, n - j0 - kJChunkBwd), pre);
       if (owner) {
         for (int jj = 0; jj < nj; ++jj) {
           // contribution of m1 = x to dE_ij[l1, c]: conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
@@ -455,11 +486,14 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       }
       atomic_add2(dAb + (long long)i * NLM2 * C + x * C + c, dai);
     }
+    float2 pre[kAtomPre];
+    chunk_fetch<0>(Ab, E_i, C, 0, min(kJChunkBwd, n), pre);
     for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
       const int nj = min(kJChunkBwd, n - j0);
       __syncthreads();
-      stage_neighbours<0>(L, Ab, E_i, j0, nj, sE, sAj);
+      chunk_commit<0>(C, nj, pre, sE, sAj);
       __syncthreads();
+      if (j0 + kJChunkBwd < n) chunk_fetch<0>(Ab, E_i, C, j0 + kJChunkBwd, min(kJChunkBwd, n - j0 - kJChunkBwd), pre);
       if (owner)
         for (int jj = 0; jj < nj; ++jj) sU[(jj * kM + x) * C + c] = cmul(sE[(jj * kNL + l1) * C + c], sYall[(j0 + jj) * kM + x]);
       __syncthreads();

@@ -295,7 +295,7 @@ constexpr int kAtomPhaseB = 2;   // forward: CG square + pass-through (needs A_k
 
 __host__ __device__ inline int atom_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
-  const int stage = kJChunk * (kNL * L.C + nlm2 * L.C) * 2;
+  const int stage = 2 * kJChunk * (kNL * L.C + nlm2 * L.C) * 2;   // two staging buffers
   const int tsz = kM * nlm2 * L.C * 2;
   return (stage > tsz ? stage : tsz) + nlm2 * L.C * 2 + N * kM * 2;
 }
@@ -321,15 +321,24 @@ __device__ __forceinline__ void stage_neighbours(const LevelDesc& L, const float
   for (int idx = threadIdx.x; idx < nj * NLM2 * C; idx += blockDim.x) sAj[idx] = Ab[(long long)j0 * NLM2 * C + idx];
 }
 
-// cg_gather writes straight to the atom's cat vector in HBM (coalesced over the channel index).
+// asynchronous copy of one neighbour chunk into a staging buffer (E_ij rows [nj][5][C], A_j rows [nj][NLM2][C]; contiguous in HBM)
 template <int NLM2>
-__global__ void __launch_bounds__(kAtomThreads)
+__device__ __forceinline__ void chunk_copy_async(const float2* __restrict__ Ab, const float2* __restrict__ E_i, int C, int j0, int nj,
+                                                 float2* sE, float2* sAj) {
+  for (int idx = threadIdx.x; idx < nj * kNL * C; idx += blockDim.x) cp_async8(sE + idx, E_i + (long long)j0 * kNL * C + idx);
+  for (int idx = threadIdx.x; idx < nj * NLM2 * C; idx += blockDim.x) cp_async8(sAj + idx, Ab + (long long)j0 * NLM2 * C + idx);
+  cp_async_commit();
+}
+
+// cg_gather writes straight to the atom's cat vector in HBM (coalesced over the channel index).
+template <int NLM2, int CT>   // CT: compile-time channel count (0: read it from the level descriptor)
+__global__ void __launch_bounds__(kAtomThreads, 3)
 k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ pos, const int* __restrict__ n_atoms,
            const int* __restrict__ atom_off, const int* __restrict__ atom_list, int B, const float* __restrict__ A_in,
            const float* __restrict__ E, float* __restrict__ cat_out, int phases) {
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
-  const int N = d.N, C = L.C;
+  const int N = d.N, C = CT ? CT : L.C;
   if ((int)blockIdx.x >= atom_off[B]) return;
   const int slot = atom_list[blockIdx.x];
   const int b = slot / N, i = slot - b * N;
@@ -339,7 +348,7 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   float2* sT = smem;
   float2* sE = smem;
   float2* sAj = sE + kJChunk * kNL * C;
-  float2* sAi = smem + (stage > tsz ? stage : tsz);
+  float2* sAi = smem + (2 * stage > tsz ? 2 * stage : tsz);
   float2* sYall = sAi + NLM2 * C;
   const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
   const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
@@ -363,15 +372,22 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   float2 acc[NLM2];
   MGB_UNROLL
   for (int q = 0; q < NLM2; ++q) acc[q] = make_float2(0.f, 0.f);
-  for (int j0 = 0; j0 < n; j0 += kJChunk) {
+  // neighbour chunks double-buffered with asynchronous copies: the next chunk is in flight from L2 while this one is consumed
+  // (both buffers live in the space that T takes over after the loop)
+  chunk_copy_async<NLM2>(Ab, E_i, C, 0, min(kJChunk, n), sE, sAj);
+  int buf = 0;
+  for (int j0 = 0; j0 < n; j0 += kJChunk, buf ^= 1) {
     const int nj = min(kJChunk, n - j0);
-    __syncthreads();
-    stage_neighbours<NLM2>(L, Ab, E_i, j0, nj, sE, sAj);
-    __syncthreads();
+    cp_async_wait_all();
+    __syncthreads();   // this chunk is visible to everyone, and everyone is done with the other buffer
+    if (j0 + kJChunk < n)
+      chunk_copy_async<NLM2>(Ab, E_i, C, j0 + kJChunk, min(kJChunk, n - j0 - kJChunk), sE + (buf ^ 1) * stage, sAj + (buf ^ 1) * stage);
+    const float2* cE = sE + buf * stage;
+    const float2* cA = sAj + buf * stage;
     if (owner) {
       for (int jj = 0; jj < nj; ++jj) {
-        const float2 u = cmul(sE[(jj * kNL + l1) * C + c], sYall[(j0 + jj) * kM + lm1]);
-        const float2* a = sAj + jj * NLM2 * C + c;
+        const float2 u = cmul(cE[(jj * kNL + l1) * C + c], sYall[(j0 + jj) * kM + lm1]);
+        const float2* a = cA + jj * NLM2 * C + c;
         MGB_UNROLL
         for (int q = 0; q < NLM2; ++q) cfma(acc[q], u, a[q * C]);
       }
