@@ -111,7 +111,9 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[k], st));
       MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[k], 0));
       const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + kMixDwAtoms - 1) / kMixDwAtoms, 148 * 2));
-      dim3 grid(chunks, kNL);
+      int kmax = 0;
+      for (int l = 0; l < kNL; ++l) kmax = std::max(kmax, L.catA[l]);
+      dim3 grid(chunks, kNL, (kmax + kMixDwThreads - 1) / kMixDwThreads);
       const int co = std::min(pick_co_rows(L.Cout), 16 + 4 * (L.Cout == 20));   // more than 20 channels: passes of 16
       const size_t sm = sizeof(float2) * kMixDwAtoms * 9 * co;
 #define MGB_MIXDW_CASE(CO)                                                                                                        \

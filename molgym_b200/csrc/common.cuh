@@ -34,6 +34,13 @@ __device__ __forceinline__ void cfmacl(float2& acc, float2 a, float2 b) {  // ac
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
 }
 
+// ---- complex atomic add (one 8-byte RED on sm_90+; needs an 8-byte aligned destination) ------------------------------
+#ifdef MGB_CUSIM
+__device__ inline void atomic_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+#else
+__device__ __forceinline__ void atomic_add2(float2* p, float2 v) { atomicAdd(p, v); }  // red.global.add.v2.f32
+#endif
+
 // ---- asynchronous 8-byte global -> shared copies (LDGSTS); the emulator build copies synchronously ----------------
 __device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* __restrict__ gmem_src) {
 #ifndef MGB_CUSIM

@@ -8,11 +8,6 @@
 
 namespace mgb {
 
-#ifdef MGB_CUSIM
-__device__ inline void atomic_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
-#else
-__device__ __forceinline__ void atomic_add2(float2* p, float2 v) { atomicAdd(p, v); }  // red.global.add.v2.f32 (sm_90+)
-#endif
 __device__ __forceinline__ void smem_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
 
 // g = sum over the (zero-padded, fixed trip count) table entries of pair p: coef * dcat[dst + c]
@@ -520,9 +515,10 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
 // atoms staged in shared memory and read as broadcasts.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMixDwThreads = 128;
-constexpr int kMixDwSlots = 3;   // catA_l <= 3 * 128
 constexpr int kMixDwAtoms = 8;   // atoms per CTA pass (their dOut rows are staged together)
 
+// grid = (chunks of the compact valid-atom list, 5 ells, 128-wide slices of k); thread = one k, all output channels of that k in
+// registers, the 2l+1 rows of an atom loaded together (up to nine independent loads in flight per thread).
 template <int CO>
 __global__ void __launch_bounds__(kMixDwThreads)
 k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ atom_off, const int* __restrict__ atom_list,
@@ -531,17 +527,18 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int Cout = L.Cout, l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1;
+  const int k = blockIdx.z * kMixDwThreads + threadIdx.x;
+  if ((int)(blockIdx.z * kMixDwThreads) >= K) return;
   const int n_at = atom_off[B];
-  const int per = max((int)((n_at + gridDim.x - 1) / gridDim.x), 2 * kMixDwAtoms);   // every CTA flushes K * Cout atomics: not too few atoms
+  const int per = max((int)((n_at + gridDim.x - 1) / gridDim.x), 2 * kMixDwAtoms);   // every CTA flushes 128 * Cout atomics: not too few atoms
   const int a0 = per * blockIdx.x, a1 = min(n_at, a0 + per);
   if (a0 >= a1) return;
   MGB_DYN_SMEM(float2, sd);   // [kMixDwAtoms][nm][CO], zero beyond Cout
-  float2 acc[kMixDwSlots][CO];
+  float2 acc[CO];
   MGB_UNROLL
-  for (int s = 0; s < kMixDwSlots; ++s)
-    MGB_UNROLL
-    for (int c = 0; c < CO; ++c) acc[s][c] = make_float2(0.f, 0.f);
+  for (int c = 0; c < CO; ++c) acc[c] = make_float2(0.f, 0.f);
   const float2* dO = reinterpret_cast<const float2*>(dA_out);
+  const bool on = k < K;
   for (int ab = a0; ab < a1; ab += kMixDwAtoms) {
     const int cnt = min(kMixDwAtoms, a1 - ab);
     __syncthreads();
@@ -551,38 +548,25 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
     }
     __syncthreads();
     for (int a = 0; a < cnt; ++a) {
-      const float2* cr = reinterpret_cast<const float2*>(cat) + (long long)atom_list[ab + a] * L.totA + L.offA[l];
+      const float2* cr = reinterpret_cast<const float2*>(cat) + (long long)atom_list[ab + a] * L.totA + L.offA[l] + k;
       const float2* ga = sd + a * nm * CO;
-#pragma unroll 3
-      for (int m = 0; m < nm; ++m) {
-        float2 xv[kMixDwSlots];
-        MGB_UNROLL
-        for (int s = 0; s < kMixDwSlots; ++s) {
-          const int k = threadIdx.x + s * kMixDwThreads;
-          xv[s] = k < K ? cr[m * K + k] : make_float2(0.f, 0.f);
-        }
-        MGB_UNROLL
-        for (int c = 0; c < CO; ++c) {
-          const float2 g = ga[m * CO + c];
+      float2 xv[2 * kL + 1];
+      MGB_UNROLL
+      for (int m = 0; m < 2 * kL + 1; ++m) xv[m] = (on && m < nm) ? cr[m * K] : make_float2(0.f, 0.f);
+      MGB_UNROLL
+      for (int m = 0; m < 2 * kL + 1; ++m) {
+        if (m < nm) {
           MGB_UNROLL
-          for (int s = 0; s < kMixDwSlots; ++s)
-            if (s * kMixDwThreads < K) cfmacl(acc[s][c], xv[s], g);
+          for (int c = 0; c < CO; ++c) cfmacl(acc[c], xv[m], ga[m * CO + c]);
         }
       }
     }
   }
-  MGB_UNROLL
-  for (int s = 0; s < kMixDwSlots; ++s) {
-    const int k = threadIdx.x + s * kMixDwThreads;
-    if (k < K) {
-      MGB_UNROLL
-      for (int c = 0; c < CO; ++c) {
-        if (c_base + c < Cout) {
-          float* dst = grad + L.p_atomW + 2ll * (L.offWA[l] + (long long)(c_base + c) * K + k);
-          if (acc[s][c].x != 0.f) atomicAdd(dst, acc[s][c].x);
-          if (acc[s][c].y != 0.f) atomicAdd(dst + 1, acc[s][c].y);
-        }
-      }
+  if (on) {
+    MGB_UNROLL
+    for (int c = 0; c < CO; ++c) {
+      if (c_base + c < Cout && (acc[c].x != 0.f || acc[c].y != 0.f))
+        atomic_add2(reinterpret_cast<float2*>(grad + L.p_atomW) + L.offWA[l] + (long long)(c_base + c) * K + k, acc[c]);
     }
   }
 }

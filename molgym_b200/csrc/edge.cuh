@@ -597,11 +597,8 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
   if (edge_thread) {
     MGB_UNROLL
     for (int c = 0; c < kEdgeC; ++c) {
-      if (c < C) {
-        float* dst = grad + L.p_edgeW + 2ll * (L.offE[l] + c * K + tid);
-        if (acc[c].x != 0.f) atomicAdd(dst, acc[c].x);
-        if (acc[c].y != 0.f) atomicAdd(dst + 1, acc[c].y);
-      }
+      if (c < C && (acc[c].x != 0.f || acc[c].y != 0.f))
+        atomic_add2(reinterpret_cast<float2*>(grad + L.p_edgeW) + L.offE[l] + c * K + tid, acc[c]);
     }
   } else if (rad_thread) {
     const int t = tid - 96;
