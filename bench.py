@@ -157,28 +157,23 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # algorithmic work model (DESIGN.md "Work model")
 # ----------------------------------------------------------------------------------------------------------------
-def atom_bwd_bytes(cfg, n_atoms, nlm2=25):
-    """Algorithmic HBM bytes of ONE launch of the dominant kernel (k_atom_bwd) over a minibatch; nlm2 = number of (l, m)
-    components of the level's input representations (1 at level 0, else 25).  Per valid atom i: dA_out[25,Cout] read +
-    per neighbour j: A_j[nlm2,C] read, E_ij[5,C] read, dE_ij[5,C] write, dA_j[nlm2,C] read-modify-write."""
-    C = cfg.num_channels_hidden
-    tot = 0
-    for n in n_atoms:
-        n = int(n)
-        per_pair = nlm2 * C * 8 + 5 * C * 8 + 5 * C * 8 + 2 * nlm2 * C * 8
-        tot += n * (25 * C * 8 + n * per_pair)
-    return tot
-
-
-def atom_bwd_flops(cfg, n_atoms, nlm2=25):
-    """FLOPs of one k_atom_bwd launch: per pair 2 x 25*nlm2 complex MAC per channel (8 flop each) + per atom the
-    transposed mix (sum_l catA_l (2l+1) Cout complex MAC) + the Clebsch-Gordan scatter."""
-    C = cfg.num_channels_hidden
-    blocks = (11, 25, 33, 35, 31) if nlm2 == 25 else (3, 1, 1, 1, 1)
-    cat = [C * x for x in blocks]
-    mix = sum(c * (2 * l + 1) for l, c in enumerate(cat)) * C * 8
-    cg = 4 * (1439 if nlm2 == 25 else 26) * C * 4
-    return sum(int(n) * (int(n) * 2 * 25 * nlm2 * C * 8 + mix + cg) for n in n_atoms)
+def atom_bwd_work(cfg, n_atoms, cat_sizes):
+    """Algorithmic HBM bytes and FLOPs of ALL k_atom_bwd launches of one step (one per CG level; two half kernels per level
+    for small minibatches), from the kernel's own decomposition.  Per valid atom i of a canvas with n atoms,
+    level k with nlm2 input components (1 at level 0, else 25), C channels and a cat vector of totA_k complex entries:
+      bytes = totA_k*8 (dcat slice) + nlm2*C*8 (A_i) + n * [nlm2*C*8 (A_j) + 5*C*8 (E_ij) + 5*C*8 (dE_ij) + 2*nlm2*C*8 (dA_j RMW)]
+      flops = n * 2 * 25*nlm2 * C * 8 (row + column Kronecker passes, complex MAC = 8 flop)
+              + 3 * n_pairs(k) * 5 * C * 4 (padded Clebsch-Gordan scatter: row, column, square; real coefficient x complex)"""
+    C, nl = cfg.num_channels_hidden, cfg.maxl + 1
+    bytes_, flops = 0, 0
+    for k in range(cfg.num_cg_levels):
+        nlm2 = 1 if k == 0 else 25
+        tot_a = sum(cat_sizes[(k * nl + l) * 2 + 1] * (2 * l + 1) for l in range(nl))
+        for n in n_atoms:
+            n = int(n)
+            bytes_ += n * (tot_a * 8 + nlm2 * C * 8 + n * (nlm2 * C * 8 + 5 * C * 8 + 5 * C * 8 + 2 * nlm2 * C * 8))
+            flops += n * (n * 2 * 25 * nlm2 * C * 8 + 3 * 25 * nlm2 * 5 * C * 4)
+    return bytes_, flops
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -356,10 +351,10 @@ def run_ours(args):
     n_timed = max(int(cnt.value), 1)
     k_ms = tot.value / n_timed
     launches_per_step_of_kernel = n_timed / args.steps
-    # per-launch algorithmic work averaged over the launches of one step (level 0 has a single input component)
-    lv = cfg.num_cg_levels
-    alg_bytes = (atom_bwd_bytes(cfg, n_atoms, 25) * (lv - 1) + atom_bwd_bytes(cfg, n_atoms, 1)) / lv
-    alg_flops = (atom_bwd_flops(cfg, n_atoms, 25) * (lv - 1) + atom_bwd_flops(cfg, n_atoms, 1)) / lv
+    # per-launch algorithmic work: the step's total over the kernel's launches in one step (levels x half kernels)
+    step_bytes, step_flops = atom_bwd_work(cfg, n_atoms, agent._cat_sizes)
+    alg_bytes = step_bytes / max(launches_per_step_of_kernel, 1.0)
+    alg_flops = step_flops / max(launches_per_step_of_kernel, 1.0)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     try:
@@ -381,7 +376,10 @@ def run_ours(args):
                      'timed_in': 'eager pass of the timed region (CUDA events around every launch of the kernel)',
                      'algorithmic_bytes_per_launch': alg_bytes, 'algorithmic_flops_per_launch': alg_flops,
                      'fp32_achieved_tflops': alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
-                     'note': 'kernel is FP32-FMA/latency bound at this size (arithmetic intensity >> ridge); see DESIGN.md'},
+                     'fp32_peak_tflops': 72.3, 'fp32_frac': (alg_flops / (k_ms * 1e-3) / 1e12 / 72.3) if k_ms > 0 else None,
+                     'note': 'the CG kernels are FP32-FMA bound (arithmetic intensity >> ridge 11 flop/B): the binding roof is the '
+                             'measured FFMA peak (profiles/r1_ffma_peak.txt), reported beside the HBM figure BASELINE.json asks for; '
+                             'see DESIGN.md section 3'},
         'wall_ms_per_step': wall / args.steps * 1e3, 'launch_mode': mode, 'eager_ms_per_step': eager_ms / args.steps,
         'graph_ms_per_step': graph_ms / args.steps if graph_ms is not None else None,
     }

@@ -232,15 +232,23 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     // transposed copies: edge weights [l][k][c'][2] then radial weights [l][t][2C]
     d.wt_edge[k] = wt;
     for (int l = 0; l < kNL; ++l)
-      plan->segs.push_back(TransposeSeg{L.p_edgeW + 2ll * L.offE[l], wt + 2ll * L.offE[l], C, L.catE[l], 2});
+      plan->segs.push_back(TransposeSeg{L.p_edgeW + 2ll * L.offE[l], wt + 2ll * L.offE[l], C, L.catE[l], 2, C});
     wt += 2ll * L.totE;
     for (int l = 0; l < kNL; ++l)
-      plan->segs.push_back(TransposeSeg{L.p_radW + (long long)l * C2 * kRadFeat, wt + (long long)l * C2 * kRadFeat, C2, kRadFeat, 1});
+      plan->segs.push_back(TransposeSeg{L.p_radW + (long long)l * C2 * kRadFeat, wt + (long long)l * C2 * kRadFeat, C2, kRadFeat, 1, C2});
     wt += (long long)kNL * C2 * kRadFeat;
-    d.wt_atom[k] = wt;   // atom-mix weights transposed to [l][k][c'][2]
-    for (int l = 0; l < kNL; ++l)
-      plan->segs.push_back(TransposeSeg{L.p_atomW + 2ll * L.offWA[l], wt + 2ll * L.offWA[l], L.Cout, L.catA[l], 2});
-    wt += 2ll * L.totWA;
+    wt = (wt + 3) & ~3ll;   // 16-byte aligned: the row-mix kernels bulk-copy these matrices into shared memory
+    d.wt_atom[k] = wt;      // atom-mix weights transposed and zero-padded to [l][k][mixCS][2]
+    L.mixCS = mix_stride_of(pick_co_rows(L.Cout));
+    {
+      int wo_t = 0;
+      for (int l = 0; l < kNL; ++l) {
+        L.offWAt[l] = wo_t;
+        plan->segs.push_back(TransposeSeg{L.p_atomW + 2ll * L.offWA[l], wt + 2ll * wo_t, L.Cout, L.catA[l], 2, L.mixCS});
+        wo_t += L.mixCS * L.catA[l];
+      }
+      wt += 2ll * wo_t;
+    }
     {
       const int zero[kNL] = {0, 0, 0, 0, 0};
       resolve_cg_table(ag, L.catA, L.offA, zero, C, false);
@@ -275,8 +283,8 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     plan->p_offsets.push_back(m.b0); plan->p_numels.push_back(hidden);
     plan->p_offsets.push_back(m.W1); plan->p_numels.push_back((long long)outn * hidden);
     plan->p_offsets.push_back(m.b1); plan->p_numels.push_back(outn);
-    plan->segs.push_back(TransposeSeg{m.W0, m.W0t, hidden, in, 1});
-    plan->segs.push_back(TransposeSeg{m.W1, m.W1t, outn, hidden, 1});
+    plan->segs.push_back(TransposeSeg{m.W0, m.W0t, hidden, in, 1, hidden});
+    plan->segs.push_back(TransposeSeg{m.W1, m.W1t, outn, hidden, 1, outn});
   };
   mlp(d.focus, d.lat, d.Wd, 1);
   mlp(d.element, d.lat, d.Wd, d.Z);

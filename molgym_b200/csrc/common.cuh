@@ -249,6 +249,8 @@ struct LevelDesc {
   int totA;          // per-atom CAT size (complex)
   int offWA[kNL];    // complex offset of l block inside the packed atom weights (sum Cout*catA)
   int totWA;
+  int mixCS;         // row stride (complex) of the transposed, padded copy of the atom weights in the scratch: [l][k][mixCS]
+  int offWAt[kNL];   // complex offset of l block inside that copy (sum mixCS*catA)
   int in_block[kNL]; // block index of the pass-through input rep inside cat_l (-1 if absent)
   int sq_block[kNL]; // first block index of the CG-square paths inside cat_l
   long long p_scales, p_phases, p_radW, p_radb, p_edgeW, p_atomW;  // float offsets into the flat parameter buffer

@@ -403,18 +403,15 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   float2* dE_i = reinterpret_cast<float2*>(dE) + ((long long)b * N + i) * N * kNL * C;
   float2* dAb = reinterpret_cast<float2*>(dA_in) + (long long)b * N * NLM2 * C;
   const float* pos_b = pos + (long long)b * N * 3;
+  // the atom's dcat slice (62 KB at the default width) arrives as ONE bulk copy (TMA, cp.async.bulk + mbarrier) issued by one
+  // thread while the others stage A_i and evaluate the neighbour harmonics
+  __shared__ SmemBarrier s_bar;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  const bool bulk = smem_fill_begin(reinterpret_cast<float*>(sDcat), dcat + 2ll * slot * L.totA, 2 * L.totA, &s_bar);
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
   neighbour_harmonics(pos_b, i, n, sYall);
-  {
-    const float2* src2 = reinterpret_cast<const float2*>(dcat) + (long long)slot * L.totA;
-    if ((L.totA & 1) == 0) {   // 16-byte aligned slices
-      const float4* src = reinterpret_cast<const float4*>(src2);
-      float4* dst = reinterpret_cast<float4*>(sDcat);
-      for (int idx = threadIdx.x; idx < L.totA / 2; idx += blockDim.x) dst[idx] = src[idx];
-    } else {
-      for (int idx = threadIdx.x; idx < L.totA; idx += blockDim.x) sDcat[idx] = src2[idx];
-    }
-  }
+  smem_fill_end(bulk, &s_bar, 0);
   __syncthreads();
 
   const bool owner = (int)threadIdx.x < kM * C;

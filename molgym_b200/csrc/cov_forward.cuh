@@ -17,6 +17,7 @@ namespace mgb {
 struct TransposeSeg {
   long long src, dst;  // float offsets (params / scratch)
   int rows, cols, elem;
+  int pad_rows;        // dst row count (>= rows; the extra rows are written as zeros)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -46,8 +47,9 @@ __global__ void k_prep_params(const TransposeSeg* __restrict__ segs, int n_seg, 
     }
     const TransposeSeg s = segs[lo];
     const int local = (int)(idx - s.dst), e = local % s.elem, t = local / s.elem;
-    const int c = t / s.rows, r = t - c * s.rows;
-    Wt[idx] = P[s.src + ((long long)r * s.cols + c) * s.elem + e];
+    const int c = t / s.pad_rows, r = t - c * s.pad_rows;
+    if (c >= s.cols) continue;   // alignment gap between two segments
+    Wt[idx] = r < s.rows ? P[s.src + ((long long)r * s.cols + c) * s.elem + e] : 0.f;
   }
 }
 
@@ -417,6 +419,7 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMixThreads = 128;
 template <int CO> constexpr int kMixStride = (CO % 4 == 2) ? CO : ((CO % 2 == 0) ? CO + 2 : CO);
+inline int mix_stride_of(int co) { return (co % 4 == 2) ? co : ((co % 2 == 0) ? co + 2 : co); }
 
 template <int CO, bool BACKWARD, int KS>
 __global__ void __launch_bounds__(kMixThreads)
@@ -437,11 +440,23 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   constexpr int CS = kMixStride<CO>;
   MGB_DYN_SMEM(float2, sW);   // [K][CS]
   {
-    const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_atom[level]) + L.offWA[l];   // [k][c'] (transposed by k_prep_params)
-    for (int idx = threadIdx.x; idx < K * CO; idx += blockDim.x) {
-      const int k = idx / CO, c = idx - k * CO;
-      sW[k * CS + c] = c < Cout ? src[k * Cout + c] : make_float2(0.f, 0.f);
+    // k_prep_params left W_l transposed and padded to the stride CS in the scratch: one bulk copy (TMA) brings the whole
+    // matrix in while the threads set up their rows
+    __shared__ SmemBarrier s_bar;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    const float* src = Wt + d.wt_atom[level] + 2ll * L.offWAt[l];
+    bool bulk = false;
+    if (L.mixCS == CS) {
+      bulk = smem_fill_begin(reinterpret_cast<float*>(sW), src, 2 * K * CS, &s_bar);
+    } else {   // stride mismatch (should not happen: the plan pads for the instantiation it launches)
+      const float2* src2 = reinterpret_cast<const float2*>(src);
+      for (int idx = threadIdx.x; idx < K * CO; idx += blockDim.x) {
+        const int k = idx / CO, c = idx - k * CO;
+        sW[k * CS + c] = c < L.mixCS ? src2[k * L.mixCS + c] : make_float2(0.f, 0.f);
+      }
     }
+    smem_fill_end(bulk, &s_bar, 0);
   }
   __syncthreads();
   const int ks = threadIdx.x % KS;
@@ -458,6 +473,16 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     MGB_UNROLL
     for (int c = 0; c < CO; ++c) acc[c] = make_float2(0.f, 0.f);
     int k = ks;
+    // eight independent row loads in flight per thread (the rows come from L2 / HBM; the weights are broadcasts from shared memory)
+    for (; k + 7 * KS < K; k += 8 * KS) {
+      float2 x[8];
+      MGB_UNROLL
+      for (int q = 0; q < 8; ++q) x[q] = crow[k + q * KS];
+      MGB_UNROLL
+      for (int q = 0; q < 8; ++q)
+        MGB_UNROLL
+        for (int c = 0; c < CO; ++c) cfma(acc[c], sW[(k + q * KS) * CS + c], x[q]);
+    }
     for (; k + 3 * KS < K; k += 4 * KS) {
       float2 x[4];
       MGB_UNROLL
