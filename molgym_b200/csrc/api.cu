@@ -430,7 +430,7 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
     dim3 egrid(pair_blocks, kNL);
     const bool small = edge_small(B, N);   // few pairs: five threads per (pair, ell)
     dim3 sgrid((unsigned)(((long long)B * N * N + kPairCsPairs - 1) / kPairCsPairs), kNL);
-    const size_t ssm = esm + sizeof(float2) * kPairCsPairs * kEdgeC;
+    const size_t ssm = esm + sizeof(float2) * kPairCsPairs * kEdgeKMaxFwd;
     if (k == 0) {
       MGB_CUDA_OK(cudaFuncSetAttribute(k_dot_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       MGB_LAUNCH(k_dot_fwd<1>, B, 256, dsm, st, plan->d_desc, k, w.n_atoms, w.A[k], w.D[k]);

@@ -7,8 +7,13 @@ static int launch_atom_bwd_ct(const mgb_cov_plan* plan, int level, int B, const 
   const LevelDesc& L = d.lv[level];
   const size_t smem = sizeof(float) * atom_bwd_smem_floats(L, d.N);
   MGB_CUDA_OK(cudaFuncSetAttribute((k_atom_bwd<NLM2, CT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGB_LAUNCH((k_atom_bwd<NLM2, CT>), B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
+             w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE,
+             small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB);
+  MGB_LAUNCH_OK("k_atom_bwd");
   if (small_atoms(B, d.N)) {
-    // column pass + own-atom terms on side3, beside the row pass -> edge backward -> dot backward chain of the main stream
+    // column pass + own-atom terms on side3, BEHIND the row pass (the two would only compete for the same SMs) and beside the
+    // edge backward -> dot backward part of the main stream
     MGB_CUDA_OK(cudaEventRecord(plan->ev_fork3[level], st));
     MGB_CUDA_OK(cudaStreamWaitEvent(plan->side3, plan->ev_fork3[level], 0));
     MGB_LAUNCH((k_atom_bwd<NLM2, CT>), B * d.N, kAtomBwdThreads, smem, plan->side3, plan->d_desc, level, pos, w.n_atoms, w.atom_off,
@@ -16,10 +21,6 @@ static int launch_atom_bwd_ct(const mgb_cov_plan* plan, int level, int B, const 
     MGB_LAUNCH_OK("k_atom_bwd");
     MGB_CUDA_OK(cudaEventRecord(plan->ev_join3[level], plan->side3));
   }
-  MGB_LAUNCH((k_atom_bwd<NLM2, CT>), B * d.N, kAtomBwdThreads, smem, st, plan->d_desc, level, pos, w.n_atoms, w.atom_off, w.atom_list, B,
-             w.A[level], w.E[level], w.dcat, w.dA[level & 1], w.dE[level & 1], accumulate_dE,
-             small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB);
-  MGB_LAUNCH_OK("k_atom_bwd");
   return MGB_OK;
 }
 

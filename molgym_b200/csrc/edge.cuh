@@ -311,6 +311,7 @@ constexpr int kEdgeCs = 5;                        // threads per (pair, ell)
 constexpr int kEdgeCg = kEdgeC / kEdgeCs;         // channels per thread
 constexpr int kPairCsPairs = 32;                  // pairs per CTA
 constexpr int kPairCsThreads = kPairCsPairs * kEdgeCs;
+constexpr int kEdgeKMaxFwd = 7 * kEdgeC;           // [E_prev (C) | dot (5 C) | radial (C)]
 
 template <int NLIN>
 __global__ void __launch_bounds__(kPairCsThreads)
@@ -325,8 +326,8 @@ k_edge_pairs_fwd_cs(const CovDesc* __restrict__ dp, int level, int B, const floa
   if ((int)(blockIdx.x * kPairCsPairs) >= total) return;
   MGB_DYN_SMEM(float2, smem);
   float2* sW = smem;                                          // [K][kEdgeC]   WE_l transposed ([k][c'])
-  float2* sR = sW + K * kEdgeC;                               // [pairs][kEdgeC] radial filter values of this ell
-  float* sRad = reinterpret_cast<float*>(sR + kPairCsPairs * kEdgeC);   // [2C][32] radial linear of this ell + [2C] bias
+  float2* sX = sW + kEdgeKMaxFwd * kEdgeC;                    // [pairs][K]    the pair's cat vector [E_prev | dot | radial]
+  float* sRad = reinterpret_cast<float*>(sX + kPairCsPairs * kEdgeKMaxFwd);   // [2C][32] radial linear of this ell + [2C] bias
   {
     const float2* src = reinterpret_cast<const float2*>(Wt + d.wt_edge[level]) + L.offE[l];
     for (int idx = threadIdx.x; idx < K * kEdgeC; idx += blockDim.x) {
@@ -336,17 +337,33 @@ k_edge_pairs_fwd_cs(const CovDesc* __restrict__ dp, int level, int B, const floa
     for (int idx = threadIdx.x; idx < C2 * kRadFeat; idx += blockDim.x) sRad[idx] = P[L.p_radW + (long long)l * C2 * kRadFeat + idx];
     for (int idx = threadIdx.x; idx < C2; idx += blockDim.x) sRad[C2 * kRadFeat + idx] = P[L.p_radb + l * C2 + idx];
   }
-  __syncthreads();
   const int pl = threadIdx.x / kEdgeCs, g = threadIdx.x - pl * kEdgeCs;
   const int p = blockIdx.x * kPairCsPairs + pl;
   const bool valid = p < total;
+  const int kprev = L.has_prev ? C : 0, kdot = (l < NLIN) ? NLIN * C : 0;
   PairGeom geo;
   long long pair = 0;
+  float2* xrow = sX + pl * kEdgeKMaxFwd;
+  constexpr int kXPer = (kEdgeKMaxFwd - kEdgeC + kEdgeCs - 1) / kEdgeCs;   // previous-edge + dot entries fetched per thread
+  float2 xin[kXPer];
   if (valid) {
     const PairId id = decode_pair(p, B, pair_off, n_atoms);
-    geo = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
     pair = ((long long)id.b * N + id.i) * N + id.j;
+    // the pair's previous edge scalars and dot matrix: the five threads of the pair fetch interleaved entries, all loads in
+    // flight before the radial arithmetic below
+    const float2* xe = reinterpret_cast<const float2*>(E_prev) + pair * kNL * C + l * C;
+    const float2* xd = reinterpret_cast<const float2*>(D) + pair * kNL * C;
+    MGB_UNROLL
+    for (int q = 0; q < kXPer; ++q) {
+      const int k = g + q * kEdgeCs;
+      if (k < kprev) xin[q] = xe[k];
+      else if (k < kprev + kdot) xin[q] = xd[k - kprev];
+    }
+    geo = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
     if (pair_slot && l == 0 && g == 0) pair_slot[p] = (int)pair;
+  }
+  __syncthreads();   // weights staged
+  if (valid) {
     float f[kRadFeat];
     rad_features_all(geo, P + L.p_scales, P + L.p_phases, f, nullptr);
     MGB_UNROLL
@@ -358,8 +375,13 @@ k_edge_pairs_fwd_cs(const CovDesc* __restrict__ dp, int level, int B, const floa
         const float* wr = sRad + (2 * k) * kRadFeat;
         MGB_UNROLL
         for (int t = 0; t < kRadFeat; ++t) { re = fmaf(wr[t], f[t], re); im = fmaf(wr[kRadFeat + t], f[t], im); }
+        xrow[kprev + kdot + k] = make_float2(re, im);
       }
-      sR[pl * kEdgeC + k] = make_float2(re, im);
+    }
+    MGB_UNROLL
+    for (int q = 0; q < kXPer; ++q) {
+      const int k = g + q * kEdgeCs;
+      if (k < kprev + kdot) xrow[k] = xin[q];
     }
   }
   __syncthreads();
@@ -368,30 +390,11 @@ k_edge_pairs_fwd_cs(const CovDesc* __restrict__ dp, int level, int B, const floa
   MGB_UNROLL
   for (int q = 0; q < kEdgeCg; ++q) acc[q] = make_float2(0.f, 0.f);
   const float2* w = sW + g * kEdgeCg;
-  int kk = 0;
-  if (L.has_prev) {
-    const float2* x = reinterpret_cast<const float2*>(E_prev) + pair * kNL * C + l * C;
-    for (int k = 0; k < C; ++k) {
-      const float2 xv = x[k];
-      MGB_UNROLL
-      for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[(kk + k) * kEdgeC + q], xv);
-    }
-    kk += C;
-  }
-  if (l < NLIN) {
-    const float2* x = reinterpret_cast<const float2*>(D) + pair * kNL * C;
 #pragma unroll 5
-    for (int k = 0; k < NLIN * C; ++k) {
-      const float2 xv = x[k];
-      MGB_UNROLL
-      for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[(kk + k) * kEdgeC + q], xv);
-    }
-    kk += NLIN * C;
-  }
-  for (int k = 0; k < C; ++k) {
-    const float2 xv = sR[pl * kEdgeC + k];
+  for (int k = 0; k < K; ++k) {
+    const float2 xv = xrow[k];
     MGB_UNROLL
-    for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[(kk + k) * kEdgeC + q], xv);
+    for (int q = 0; q < kEdgeCg; ++q) cfma(acc[q], w[k * kEdgeC + q], xv);
   }
   float2* Eo = reinterpret_cast<float2*>(E_out) + pair * kNL * C + l * C;
   MGB_UNROLL
