@@ -344,7 +344,7 @@ def run_ours(args):
     # host time shows up as the gap between start.record() and the first kernel: elapsed_time includes it.
     e2e_value = B * world / (e2e_ms / e2e_steps * 1e-3)
     h2d = pos.numel() * 4 + charges.numel() * 4 + bags.numel() * 4 + act_d.numel() * 4 + old_d.numel() * 4 + adv_d.numel() * 8 + ret_d.numel() * 8
-    d2h = 6 * 8
+    d2h = 8 * 8   # the loss-info block (8 doubles) read back every step
 
     if rank != 0:
         if world > 1:

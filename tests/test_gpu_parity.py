@@ -60,7 +60,7 @@ def test_golden_step_loss_and_gradients(name):
     assert_grads_close(grads_of(agent), golden_grads(g))
 
 
-@pytest.mark.parametrize('which,batch', [('C2', 140), ('C3', 96), ('C5', 24)])
+@pytest.mark.parametrize('which,batch', [('C2', 140), ('C3', 96), ('C4', 30), ('C5', 24)])
 def test_fresh_canvases_against_oracle(which, batch):
     from oracle.molgym_oracle import CovariantOracle, ppo_loss
     from molgym_b200 import ppo
