@@ -177,7 +177,11 @@ inline bool edge_bwd_split(int B, int N) {
 // small minibatches (the grid of one-atom CTAs is about one wave): the atom kernels are launched as two half kernels, the
 // half that is off the critical path on a side stream (forward: CG square + pass-through blocks of cat, which only need
 // A_k; backward: column pass + own-atom terms, which the edge backward does not wait for)
-inline bool small_atoms(int B, int N) { return (long long)B * N < 1536; }
+inline bool small_atoms(int B, int N) {
+  const char* e = std::getenv("MGB_SMALL_ATOMS");   // tests / tuning: override the slot threshold
+  const long long limit = e ? std::atoll(e) : 2560;   // measured: helps up to ~1.5 k atom slots (C2/140, C3/128), hurts at C4/512
+  return (long long)B * N < limit;
+}
 // a few thousand pairs only: five threads per (pair, ell) (k_edge_pairs_*_cs)
 inline bool edge_small(int B, int N) {
   const int m = edge_mode_override();
