@@ -267,8 +267,15 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(grad, op=dist.ReduceOp.SUM)
 
+    # ppo.train's inner loop (ppo.py:118-131): optimizer.zero_grad() once per epoch, then every minibatch of the epoch runs
+    # compute_loss + backward and the gradients accumulate; EPOCH_LEN minibatches per epoch here
+    EPOCH_LEN = 4
+    e2e_count = [0]
+
     def e2e_step():
-        agent.zero_grad()
+        if e2e_count[0] % EPOCH_LEN == 0:
+            agent.zero_grad()
+        e2e_count[0] += 1
         loss, info_d = ppo.compute_loss(agent, data, CLIP, VF, ENT)
         (loss / world).backward()
         return info_d
@@ -374,7 +381,11 @@ def run_ours(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config_json(cfg, world), 'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'canvases/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps},
+                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+                'note': 'ppo.train inner loop (ppo.py:118-131): zero_grad once per epoch of 4 minibatches, then compute_loss + '
+                        'loss.backward() per minibatch on host observation tuples; consecutive minibatches alternate between two '
+                        'pipeline slots, so the forward of step i+1 overlaps the backward of step i (the parameters are fixed within '
+                        'a PPO epoch); `value` is the strictly sequential device-resident step'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': args.profile_kernel, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': traffic,

@@ -117,6 +117,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         self.canvas_size = self.observation_space.canvas_space.size
         self.data_parallel = False   # set by molgym_b200.parallel.shard_agent
         self.fused_ppo = True        # molgym_b200.ppo.compute_loss may use fused_ppo_loss (CUDA-graph replay of the whole step)
+        self.fused_sync_params = False   # True: the fused step waits for the caller's stream every time (see fused_ppo_loss)
         self._init_native()
         self._init_parameters()
 
@@ -151,6 +152,10 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         self._cat_sizes = list(cats)
         self._ws_cache: Dict[int, torch.Tensor] = {}
         self._fused_cache: Dict[tuple, _FusedState] = {}
+        self._fused_streams = None
+        self._fused_turn = 0
+        self._fused_param_version = None
+        self._fused_acc_event = None
 
     def _param_shapes(self) -> Dict[str, tuple]:
         C, Z, cpe, W, G = self.num_channels_hidden, len(self.zs), self.num_channels_per_element, self.network_width, self.num_gaussians
@@ -233,7 +238,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ('_plan', '_cfg', '_ws_cache', '_fused_cache', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
+        for k in ('_plan', '_cfg', '_ws_cache', '_fused_cache', '_fused_streams', '_fused_acc_event', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
             state.pop(k, None)
         return state
 
@@ -326,8 +331,8 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         torch.cuda.current_stream(dev).wait_stream(side)
         return graph
 
-    def _fused_state(self, B: int, clip_ratio: float, vf_coef: float, entropy_coef: float) -> _FusedState:
-        key = (B, float(clip_ratio), float(vf_coef), float(entropy_coef), self._flat.data_ptr())
+    def _fused_state(self, B: int, clip_ratio: float, vf_coef: float, entropy_coef: float, slot: int) -> _FusedState:
+        key = (B, float(clip_ratio), float(vf_coef), float(entropy_coef), self._flat.data_ptr(), slot)
         st = self._fused_cache.get(key)
         if st is not None:
             return st
@@ -365,6 +370,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         st.event = torch.cuda.Event()
         st.B = B
         st.generation = 0
+        st.stream = self._fused_streams[slot]
         o = _cabi.CovOutputs()
         o.logp, o.ent, o.v = st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr()
         st.outputs = o
@@ -393,7 +399,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             st.dev.copy_(st.host)
             st.g_forward = self._capture(forward_and_loss)
             st.g_backward = self._capture(backward)
-        if len(self._fused_cache) >= 4:   # minibatch size + remainder size (+ a change of coefficients): keep the cache small
+        if len(self._fused_cache) >= 8:   # (minibatch size + remainder size) x two pipeline slots (+ a change of coefficients)
             self._fused_cache.pop(next(iter(self._fused_cache)))
         self._fused_cache[key] = st
         return st
@@ -403,11 +409,22 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         """The arithmetic of ppo.compute_loss (ppo.py:18-63) on this agent, as one pinned staging copy and two CUDA-graph
         replays: forward + PPO-clip loss (float64, k_ppo_loss), then the backward into a scratch gradient, enqueued right away
         (ppo.train always differentiates the loss it just computed, ppo.py:126-131).  Returns (loss, info) like compute_loss;
-        loss.backward() scales the scratch gradient into the parameters' .grad."""
+        loss.backward() scales the scratch gradient into the parameters' .grad.
+
+        Consecutive calls alternate between two pipeline slots (own stream, staging buffers, workspace, graphs): within a PPO
+        epoch the minibatches are independent — the parameters only move at optimizer.step() (ppo.py:122-146) — so the forward
+        of minibatch i+1 runs beside the backward of minibatch i.  The slot's stream waits for the caller's stream only when the
+        parameters changed since the last fused call (version counter of the flat buffer; `fused_sync_params = True` forces the
+        wait every time, for code that edits parameters through `.data`); the caller's stream waits for the accumulated
+        gradient in loss.backward()."""
         B = len(observations)
         if not self._params_aliased():
             self._realias()
-        st = self._fused_state(B, clip_ratio, vf_coef, entropy_coef)
+        if self._fused_streams is None:
+            self._fused_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+        slot = self._fused_turn
+        self._fused_turn ^= 1
+        st = self._fused_state(B, clip_ratio, vf_coef, entropy_coef, slot)
         st.generation += 1
         actions_np = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
         assert actions_np.shape == (B, 6)
@@ -417,17 +434,24 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         st.h_adv[...] = adv
         st.h_ret[...] = ret
         with torch.cuda.device(self.device):
-            st.dev.copy_(st.host, non_blocking=True)
-            st.g_forward.replay()
-            if self._is_sharded():
-                pass   # every rank's loss is the mean over ITS slice, like the unfused path (bench / ppo divide by the world size)
-            st.info_host.copy_(st.info, non_blocking=True)
-            st.event.record()
-            st.g_backward.replay()
-            if self._is_sharded():
-                torch.distributed.all_reduce(st.grad, op=torch.distributed.ReduceOp.SUM)   # the path's one exchange step
-            loss_dev = st.info[0].clone()
+            current = torch.cuda.current_stream(self.device)
+            version = (self._flat._version, self._flat.data_ptr())
+            if self.fused_sync_params or version != self._fused_param_version:
+                for stream in self._fused_streams:   # parameter updates enqueued on the caller's stream come first
+                    stream.wait_stream(current)
+                self._fused_param_version = version
+            with torch.cuda.stream(st.stream):
+                st.dev.copy_(st.host, non_blocking=True)
+                st.g_forward.replay()
+                st.info_host.copy_(st.info, non_blocking=True)
+                loss_dev = st.info[0].clone()
+                st.event.record(st.stream)
+                st.g_backward.replay()
+                if self._is_sharded():
+                    # the path's one exchange step; every rank's loss is the mean over ITS slice, like the op-by-op path
+                    torch.distributed.all_reduce(st.grad, op=torch.distributed.ReduceOp.SUM)
             st.event.synchronize()
+            current.wait_event(st.event)   # loss_dev is consumed on the caller's stream
         vals = st.info_host.numpy()
         info = dict(policy_loss=float(vals[1]), entropy_loss=float(vals[2]), vf_loss=float(vals[3]), total_loss=float(vals[0]),
                     approx_kl=float(vals[4]), clip_fraction=float(vals[5]))
@@ -435,12 +459,21 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         return loss, info
 
     def _fused_backward(self, st: _FusedState, g: torch.Tensor):
-        keep = self._attach_grads()
-        scale = g.detach().to(torch.float32)
-        if keep:
-            self._flat_grad.add_(st.grad * scale)
-        else:
-            torch.mul(st.grad, scale, out=self._flat_grad)
+        with torch.cuda.device(self.device):
+            current = torch.cuda.current_stream(self.device)
+            keep = self._attach_grads()                      # may zero the flat gradient on the caller's stream
+            scale = g.detach().to(torch.float32)
+            st.stream.wait_stream(current)                   # ... and the cotangent is produced there
+            if self._fused_acc_event is not None:
+                st.stream.wait_event(self._fused_acc_event)  # accumulations of the two slots into .grad stay ordered
+            with torch.cuda.stream(st.stream):
+                if keep:
+                    self._flat_grad.add_(st.grad * scale)
+                else:
+                    torch.mul(st.grad, scale, out=self._flat_grad)
+                self._fused_acc_event = torch.cuda.Event()
+                self._fused_acc_event.record(st.stream)
+            current.wait_event(self._fused_acc_event)        # whoever reads .grad next on the caller's stream sees it complete
 
     # ------------------------------------------------------------------------------------------------------
     # the reference surface

@@ -149,14 +149,40 @@ def test_fused_ppo_step_matches_the_op_by_op_path():
         with torch.no_grad():
             for p in agent.parameters():
                 p.add_(0.01 * torch.randn_like(p))
-    # a loss that was superseded before being differentiated must not silently use the newer step's gradient
+    # consecutive fused steps alternate between two pipeline slots: two losses may be alive at once, a third call reuses the
+    # first slot, and a loss superseded that way must raise instead of silently using the newer step's gradient
     agent.fused_ppo = True
+    agent.zero_grad()
     d = batch(300)
     first, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
     second, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
+    third, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
     with pytest.raises(RuntimeError):
         first.backward()
     second.backward()
+    third.backward()
+    twice = {k: v.copy() for k, v in grads_of(agent).items()}
+    agent.fused_ppo = False
+    agent.zero_grad()
+    for _ in range(2):
+        loss, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
+        loss.backward()
+    assert_grads_close(twice, grads_of(agent))
+    # parameters edited on the caller's stream are seen by the next fused step (version counter of the flat buffer)
+    agent.fused_ppo = True
+    with torch.no_grad():
+        for p in agent.parameters():
+            p.mul_(1.01)
+    agent.zero_grad()
+    loss_f, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
+    loss_f.backward()
+    got = {k: v.copy() for k, v in grads_of(agent).items()}
+    agent.fused_ppo = False
+    agent.zero_grad()
+    loss_u, _ = ppo.compute_loss(agent, d, 0.2, 0.5, 0.01)
+    loss_u.backward()
+    assert abs(loss_f.item() - loss_u.item()) <= 1e-6 * max(1.0, abs(loss_u.item()))
+    assert_grads_close(got, grads_of(agent))
 
 
 def test_gradients_accumulate_over_minibatches_like_autograd():
