@@ -242,7 +242,7 @@ def run_ours(args):
     if not os.environ.get('MOLGYM_B200_NO_GRAPH'):
         try:
             g = torch.cuda.CUDAGraph()
-            cap_stream = torch.cuda.Stream(dev)
+            cap_stream = torch.cuda.Stream(dev, priority=-5)   # main-chain kernels outrank the weight-gradient side streams
             cap_stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(cap_stream):
                 with torch.cuda.graph(g, stream=cap_stream):

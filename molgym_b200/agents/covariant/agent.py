@@ -323,7 +323,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         fn(torch.cuda.current_stream(dev).cuda_stream)   # eager warm-up: function attributes, lazy module loading
         torch.cuda.current_stream(dev).synchronize()
         graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(dev)
+        side = torch.cuda.Stream(dev, priority=-5)   # the critical chain outranks the plan's (default-priority) side streams
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             with torch.cuda.graph(graph, stream=side):

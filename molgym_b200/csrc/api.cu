@@ -330,7 +330,14 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   MGB_CUDA_OK(cudaMemcpy(plan->d_segs, plan->segs.data(), sizeof(TransposeSeg) * plan->segs.size(), cudaMemcpyHostToDevice));
   MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
   MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side2, cudaStreamNonBlocking));
-  MGB_CUDA_OK(cudaStreamCreateWithFlags(&plan->side3, cudaStreamNonBlocking));
+  {
+    // side3 carries the half of the atom kernels that the NEXT level waits for: above the weight-gradient streams, below a
+    // high-priority main stream (the Python layer captures its graphs on one)
+    int lo = 0, hi = 0;
+    MGB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo: least priority (numerically largest), hi: greatest
+    const int mid = hi < lo - 1 ? lo - (lo - hi) / 2 : lo;
+    MGB_CUDA_OK(cudaStreamCreateWithPriority(&plan->side3, cudaStreamNonBlocking, mid));
+  }
   for (int q = 0; q <= kMaxLevels; ++q) {
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_fork[q], cudaEventDisableTiming));
     MGB_CUDA_OK(cudaEventCreateWithFlags(&plan->ev_join[q], cudaEventDisableTiming));

@@ -60,6 +60,8 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 typedef void* cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return 0; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
