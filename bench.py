@@ -238,29 +238,42 @@ def run_ours(args):
 
     # The device-resident step works on fixed buffers, so its launches + memsets can be captured once into a CUDA graph and
     # replayed (the gradient all-reduce stays outside the graph).  MOLGYM_B200_NO_GRAPH=1 keeps only the eager launches.
-    graph = None
+    def capture(ws_, outs_, logp_, ent_, v_, g3_, info_, grad_):
+        g = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(dev, priority=-5)   # main-chain kernels outrank the weight-gradient side streams
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap_stream):
+            with torch.cuda.graph(g, stream=cap_stream):
+                s_ptr = torch.cuda.current_stream(dev).cuda_stream
+                _cabi.check(lib, lib.mgb_cov_forward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
+                                                     act_d.data_ptr(), agent._flat.data_ptr(), ws_.data_ptr(), ws_.numel(),
+                                                     ctypes.byref(outs_), s_ptr))
+                _cabi.check(lib, lib.mgb_ppo_loss(B, logp_.data_ptr(), ent_.data_ptr(), v_.data_ptr(), old_d.data_ptr(),
+                                                  adv_d.data_ptr(), ret_d.data_ptr(), CLIP, VF, ENT, inv_global, info_.data_ptr(),
+                                                  g3_[0].data_ptr(), g3_[1].data_ptr(), g3_[2].data_ptr(), s_ptr))
+                _cabi.check(lib, lib.mgb_cov_backward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
+                                                      act_d.data_ptr(), agent._flat.data_ptr(), ws_.data_ptr(), ws_.numel(),
+                                                      g3_[0].data_ptr(), g3_[1].data_ptr(), g3_[2].data_ptr(), grad_.data_ptr(), 0, s_ptr))
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        return g
+
+    graph, graph2, grad2, extra = None, None, None, []
     if not os.environ.get('MOLGYM_B200_NO_GRAPH'):
         try:
-            g = torch.cuda.CUDAGraph()
-            cap_stream = torch.cuda.Stream(dev, priority=-5)   # main-chain kernels outrank the weight-gradient side streams
-            cap_stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(cap_stream):
-                with torch.cuda.graph(g, stream=cap_stream):
-                    s_ptr = torch.cuda.current_stream(dev).cuda_stream
-                    _cabi.check(lib, lib.mgb_cov_forward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
-                                                         act_d.data_ptr(), agent._flat.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                         ctypes.byref(outs), s_ptr))
-                    _cabi.check(lib, lib.mgb_ppo_loss(B, logp.data_ptr(), ent.data_ptr(), v.data_ptr(), old_d.data_ptr(),
-                                                      adv_d.data_ptr(), ret_d.data_ptr(), CLIP, VF, ENT, inv_global, info.data_ptr(),
-                                                      g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), s_ptr))
-                    _cabi.check(lib, lib.mgb_cov_backward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
-                                                          act_d.data_ptr(), agent._flat.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                          g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), grad.data_ptr(), 0, s_ptr))
-            torch.cuda.current_stream(dev).wait_stream(cap_stream)
-            graph = g
+            graph = capture(ws, outs, logp, ent, v, (g_logp, g_ent, g_v), info, grad)
+            # more independent slots (own workspace / outputs / gradient) for the multi-slot throughput figure below
+            extra = []
+            for _ in range(int(os.environ.get('MOLGYM_B200_SLOTS', '2')) - 1):
+                ws2 = torch.empty_like(ws)
+                o2 = [torch.empty(B, **f32) for _ in range(6)]
+                outs2 = _cabi.CovOutputs()
+                outs2.logp, outs2.ent, outs2.v = o2[0].data_ptr(), o2[1].data_ptr(), o2[2].data_ptr()
+                info2, grad2 = torch.zeros_like(info), torch.zeros_like(grad)
+                graph2 = capture(ws2, outs2, o2[0], o2[1], o2[2], o2[3:], info2, grad2)
+                extra.append((graph2, grad2, (ws2, o2, outs2, info2)))
         except Exception as exc:   # pragma: no cover
             sys.stderr.write(f'CUDA graph capture failed ({exc}); eager launches only\n')
-            graph = None
+            graph = graph2 = None
 
     def graph_step():
         graph.replay()
@@ -344,6 +357,40 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
+    # ---- the same device-resident step with TWO independent slots replayed alternately on two streams (what the e2e path
+    # does with consecutive minibatches of an epoch): whole region timed, no L2 flush inside it (reported beside `value`)
+    two_slot_ms = None
+    if graph2 is not None:
+        slots = [(graph, grad, torch.cuda.Stream(dev))] + [(g_, gr_, torch.cuda.Stream(dev)) for g_, gr_, _ in extra]
+
+        def two_slot_region(n):
+            cur = torch.cuda.current_stream(dev)
+            for _, _, st_ in slots:
+                st_.wait_stream(cur)
+            for s_ in range(n):
+                g_, gr_, st_ = slots[s_ % len(slots)]
+                with torch.cuda.stream(st_):
+                    g_.replay()
+                    if world > 1:
+                        dist.all_reduce(gr_, op=dist.ReduceOp.SUM)
+            for _, _, st_ in slots:
+                cur.wait_stream(st_)
+
+        two_slot_region(max(4, args.warmup))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        two_slot_region(args.steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        two_slot_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([two_slot_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            two_slot_ms = float(t.item())
+
     # ---- e2e through the public API (host observations, packing, H2D, torch loss, D2H of the loss info)
     e2e_steps = max(10, args.steps // 4)
     e2e_ms, e2e_wall, _ = timed(e2e_step, e2e_steps, max(3, args.warmup // 4))
@@ -402,6 +449,10 @@ def run_ours(args):
                              'see DESIGN.md section 3'},
         'wall_ms_per_step': wall / args.steps * 1e3, 'launch_mode': mode, 'eager_ms_per_step': eager_ms / args.steps,
         'graph_ms_per_step': graph_ms / args.steps if graph_ms is not None else None,
+        'two_slot': None if two_slot_ms is None else {
+            'ms_per_step': two_slot_ms / args.steps, 'value': B * world / (two_slot_ms / args.steps * 1e-3), 'unit': 'canvases/s',
+            'note': 'device-resident steps of two independent slots replayed alternately on two streams (forward of one beside the '
+                    'backward of the other), whole region timed without L2 flushes; `value` above is the strictly sequential step'},
     }
     if not args.no_cpu_baseline and world == 1:
         cpu = run_cpu(cfg, steps=5, warmup=1, budget_s=20.0)
