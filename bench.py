@@ -1,6 +1,7 @@
 """bench.py — PPO-minibatch forward+backward throughput of the covariant agent (canvases / s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
+    (MOLGYM_B200_SLOTS=n: number of independent slots of the `two_slot` figure, default 2; MOLGYM_B200_NO_GRAPH=1: eager launches only)
 
 A "step" is one pass of the hot path over one minibatch of synthetic canvases: forward (Cormorant body + heads) ->
 PPO-clip loss -> backward -> (N > 1) gradient all-reduce.  Weak scaling: every rank processes its own minibatch of the
@@ -382,7 +383,9 @@ def run_ours(args):
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         two_slot_region(args.steps)
+        t_host = time.perf_counter() - t_host   # host time spent enqueuing (cudaGraphLaunch): the floor of any replay-based loop
         e1.record()
         torch.cuda.synchronize(dev)
         two_slot_ms = e0.elapsed_time(e1)
@@ -451,6 +454,7 @@ def run_ours(args):
         'graph_ms_per_step': graph_ms / args.steps if graph_ms is not None else None,
         'two_slot': None if two_slot_ms is None else {
             'ms_per_step': two_slot_ms / args.steps, 'value': B * world / (two_slot_ms / args.steps * 1e-3), 'unit': 'canvases/s',
+            'host_enqueue_ms_per_step': t_host / args.steps * 1e3,
             'note': 'device-resident steps of two independent slots replayed alternately on two streams (forward of one beside the '
                     'backward of the other), whole region timed without L2 flushes; `value` above is the strictly sequential step'},
     }
