@@ -34,6 +34,36 @@ __device__ __forceinline__ void cfmacl(float2& acc, float2 a, float2 b) {  // ac
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
 }
 
+// ---- packed FP32 pairs (Blackwell FFMA2: fma.rn.f32x2, two IEEE fp32 FMAs per instruction) -----------------------
+// A complex MAC acc += w * x costs four FFMAs; with two pair accumulators
+//     P += (w.re, w.im) * (x.re, x.re)      Q += (w.re, w.im) * (x.im, x.im)
+// it costs two FFMA2s and the product is recovered once at the end: w*x = (P.lo - Q.hi, P.hi + Q.lo),
+// conj(w)*x = (P.lo + Q.hi, Q.lo - P.hi).  The pair (w.re, w.im) is the complex number as it sits in memory.
+#ifndef MGB_CUSIM
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ void fma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 as_pair(float2 v) { return pack2(v.x, v.y); }
+#else
+struct f32x2 { float lo, hi; };
+__device__ inline f32x2 pack2(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ inline float2 unpack2(f32x2 v) { return make_float2(v.lo, v.hi); }
+__device__ inline void fma2(f32x2& acc, f32x2 a, f32x2 b) { acc.lo = fmaf(a.lo, b.lo, acc.lo); acc.hi = fmaf(a.hi, b.hi, acc.hi); }
+__device__ inline f32x2 as_pair(float2 v) { return f32x2{v.x, v.y}; }
+#endif
+// w * x  and  conj(w) * x  from the pair accumulators above
+__device__ __forceinline__ float2 cpair_mul(f32x2 P, f32x2 Q) { const float2 p = unpack2(P), q = unpack2(Q); return make_float2(p.x - q.y, p.y + q.x); }
+__device__ __forceinline__ float2 cpair_mulc(f32x2 P, f32x2 Q) { const float2 p = unpack2(P), q = unpack2(Q); return make_float2(p.x + q.y, q.x - p.y); }
+
 // ---- complex atomic add (one 8-byte RED on sm_90+; needs an 8-byte aligned destination) ------------------------------
 #ifdef MGB_CUSIM
 __device__ inline void atomic_add2(float2* p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }

@@ -531,9 +531,10 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   const int a0 = per * blockIdx.x, a1 = min(n_at, a0 + per);
   if (a0 >= a1) return;
   MGB_DYN_SMEM(float2, sd);   // [kMixDwAtoms][nm][CO], zero beyond Cout
-  float2 acc[CO];
+  // pair accumulators (FFMA2): P[c] += g[c] * (x.re, x.re), Q[c] += g[c] * (x.im, x.im);  conj(x) * g = (P.lo + Q.hi, P.hi - Q.lo)
+  f32x2 P[CO], Q[CO];
   MGB_UNROLL
-  for (int c = 0; c < CO; ++c) acc[c] = make_float2(0.f, 0.f);
+  for (int c = 0; c < CO; ++c) { P[c] = pack2(0.f, 0.f); Q[c] = pack2(0.f, 0.f); }
   const float2* dO = reinterpret_cast<const float2*>(dA_out);
   const bool on = k < K;
   for (int ab = a0; ab < a1; ab += kMixDwAtoms) {
@@ -553,8 +554,13 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
       MGB_UNROLL
       for (int m = 0; m < 2 * kL + 1; ++m) {
         if (m < nm) {
+          const f32x2 xr = pack2(xv[m].x, xv[m].x), xi = pack2(xv[m].y, xv[m].y);
           MGB_UNROLL
-          for (int c = 0; c < CO; ++c) cfmacl(acc[c], xv[m], ga[m * CO + c]);
+          for (int c = 0; c < CO; ++c) {
+            const f32x2 gp = as_pair(ga[m * CO + c]);
+            fma2(P[c], gp, xr);
+            fma2(Q[c], gp, xi);
+          }
         }
       }
     }
@@ -562,8 +568,10 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   if (on) {
     MGB_UNROLL
     for (int c = 0; c < CO; ++c) {
-      if (c_base + c < Cout && (acc[c].x != 0.f || acc[c].y != 0.f))
-        atomic_add2(reinterpret_cast<float2*>(grad + L.p_atomW) + L.offWA[l] + (long long)(c_base + c) * K + k, acc[c]);
+      const float2 p = unpack2(P[c]), q = unpack2(Q[c]);
+      const float2 acc = make_float2(p.x + q.y, p.y - q.x);
+      if (c_base + c < Cout && (acc.x != 0.f || acc.y != 0.f))
+        atomic_add2(reinterpret_cast<float2*>(grad + L.p_atomW) + L.offWA[l] + (long long)(c_base + c) * K + k, acc);
     }
   }
 }

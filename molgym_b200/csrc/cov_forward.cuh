@@ -469,9 +469,10 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const float2* crow = reinterpret_cast<const float2*>(cat) + slot * L.totA + L.offA[l] + m * K;
   const long long orow = (slot * kM + l * l + m) * Cout;
   if (!BACKWARD) {
-    float2 acc[CO];
+    // pair accumulators (FFMA2, see common.cuh): P[c] += W[k][c] * (x.re, x.re), Q[c] += W[k][c] * (x.im, x.im)
+    f32x2 P[CO], Q[CO];
     MGB_UNROLL
-    for (int c = 0; c < CO; ++c) acc[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < CO; ++c) { P[c] = pack2(0.f, 0.f); Q[c] = pack2(0.f, 0.f); }
     int k = ks;
     // eight independent row loads in flight per thread (the rows come from L2 / HBM; the weights are broadcasts from shared memory)
     for (; k + 7 * KS < K; k += 8 * KS) {
@@ -479,26 +480,30 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       MGB_UNROLL
       for (int q = 0; q < 8; ++q) x[q] = crow[k + q * KS];
       MGB_UNROLL
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < 8; ++q) {
+        const f32x2 xr = pack2(x[q].x, x[q].x), xi = pack2(x[q].y, x[q].y);
         MGB_UNROLL
-        for (int c = 0; c < CO; ++c) cfma(acc[c], sW[(k + q * KS) * CS + c], x[q]);
-    }
-    for (; k + 3 * KS < K; k += 4 * KS) {
-      float2 x[4];
-      MGB_UNROLL
-      for (int q = 0; q < 4; ++q) x[q] = crow[k + q * KS];
-      MGB_UNROLL
-      for (int q = 0; q < 4; ++q)
-        MGB_UNROLL
-        for (int c = 0; c < CO; ++c) cfma(acc[c], sW[(k + q * KS) * CS + c], x[q]);
+        for (int c = 0; c < CO; ++c) {
+          const f32x2 w = as_pair(sW[(k + q * KS) * CS + c]);
+          fma2(P[c], w, xr);
+          fma2(Q[c], w, xi);
+        }
+      }
     }
     for (; k < K; k += KS) {
       const float2 x = crow[k];
+      const f32x2 xr = pack2(x.x, x.x), xi = pack2(x.y, x.y);
       MGB_UNROLL
-      for (int c = 0; c < CO; ++c) cfma(acc[c], sW[k * CS + c], x);
+      for (int c = 0; c < CO; ++c) {
+        const f32x2 w = as_pair(sW[k * CS + c]);
+        fma2(P[c], w, xr);
+        fma2(Q[c], w, xi);
+      }
     }
+    float2 acc[CO];
     MGB_UNROLL
     for (int c = 0; c < CO; ++c) {
+      acc[c] = cpair_mul(P[c], Q[c]);
       MGB_UNROLL
       for (int o = KS / 2; o > 0; o >>= 1) {
         acc[c].x += __shfl_xor_sync(0xffffffffu, acc[c].x, o);
@@ -518,11 +523,20 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int c = 0; c < CO; ++c) g[c] = c < Cout ? gi[c] : make_float2(0.f, 0.f);
     float2* o = reinterpret_cast<float2*>(out) + slot * L.totA + L.offA[l] + m * K;
     if (valid) {
+      // conj(W[k][c]) * g[c] with pair accumulators: the broadcast pairs of g are formed once per row
+      f32x2 gr[CO], gq[CO];
+      MGB_UNROLL
+      for (int c = 0; c < CO; ++c) { gr[c] = pack2(g[c].x, g[c].x); gq[c] = pack2(g[c].y, g[c].y); }
+#pragma unroll 2
       for (int k = ks; k < K; k += KS) {
-        float2 acc = make_float2(0.f, 0.f);
+        f32x2 P = pack2(0.f, 0.f), Q = pack2(0.f, 0.f);
         MGB_UNROLL
-        for (int c = 0; c < CO; ++c) cfmacl(acc, sW[k * CS + c], g[c]);
-        o[k] = acc;
+        for (int c = 0; c < CO; ++c) {
+          const f32x2 w = as_pair(sW[k * CS + c]);
+          fma2(P, w, gr[c]);
+          fma2(Q, w, gq[c]);
+        }
+        o[k] = cpair_mulc(P, Q);
       }
     }
   }
