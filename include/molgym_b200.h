@@ -177,6 +177,12 @@ int mgb_int_backward(mgb_int_plan* plan, int32_t batch, const int32_t* d_numbers
  * mgb_profile_kernel(substr): from now on bracket every launch whose kernel name contains `substr` with CUDA events on
  *   the launching stream (NULL or "" switches it off).  mgb_profile_read: synchronise those events, return the summed
  *   duration in milliseconds and the number of launches timed, and reset. */
+/* dst = (accumulate ? dst : 0) + scale * src over n floats; `scale` points to ONE device scalar (float64 when scale_is_double,
+ * else float32).  Used by the fused PPO step to fold the ready scratch gradient into the parameters' .grad with the cotangent
+ * autograd hands over (replaces torch's cast + multiply + add; reference: the gradient accumulation of loss.backward(),
+ * molgym/ppo.py:131).  dst / src 16-byte aligned. */
+int mgb_scale_accumulate(float* dst, const float* src, const void* scale, int32_t scale_is_double, int64_t n, int32_t accumulate,
+                         void* stream);
 int64_t mgb_launch_count(void);
 int mgb_profile_kernel(const char* substr);
 int mgb_profile_read(double* total_ms, int64_t* launches);

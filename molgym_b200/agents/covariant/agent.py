@@ -368,6 +368,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         st.grad = torch.zeros_like(self._flat_grad)
         st.ws = torch.empty(lib.mgb_cov_workspace_bytes(self._plan, B), dtype=torch.uint8, device=dev)
         st.event = torch.cuda.Event()
+        st.acc_event = torch.cuda.Event()
         st.B = B
         st.generation = 0
         st.stream = self._fused_streams[slot]
@@ -459,21 +460,24 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         return loss, info
 
     def _fused_backward(self, st: _FusedState, g: torch.Tensor):
+        lib = _lib.load()
         with torch.cuda.device(self.device):
             current = torch.cuda.current_stream(self.device)
             keep = self._attach_grads()                      # may zero the flat gradient on the caller's stream
-            scale = g.detach().to(torch.float32)
+            scale = g.detach()
+            if scale.dtype not in (torch.float32, torch.float64) or not scale.is_cuda:
+                scale = scale.to(device=self.device, dtype=torch.float32)
             st.stream.wait_stream(current)                   # ... and the cotangent is produced there
             if self._fused_acc_event is not None:
                 st.stream.wait_event(self._fused_acc_event)  # accumulations of the two slots into .grad stay ordered
-            with torch.cuda.stream(st.stream):
-                if keep:
-                    self._flat_grad.add_(st.grad * scale)
-                else:
-                    torch.mul(st.grad, scale, out=self._flat_grad)
-                self._fused_acc_event = torch.cuda.Event()
-                self._fused_acc_event.record(st.stream)
-            current.wait_event(self._fused_acc_event)        # whoever reads .grad next on the caller's stream sees it complete
+            # .grad (+)= cotangent * scratch gradient: one kernel on the slot's stream, behind the backward graph
+            _cabi.check(lib, lib.mgb_scale_accumulate(self._flat_grad.data_ptr(), st.grad.data_ptr(), scale.data_ptr(),
+                                                      1 if scale.dtype == torch.float64 else 0, self._flat_grad.numel(),
+                                                      1 if keep else 0, st.stream.cuda_stream))
+            scale.record_stream(st.stream)
+            st.acc_event.record(st.stream)
+            self._fused_acc_event = st.acc_event
+            current.wait_event(st.acc_event)                 # whoever reads .grad next on the caller's stream sees it complete
 
     # ------------------------------------------------------------------------------------------------------
     # the reference surface

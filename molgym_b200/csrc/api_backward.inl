@@ -219,6 +219,17 @@ int mgb_ppo_loss(int32_t B, const float* logp, const float* ent, const float* v,
   return MGB_OK;
 }
 
+int mgb_scale_accumulate(float* dst, const float* src, const void* scale, int32_t scale_is_double, int64_t n, int32_t accumulate,
+                         void* stream) {
+  if (!dst || !src || !scale) return fail(MGB_ERR_INVALID, "null argument");
+  if (n <= 0) return MGB_OK;
+  if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) return fail(MGB_ERR_INVALID, "dst / src must be 16-byte aligned");
+  const int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 4);
+  MGB_LAUNCH(k_scale_accumulate, grid, 256, 0, (cudaStream_t)stream, dst, src, scale, scale_is_double, (long long)n, accumulate);
+  MGB_LAUNCH_OK("k_scale_accumulate");
+  return MGB_OK;
+}
+
 int64_t mgb_launch_count(void) { return g_prof.launches; }
 
 int mgb_profile_kernel(const char* substr) {

@@ -634,6 +634,27 @@ k_input_dw(const CovDesc* __restrict__ dp, int B, int per_cta, const int* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// dst = (accumulate ? dst : 0) + scale * src over the flat gradient; `scale` is a device scalar (float64 or float32): the
+// cotangent autograd hands to the fused PPO loss (agents/covariant/agent.py::_fused_backward) — one launch instead of a cast,
+// a multiply and an add.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_scale_accumulate(float* __restrict__ dst, const float* __restrict__ src, const void* __restrict__ scale,
+                                   int scale_is_double, long long n, int accumulate) {
+  const float sc = scale_is_double ? (float)*reinterpret_cast<const double*>(scale) : *reinterpret_cast<const float*>(scale);
+  const long long n4 = n >> 2;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = s4[i];
+    float4 y = accumulate ? d4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    y.x = fmaf(sc, x.x, y.x); y.y = fmaf(sc, x.y, y.y); y.z = fmaf(sc, x.z, y.z); y.w = fmaf(sc, x.w, y.w);
+    d4[i] = y;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = fmaf(sc, src[i], accumulate ? dst[i] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // PPO-clip loss (molgym/ppo.py:28-52) and its cotangents, float64 like the reference (adv / ret are float64).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_ppo_loss(int B, const float* __restrict__ logp, const float* __restrict__ ent, const float* __restrict__ v,
