@@ -264,7 +264,10 @@ def run_ours(args):
             graph = capture(ws, outs, logp, ent, v, (g_logp, g_ent, g_v), info, grad)
             # more independent slots (own workspace / outputs / gradient) for the multi-slot throughput figure below
             extra = []
-            for _ in range(int(os.environ.get('MOLGYM_B200_SLOTS', '2')) - 1):
+            n_extra = int(os.environ.get('MOLGYM_B200_SLOTS', '2')) - 1
+            if ws.numel() * (n_extra + 3) > 0.5 * torch.cuda.get_device_properties(dev).total_memory:
+                n_extra = 0   # the agent's own fused slots need their workspaces too
+            for _ in range(n_extra):
                 ws2 = torch.empty_like(ws)
                 o2 = [torch.empty(B, **f32) for _ in range(6)]
                 outs2 = _cabi.CovOutputs()
@@ -361,7 +364,7 @@ def run_ours(args):
     # ---- the same device-resident step with TWO independent slots replayed alternately on two streams (what the e2e path
     # does with consecutive minibatches of an epoch): whole region timed, no L2 flush inside it (reported beside `value`)
     two_slot_ms = None
-    if graph2 is not None:
+    if extra:
         slots = [(graph, grad, torch.cuda.Stream(dev))] + [(g_, gr_, torch.cuda.Stream(dev)) for g_, gr_, _ in extra]
 
         def two_slot_region(n):

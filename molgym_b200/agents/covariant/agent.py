@@ -424,7 +424,11 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         if self._fused_streams is None:
             self._fused_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
         slot = self._fused_turn
-        self._fused_turn ^= 1
+        # two slots double the workspace (cat / dcat dominate: ~10 GB at C5 with 1024 canvases): keep one when that is too much
+        if 2 * _lib.load().mgb_cov_workspace_bytes(self._plan, B) > 0.25 * torch.cuda.get_device_properties(self.device).total_memory:
+            slot = 0
+        else:
+            self._fused_turn ^= 1
         st = self._fused_state(B, clip_ratio, vf_coef, entropy_coef, slot)
         st.generation += 1
         actions_np = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
