@@ -169,7 +169,8 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
   /* fork: the edge weight gradients (reductions over pairs of the scratch just written) run on side2 */                            \
   MGB_CUDA_OK(cudaEventRecord(plan->ev_fork2[k], st));                                                                              \
   MGB_CUDA_OK(cudaStreamWaitEvent(plan->side2, plan->ev_fork2[k], 0));                                                              \
-  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 0, plan->side2, plan->d_desc, k, B, w.pair_off, w.pair_slot, EPREV, w.D[k], sc, grad); \
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_edge_dw<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(float) * kEdgeDwBufFloats))); \
+  MGB_LAUNCH(k_edge_dw<NL>, dwgrid, kEdgeDwThreads, 2 * sizeof(float) * kEdgeDwBufFloats, plan->side2, plan->d_desc, k, B, w.pair_off, w.pair_slot, EPREV, w.D[k], sc, grad); \
   MGB_LAUNCH_OK("k_edge_dw");                                                                                                       \
   MGB_CUDA_OK(cudaEventRecord(plan->ev_join2[k], plan->side2));                                                                     \
   MGB_LAUNCH(k_dot_bwd<NL>, B * N, DOTTHREADS, 0, st, plan->d_desc, k, w.n_atoms, w.A[k], w.dD, split ? NL : 1, slice, w.dA[k & 1]);

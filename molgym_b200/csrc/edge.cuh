@@ -526,6 +526,9 @@ constexpr int kEdgeDwTile = 32;
 constexpr int kEdgeKMax = 7 * kEdgeC;   // [E_prev (C) | dot (5 C) | radial (C)]
 static_assert(kRadFeat == 32, "warp 3 of k_edge_dw maps one lane to one radial feature");
 
+// shared memory of one staging buffer (floats): cat tile + dpre + dR + f
+constexpr int kEdgeDwBufFloats = kEdgeDwTile * (2 * kEdgeKMax + 2 * kEdgeC + 2 * kEdgeC + kRadFeat);
+
 template <int NLIN>
 __global__ void __launch_bounds__(kEdgeDwThreads)
 k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict__ pair_off, const int* __restrict__ pair_slot,
@@ -537,63 +540,87 @@ k_edge_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restric
   const int per = max((int)((total + gridDim.x - 1) / gridDim.x), kEdgeDwTile);   // at least one full tile per CTA: fewer atomics
   const int p_begin = per * blockIdx.x, p_end = min(total, p_begin + per);
   if (p_begin >= p_end) return;
-  __shared__ __align__(16) float2 s_cat[kEdgeDwTile][kEdgeKMax];
-  __shared__ __align__(16) float2 s_dpre[kEdgeDwTile][kEdgeC];
-  __shared__ __align__(16) float s_dR[kEdgeDwTile][2 * kEdgeC];
-  __shared__ float s_f[kEdgeDwTile][kRadFeat];
+  // two staging buffers filled with cp.async: the next tile of pairs is in flight while the current one is reduced
+  MGB_DYN_SMEM(float, smem);
   const int tid = threadIdx.x;
   const bool edge_thread = tid < K, rad_thread = tid >= 96;
   const int kprev = L.has_prev ? C : 0, kdot = (l < NLIN) ? NLIN * C : 0;
+  auto cat_of = [&](int buf) { return reinterpret_cast<float2*>(smem + buf * kEdgeDwBufFloats); };                       // [tile][kEdgeKMax]
+  auto dpre_of = [&](int buf) { return cat_of(buf) + kEdgeDwTile * kEdgeKMax; };                                          // [tile][kEdgeC]
+  auto dR_of = [&](int buf) { return reinterpret_cast<float*>(dpre_of(buf) + kEdgeDwTile * kEdgeC); };                    // [tile][2 kEdgeC]
+  auto f_of = [&](int buf) { return dR_of(buf) + kEdgeDwTile * 2 * kEdgeC; };                                             // [tile][32]
   // channels beyond C stay zero for the whole kernel
-  for (int idx = tid; idx < kEdgeDwTile * kEdgeC; idx += blockDim.x) {
-    s_dpre[idx / kEdgeC][idx % kEdgeC] = make_float2(0.f, 0.f);
-    s_dR[idx / kEdgeC][2 * (idx % kEdgeC)] = 0.f;
-    s_dR[idx / kEdgeC][2 * (idx % kEdgeC) + 1] = 0.f;
+  for (int idx = tid; idx < 2 * kEdgeDwTile * kEdgeC; idx += blockDim.x) {
+    const int buf = idx / (kEdgeDwTile * kEdgeC), r = idx - buf * kEdgeDwTile * kEdgeC;
+    dpre_of(buf)[r] = make_float2(0.f, 0.f);
+    dR_of(buf)[2 * r] = 0.f;
+    dR_of(buf)[2 * r + 1] = 0.f;
   }
+  __syncthreads();
+  const float2* Ep = reinterpret_cast<const float2*>(E_prev);
+  const float2* Dp = reinterpret_cast<const float2*>(D);
+  const float2* Rp = reinterpret_cast<const float2*>(sc.R);
+  // stage one tile: thread k < K copies column k of the tile's cat rows (no index arithmetic beyond the pair slot), warp 3
+  // copies dpre / dR / f
+  auto stage = [&](int p0, int np, int buf) {
+    if (edge_thread) {
+      float2* dst = cat_of(buf) + tid;
+      if (tid < kprev) {
+        const float2* src = Ep + l * C + tid;
+        for (int q = 0; q < np; ++q) cp_async8(dst + q * kEdgeKMax, src + (long long)pair_slot[p0 + q] * kNL * C);
+      } else if (tid < kprev + kdot) {
+        const float2* src = Dp + (tid - kprev);
+        for (int q = 0; q < np; ++q) cp_async8(dst + q * kEdgeKMax, src + (long long)pair_slot[p0 + q] * kNL * C);
+      } else {
+        const float2* src = Rp + ((long long)p0 * kNL + l) * C + (tid - kprev - kdot);
+        for (int q = 0; q < np; ++q) cp_async8(dst + q * kEdgeKMax, src + (long long)q * kNL * C);
+      }
+    } else if (rad_thread) {
+      const int lane = tid - 96;
+      const float2* sp = reinterpret_cast<const float2*>(sc.dpre) + ((long long)p0 * kNL + l) * C;
+      const float2* sr = reinterpret_cast<const float2*>(sc.dR) + ((long long)p0 * kNL + l) * C;
+      for (int idx = lane; idx < np * C; idx += 32) {
+        const int q = idx / C, c = idx - q * C;
+        cp_async8(dpre_of(buf) + q * kEdgeC + c, sp + (long long)q * kNL * C + c);
+        cp_async8(reinterpret_cast<float2*>(dR_of(buf)) + q * kEdgeC + c, sr + (long long)q * kNL * C + c);
+      }
+      const float2* sf = reinterpret_cast<const float2*>(sc.f + (long long)p0 * kRadFeat);
+      for (int idx = lane; idx < np * (kRadFeat / 2); idx += 32) cp_async8(reinterpret_cast<float2*>(f_of(buf)) + idx, sf + idx);
+    }
+    cp_async_commit();
+  };
   float2 acc[kEdgeC];
   MGB_UNROLL
   for (int c = 0; c < kEdgeC; ++c) acc[c] = make_float2(0.f, 0.f);
   float racc[2 * kEdgeC], bacc = 0.f;
   MGB_UNROLL
   for (int o = 0; o < 2 * kEdgeC; ++o) racc[o] = 0.f;
-  const float2* Ep = reinterpret_cast<const float2*>(E_prev);
-  const float2* Dp = reinterpret_cast<const float2*>(D);
-  const float2* Rp = reinterpret_cast<const float2*>(sc.R);
-  for (int p0 = p_begin; p0 < p_end; p0 += kEdgeDwTile) {
+  stage(p_begin, min(kEdgeDwTile, p_end - p_begin), 0);
+  int buf = 0;
+  for (int p0 = p_begin; p0 < p_end; p0 += kEdgeDwTile, buf ^= 1) {
     const int np = min(kEdgeDwTile, p_end - p0);
-    __syncthreads();
-    for (int idx = tid; idx < np * K; idx += blockDim.x) {
-      const int q = idx / K, k = idx - q * K;
-      float2 x;
-      if (k < kprev) x = Ep[(long long)pair_slot[p0 + q] * kNL * C + l * C + k];
-      else if (k < kprev + kdot) x = Dp[(long long)pair_slot[p0 + q] * kNL * C + (k - kprev)];
-      else x = Rp[((long long)(p0 + q) * kNL + l) * C + (k - kprev - kdot)];
-      s_cat[q][k] = x;
-    }
-    for (int idx = tid; idx < np * C; idx += blockDim.x) {
-      const int q = idx / C, c = idx - q * C;
-      s_dpre[q][c] = reinterpret_cast<const float2*>(sc.dpre)[((long long)(p0 + q) * kNL + l) * C + c];
-      const float2 r = reinterpret_cast<const float2*>(sc.dR)[((long long)(p0 + q) * kNL + l) * C + c];
-      s_dR[q][2 * c] = r.x;
-      s_dR[q][2 * c + 1] = r.y;
-    }
-    for (int idx = tid; idx < np * kRadFeat; idx += blockDim.x) s_f[idx / kRadFeat][idx % kRadFeat] = sc.f[(long long)p0 * kRadFeat + idx];
-    __syncthreads();
+    cp_async_wait_all();
+    __syncthreads();   // this tile is visible to everyone, and everyone is done with the other buffer
+    if (p0 + kEdgeDwTile < p_end) stage(p0 + kEdgeDwTile, min(kEdgeDwTile, p_end - p0 - kEdgeDwTile), buf ^ 1);
     if (edge_thread) {
+      const float2* s_cat = cat_of(buf) + tid;
+      const float2* s_dpre = dpre_of(buf);
 #pragma unroll 2
       for (int q = 0; q < np; ++q) {
-        const float2 x = s_cat[q][tid];
+        const float2 x = s_cat[q * kEdgeKMax];
         MGB_UNROLL
-        for (int c = 0; c < kEdgeC; ++c) cfmacl(acc[c], x, s_dpre[q][c]);
+        for (int c = 0; c < kEdgeC; ++c) cfmacl(acc[c], x, s_dpre[q * kEdgeC + c]);
       }
     } else if (rad_thread) {
       const int t = tid - 96;
+      const float* s_dR = dR_of(buf);
+      const float* s_f = f_of(buf);
 #pragma unroll 2
       for (int q = 0; q < np; ++q) {
-        const float f = s_f[q][t];
+        const float f = s_f[q * kRadFeat + t];
         MGB_UNROLL
-        for (int o = 0; o < 2 * kEdgeC; ++o) racc[o] = fmaf(s_dR[q][o], f, racc[o]);
-        if (t < 2 * kEdgeC) bacc += s_dR[q][t];
+        for (int o = 0; o < 2 * kEdgeC; ++o) racc[o] = fmaf(s_dR[q * 2 * kEdgeC + o], f, racc[o]);
+        if (t < 2 * kEdgeC) bacc += s_dR[q * 2 * kEdgeC + t];
       }
     }
   }
