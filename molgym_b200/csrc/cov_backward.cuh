@@ -537,6 +537,13 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
   for (int c = 0; c < CO; ++c) { P[c] = pack2(0.f, 0.f); Q[c] = pack2(0.f, 0.f); }
   const float2* dO = reinterpret_cast<const float2*>(dA_out);
   const bool on = k < K;
+  // the rows of the NEXT atom are fetched while the current atom's rows are consumed (software pipeline over the atom list)
+  float2 xn[2 * kL + 1];
+  {
+    const float2* cr = reinterpret_cast<const float2*>(cat) + (long long)atom_list[a0] * L.totA + L.offA[l] + k;
+    MGB_UNROLL
+    for (int m = 0; m < 2 * kL + 1; ++m) xn[m] = (on && m < nm) ? cr[m * K] : make_float2(0.f, 0.f);
+  }
   for (int ab = a0; ab < a1; ab += kMixDwAtoms) {
     const int cnt = min(kMixDwAtoms, a1 - ab);
     __syncthreads();
@@ -546,11 +553,15 @@ k_mix_dw(const CovDesc* __restrict__ dp, int level, int B, const int* __restrict
     }
     __syncthreads();
     for (int a = 0; a < cnt; ++a) {
-      const float2* cr = reinterpret_cast<const float2*>(cat) + (long long)atom_list[ab + a] * L.totA + L.offA[l] + k;
       const float2* ga = sd + a * nm * CO;
       float2 xv[2 * kL + 1];
       MGB_UNROLL
-      for (int m = 0; m < 2 * kL + 1; ++m) xv[m] = (on && m < nm) ? cr[m * K] : make_float2(0.f, 0.f);
+      for (int m = 0; m < 2 * kL + 1; ++m) xv[m] = xn[m];
+      if (ab + a + 1 < a1) {
+        const float2* cr = reinterpret_cast<const float2*>(cat) + (long long)atom_list[ab + a + 1] * L.totA + L.offA[l] + k;
+        MGB_UNROLL
+        for (int m = 0; m < 2 * kL + 1; ++m) xn[m] = (on && m < nm) ? cr[m * K] : make_float2(0.f, 0.f);
+      }
       MGB_UNROLL
       for (int m = 0; m < 2 * kL + 1; ++m) {
         if (m < nm) {
