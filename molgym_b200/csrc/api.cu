@@ -335,7 +335,8 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     // high-priority main stream (the Python layer captures its graphs on one)
     int lo = 0, hi = 0;
     MGB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo: least priority (numerically largest), hi: greatest
-    const int mid = hi < lo - 1 ? lo - (lo - hi) / 2 : lo;
+    int mid = hi < lo - 1 ? lo - (lo - hi) / 2 : lo;
+    if (const char* e = std::getenv("MGB_SIDE3_PRIO")) mid = std::atoi(e);   // tuning knob
     MGB_CUDA_OK(cudaStreamCreateWithPriority(&plan->side3, cudaStreamNonBlocking, mid));
   }
   for (int q = 0; q <= kMaxLevels; ++q) {
