@@ -118,6 +118,17 @@ def ppo_loss(logp, ent, v, old_logp, adv, ret, clip, vf, ent_coef, inv_b=None):
     return info, g
 
 
+def scale_accumulate(dst, src, scale, accumulate):
+    """mgb_scale_accumulate on host arrays (dst / src must be 16-byte aligned: numpy allocations are)."""
+    L = lib()
+    dst = np.ascontiguousarray(dst, np.float32).copy()
+    src = np.ascontiguousarray(src, np.float32)
+    sc = np.asarray([scale])
+    assert sc.dtype in (np.float32, np.float64)
+    _cabi.check(L, L.mgb_scale_accumulate(ptr(dst), ptr(src), ptr(sc), 1 if sc.dtype == np.float64 else 0, dst.size, int(accumulate), None))
+    return dst
+
+
 def pack(zs, canvas_size, labels, xyz):
     L = lib()
     cfg = _cabi.CovConfig()

@@ -114,6 +114,20 @@ def test_ppo_loss_kernel_matches_oracle_including_clipped_and_tied_branches():
     np.testing.assert_allclose(gv, tv.grad.numpy(), rtol=1e-6, atol=1e-9)
 
 
+def test_scale_accumulate_kernel():
+    """.grad (+)= cotangent * scratch gradient of the fused PPO step (mgb_scale_accumulate): float64 / float32 device scalar,
+    overwrite / accumulate, lengths that are not a multiple of the vector width."""
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 64, 1003):
+        dst, src = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+        for scale in (np.float64(0.25), np.float32(-1.5)):
+            got = runner.scale_accumulate(dst, src, scale, accumulate=False)
+            np.testing.assert_array_equal(got, (np.float32(scale) * src).astype(np.float32))
+            got = runner.scale_accumulate(dst, src, scale, accumulate=True)
+            ref = np.float32(scale) * src.astype(np.float64) + dst   # one fused multiply-add per element
+            np.testing.assert_allclose(got, ref.astype(np.float32), rtol=1e-6, atol=1e-7)
+
+
 def test_packer_matches_oracle_and_rejects_bad_labels():
     cfg = synth.CONFIGS['C3']
     obs, _ = synth.make_observations(cfg, batch=9)
