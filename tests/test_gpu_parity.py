@@ -88,10 +88,13 @@ def test_fresh_canvases_against_oracle(which, batch):
 @pytest.mark.parametrize('mode', ['0', '1', '2'])
 def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
     """The per-pair edge kernels exist in three decompositions picked by minibatch size (thread per pair, per (pair, ell),
-    five threads per (pair, ell)); MGB_EDGE_MODE forces each of them on the same canvases."""
+    five threads per (pair, ell)); MGB_EDGE_MODE forces each of them on the same canvases.  Mode 0 also forces the
+    large-minibatch atom path (MGB_SMALL_ATOMS=0), which the small parity batches would otherwise never take."""
     from oracle.molgym_oracle import CovariantOracle, ppo_loss
     from molgym_b200 import ppo
     monkeypatch.setenv('MGB_EDGE_MODE', mode)
+    if mode == '0':   # together with the large-minibatch atom path (combined atom kernels, tiled InputLinear weight gradient)
+        monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
     cfg = synth.CONFIGS['C3']
     torch.manual_seed(5)
     agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())

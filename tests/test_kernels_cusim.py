@@ -47,6 +47,8 @@ def test_golden_forward_backward(name):
 def test_fresh_canvases_against_oracle(levels, beta, zs, canvas, edge_mode, monkeypatch):
     if edge_mode is not None:   # the three decompositions of the per-pair edge kernels (plan.cuh: edge_mode_override)
         monkeypatch.setenv('MGB_EDGE_MODE', edge_mode)
+        if edge_mode == '0':    # ... and the large-minibatch atom path (combined atom kernels, tiled InputLinear gradient)
+            monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
     cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=canvas, network_width=32, num_cg_levels=levels, beta=beta,
                               bag={z: 2 for z in zs if z}, bag_scale=4, seed=levels)
     torch.manual_seed(levels)
