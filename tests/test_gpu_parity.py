@@ -85,6 +85,30 @@ def test_fresh_canvases_against_oracle(which, batch):
     assert_grads_close(grads_of(agent), ref_grads)
 
 
+def test_six_species_24_output_channels_against_oracle():
+    """Z = 6 species x 4 channels = 24 output channels: the widest register tile of the row mix (CO = 32) and two channel
+    passes of the atom-mix weight gradient, paths the benchmark configurations (Z <= 5) never take."""
+    from oracle.molgym_oracle import CovariantOracle, ppo_loss
+    from molgym_b200 import ppo
+    zs = [0, 1, 6, 7, 8, 9]
+    cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=6, network_width=64, bag={z: 2 for z in zs if z}, bag_scale=4, seed=3)
+    torch.manual_seed(9)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle.load_state_dict({k: v.detach().cpu() for k, v in agent.state_dict().items()})
+    obs, n = synth.make_observations(cfg, batch=20)
+    act = synth.make_actions(cfg, obs, n)
+    ref = oracle.step(obs, act)
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, ref['logp'].detach().numpy())
+    loss, _ = ppo.compute_loss(agent, dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret), 0.2, 0.5, 0.01)
+    loss.backward()
+    ref_loss, _ = ppo_loss(ref['logp'], ref['ent'], ref['v'], old_logp, adv, ret, 0.2, 0.5, 0.01)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5
+    ref_grads = {k: (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k, p in oracle.named_parameters()}
+    assert_grads_close(grads_of(agent), ref_grads)
+
+
 @pytest.mark.parametrize('mode', ['0', '1', '2'])
 def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
     """The per-pair edge kernels exist in three decompositions picked by minibatch size (thread per pair, per (pair, ell),

@@ -43,7 +43,8 @@ def test_golden_forward_backward(name):
 
 
 @pytest.mark.parametrize('levels,beta,zs,canvas,edge_mode', [(1, -10.0, [0, 9, 16], 7, None), (2, None, [0, 1, 6, 7, 8], 6, '0'),
-                                                             (2, None, [0, 1, 6, 7, 8], 6, '1'), (2, None, [0, 1, 6, 7, 8], 6, '2')])
+                                                             (2, None, [0, 1, 6, 7, 8], 6, '1'), (2, None, [0, 1, 6, 7, 8], 6, '2'),
+                                                             (2, -5.0, [0, 1, 6, 7, 8, 9], 5, None)])   # 24 output channels: two passes of the weight-gradient kernel, CO = 32 row mix
 def test_fresh_canvases_against_oracle(levels, beta, zs, canvas, edge_mode, monkeypatch):
     if edge_mode is not None:   # the three decompositions of the per-pair edge kernels (plan.cuh: edge_mode_override)
         monkeypatch.setenv('MGB_EDGE_MODE', edge_mode)
