@@ -109,6 +109,35 @@ def test_six_species_24_output_channels_against_oracle():
     assert_grads_close(grads_of(agent), ref_grads)
 
 
+def test_odd_hyperparameters_against_oracle():
+    """6 hidden channels (run-time channel stride, zero-padded edge tiles), 3 channels per element (9 output channels), width 30
+    (the row MLPs fall back from the bulk-copy kernels; unaligned bulk copies fall back to plain loads), 2 Gaussians."""
+    from oracle.molgym_oracle import CovariantOracle, ppo_loss
+    from molgym_b200 import ppo
+    zs = [0, 1, 8]
+    cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=5, network_width=30, num_cg_levels=2, beta=-3.0,
+                              num_channels_hidden=6, num_channels_per_element=3, num_gaussians=2, bag={1: 3, 8: 2}, bag_scale=4, seed=5)
+    torch.manual_seed(4)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    oracle.load_state_dict({k: v.detach().cpu() for k, v in agent.state_dict().items()})
+    obs, n = synth.make_observations(cfg, batch=25)
+    act = synth.make_actions(cfg, obs, n)
+    ref = oracle.step(obs, act)
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, ref['logp'].detach().numpy())
+    for fused in (True, False):
+        agent.fused_ppo = fused
+        agent.zero_grad()
+        loss, _ = ppo.compute_loss(agent, dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret), 0.2, 0.5, 0.01)
+        loss.backward()
+        if fused:
+            ref_loss, _ = ppo_loss(ref['logp'], ref['ent'], ref['v'], old_logp, adv, ret, 0.2, 0.5, 0.01)
+            ref_loss.backward()
+        assert abs(loss.item() - ref_loss.item()) <= 1e-5
+        ref_grads = {k: (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k, p in oracle.named_parameters()}
+        assert_grads_close(grads_of(agent), ref_grads)
+
+
 @pytest.mark.parametrize('mode', ['0', '1', '2'])
 def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
     """The per-pair edge kernels exist in three decompositions picked by minibatch size (thread per pair, per (pair, ell),

@@ -75,6 +75,31 @@ def test_fresh_canvases_against_oracle(levels, beta, zs, canvas, edge_mode, monk
     assert_grads_close(grad, ref_grads)
 
 
+def test_odd_hyperparameters_take_the_generic_paths():
+    """6 hidden channels (run-time channel stride instead of the compile-time 10, zero-padded edge register tiles), 3 channels
+    per element, network width 30 (not a multiple of 4: the row MLPs fall back from the bulk-copy kernels), 2 Gaussians."""
+    zs = [0, 1, 8]
+    cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=5, network_width=30, num_cg_levels=2, beta=-3.0,
+                              num_channels_hidden=6, num_channels_per_element=3, num_gaussians=2, bag={1: 3, 8: 2}, bag_scale=4, seed=5)
+    torch.manual_seed(4)
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    B = 6
+    obs, n = synth.make_observations(cfg, batch=B)
+    act = synth.make_actions(cfg, obs, n)
+    pos, charges, bags = pack_observations(obs, cfg.zs, cfg.canvas_size)
+    ref = oracle.evaluate(pos, charges, bags, act)
+    sim = runner.CusimCov(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    out = sim.forward(pos, charges, bags, act, sim.flatten(oracle.state_dict()))
+    for key in ('logp', 'ent', 'v'):
+        assert_outputs_close(out[key], ref[key].detach().numpy(), rel=OUT_REL, what=key)
+    rng = np.random.default_rng(2)
+    gl, ge, gv = (rng.normal(size=B).astype(np.float32) for _ in range(3))
+    (ref['logp'] * torch.tensor(gl) + ref['ent'] * torch.tensor(ge) + ref['v'] * torch.tensor(gv)).sum().backward()
+    grad = sim.unflatten(sim.backward(gl, ge, gv), {k: tuple(v.shape) for k, v in oracle.state_dict().items()})
+    ref_grads = {k: (p.grad.numpy() if p.grad is not None else np.zeros(p.shape, np.float32)) for k, p in oracle.named_parameters()}
+    assert_grads_close(grad, ref_grads)
+
+
 def test_edge_canvases_empty_single_full():
     """Empty canvas (bias-only logits, uniform orientation), one atom, completely filled canvas."""
     cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=32, canvas_size=4, bag={16: 1, 9: 4})
