@@ -8,14 +8,16 @@ sampling.  There is no CPU fallback: without the CUDA library / a CUDA device co
 """
 import ctypes
 import math
+import weakref
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
 import torch.nn as nn
 
-from molgym_b200 import _cabi, _lib
+from molgym_b200 import _cabi
 from molgym_b200.agents._flat import FlatParamMixin
+from molgym_b200.agents._runtime import CudaRuntime
 from molgym_b200.agents.base import AbstractActorCritic
 from molgym_b200.agents.covariant import sampling
 from molgym_b200.agents.covariant.packing import pack_observations
@@ -60,6 +62,35 @@ class _CovEvaluate(torch.autograd.Function):
         return (None, ) * 6
 
 
+class _CovEvaluateSlot(torch.autograd.Function):
+    """The same function evaluated by CUDA-graph replays on the persistent buffers of an evaluation slot (the path the
+    reference's unchanged ppo.compute_loss takes: agent.step(obs, act) -> torch loss -> loss.backward())."""
+
+    @staticmethod
+    def forward(ctx, anchor, agent, st):
+        st.g_forward.replay()
+        outs = agent._slot_outputs(st, st.out_all.clone())   # one copy: the slot's buffers are reused by the next step
+        ctx.agent, ctx.st, ctx.generation = agent, st, st.generation
+        st.live, st.done = weakref.ref(ctx), False   # the slot is busy until this node ran its backward or was dropped
+        ctx.mark_non_differentiable(*outs[3:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_logp, g_ent, g_v, *unused):
+        st, agent = ctx.st, ctx.agent
+        if st.generation != ctx.generation:
+            raise RuntimeError('internal: evaluation slot reused before its backward ran')
+        for dst, g in zip(st.cot, (g_logp, g_ent, g_v)):
+            if g is None:
+                dst.zero_()
+            else:
+                dst.copy_(g)
+        st.g_backward.replay()
+        agent._accumulate_scratch(st.grad, agent._one, agent._rt.current_stream())
+        st.done = True
+        return None, None, None
+
+
 class _FusedPPOLoss(torch.autograd.Function):
     """The scalar PPO loss of CovariantAC.fused_ppo_loss.  Its parameter gradient already sits in the step's scratch buffer
     (the backward graph was enqueued right behind the forward); backward() scales it by the incoming cotangent into `.grad`."""
@@ -78,12 +109,20 @@ class _FusedPPOLoss(torch.autograd.Function):
         return None, None, None, None
 
 
-class _FusedState:
-    """Persistent buffers + captured CUDA graphs of the fused PPO step for one minibatch size."""
+class _StepState:
+    """Persistent buffers + captured CUDA graphs of one minibatch size (fused PPO step or evaluation slot)."""
     pass
 
 
+def _as_numpy_actions(actions, n: int, width: int) -> np.ndarray:
+    a = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
+    assert a.shape == (n, width)
+    return a
+
+
 class CovariantAC(FlatParamMixin, AbstractActorCritic):
+    _runtime_cls = CudaRuntime   # the test-suite's emulator-backed subclass substitutes a host runtime
+
     def __init__(
         self,
         observation_space,
@@ -100,7 +139,8 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         device=None,
     ):
         super().__init__(observation_space, action_space)
-        self.device = _lib.require_cuda_device(device)
+        self._rt = self._runtime_cls(device)
+        self.device = self._rt.device
         self.dtype = torch.float
         self.zs = list(self.observation_space.zs)
         self.min_distance, self.max_distance = min_max_distance
@@ -118,6 +158,8 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         self.data_parallel = False   # set by molgym_b200.parallel.shard_agent
         self.fused_ppo = True        # molgym_b200.ppo.compute_loss may use fused_ppo_loss (CUDA-graph replay of the whole step)
         self.fused_sync_params = False   # True: the fused step waits for the caller's stream every time (see fused_ppo_loss)
+        self.graph_evaluate = True   # evaluate-mode step() under autograd replays CUDA graphs on persistent slots
+        self._check_supported()
         self._init_native()
         self._init_parameters()
 
@@ -130,12 +172,35 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                     num_channels_per_element=self.num_channels_per_element, num_gaussians=self.num_gaussians,
                     bag_scale=self.bag_scale, beta=self.beta)
 
+    def _check_supported(self):
+        """The reference accepts any hyper-parameters (tools/arg_parser.py:55-61); the sm_100a kernels are instantiated for the
+        ranges below (they cover BASELINE.json's five configurations and the reference's defaults)."""
+        problems = []
+        if self.max_sh != 4:
+            problems.append(f'maxl={self.max_sh} (supported: 4)')
+        if not 1 <= self.num_cg_levels <= 4:
+            problems.append(f'num_cg_levels={self.num_cg_levels} (supported: 1..4)')
+        if not 1 <= self.num_channels_hidden <= 10:
+            problems.append(f'num_channels_hidden={self.num_channels_hidden} (supported: 1..10)')
+        if not 1 <= self.num_channels_per_element <= 4:
+            problems.append(f'num_channels_per_element={self.num_channels_per_element} (supported: 1..4)')
+        if self.num_channels_out > 32:
+            problems.append(f'len(zs) * num_channels_per_element={self.num_channels_out} (supported: <= 32)')
+        if not 1 <= self.canvas_size <= 64:
+            problems.append(f'canvas_size={self.canvas_size} (supported: 1..64)')
+        if not 1 <= self.num_gaussians <= 8:
+            problems.append(f'num_gaussians={self.num_gaussians} (supported: 1..8)')
+        if not 1 <= self.network_width <= 1024:
+            problems.append(f'network_width={self.network_width} (supported: 1..1024)')
+        if problems:
+            raise ValueError('molgym_b200.CovariantAC: unsupported hyper-parameters: ' + '; '.join(problems))
+
     def _init_native(self):
-        lib = _lib.load()
+        lib = self._rt.lib()
         self._cfg = _cabi.make_config(self.zs, self.canvas_size, **self._config_kwargs())
         xyz, w = _lebedev_071()
         plan = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
+        with self._rt.device_ctx():
             _cabi.check(lib, lib.mgb_cov_plan_create(ctypes.byref(self._cfg), xyz.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                                      w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(w), ctypes.byref(plan)))
         self._plan = plan
@@ -151,11 +216,13 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         assert len(self._p_names) == n
         self._cat_sizes = list(cats)
         self._ws_cache: Dict[int, torch.Tensor] = {}
-        self._fused_cache: Dict[tuple, _FusedState] = {}
+        self._fused_cache: Dict[tuple, _StepState] = {}
+        self._eval_cache: Dict[int, list] = {}
         self._fused_streams = None
         self._fused_turn = 0
         self._fused_param_version = None
         self._fused_acc_event = None
+        self._one = torch.ones(1, dtype=torch.float32, device=self.device)
 
     def _param_shapes(self) -> Dict[str, tuple]:
         C, Z, cpe, W, G = self.num_channels_hidden, len(self.zs), self.num_channels_per_element, self.network_width, self.num_gaussians
@@ -238,19 +305,28 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ('_plan', '_cfg', '_ws_cache', '_fused_cache', '_fused_streams', '_fused_acc_event', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
+        for k in ('_rt', '_plan', '_cfg', '_ws_cache', '_fused_cache', '_eval_cache', '_fused_streams', '_fused_acc_event', '_one',
+                  '_flat', '_flat_grad', '_grad_local', '_grad_pending', '_views', '_grad_views', '_param_list'):
             state.pop(k, None)
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
-        self.device = _lib.require_cuda_device(self.device)
+        self.__dict__.setdefault('graph_evaluate', True)
+        # torch.load(map_location=...) moves the unpickled parameters: follow them when they sit on a usable device
+        # (tools/model_util.py:93-117 loads whole modules), else keep the pickled device, else the current one
+        where = next(iter(torch.nn.Module.parameters(self))).device
+        try:
+            self._rt = self._runtime_cls(where)
+        except Exception:
+            self._rt = self._runtime_cls(None)
+        self.device = self._rt.device
         self._init_native()
         self._rebuild_flat_after_unpickle()
 
     def __del__(self):
         try:
-            _lib.load().mgb_cov_plan_destroy(self._plan)
+            self._rt.lib().mgb_cov_plan_destroy(self._plan)
         except Exception:
             pass
 
@@ -258,8 +334,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
     # raw forward / backward through the C ABI
     # ------------------------------------------------------------------------------------------------------
     def _workspace(self, B: int, fresh: bool) -> torch.Tensor:
-        lib = _lib.load()
-        nbytes = lib.mgb_cov_workspace_bytes(self._plan, B)
+        nbytes = self._rt.lib().mgb_cov_workspace_bytes(self._plan, B)
         if fresh:
             return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         ws = self._ws_cache.get(B)
@@ -268,28 +343,40 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             self._ws_cache = {B: ws}
         return ws
 
+    def _out_layout(self, B: int):
+        """Segments (in floats) of the packed output block: logp, ent, v, logp_parts, focus_probs, element_probs, gmm,
+        coefficients, log_z."""
+        N, Z, G, cpe = self.canvas_size, len(self.zs), self.num_gaussians, self.num_channels_per_element
+        shapes = [(B, ), (B, ), (B, ), (B, 4), (B, N), (B, Z), (B, 3, G), (B, 25, cpe, 2), (B, )]
+        offs, o = [], 0
+        for sh in shapes:
+            offs.append(o)
+            o += int(np.prod(sh))
+        return shapes, offs, o
+
+    def _slot_outputs(self, st, block: torch.Tensor):
+        return tuple(block[o:o + int(np.prod(sh))].view(sh) for sh, o in zip(st.out_shapes, st.out_offs))
+
+    def _cov_outputs(self, block: torch.Tensor, B: int, want_extras: bool):
+        shapes, offs, _ = self._out_layout(B)
+        o = _cabi.CovOutputs()
+        base = block.data_ptr()
+        names = ('logp', 'ent', 'v', 'logp_parts', 'focus_probs', 'element_probs', 'gmm', 'coefficients', 'log_z')
+        for name, off in list(zip(names, offs))[:9 if want_extras else 3]:
+            setattr(o, name, base + 4 * off)
+        return o, shapes, offs
+
     def _forward_raw(self, pos, charges, bags, actions, want_extras=True, policy_only_ws=None):
-        lib = _lib.load()
+        lib = self._rt.lib()
         if not self._params_aliased():
             self._realias()
-        B, N, Z = pos.shape[0], self.canvas_size, len(self.zs)
-        dev = self.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        logp, ent, v = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
-        extras = ()
-        o = _cabi.CovOutputs()
-        o.logp, o.ent, o.v = logp.data_ptr(), ent.data_ptr(), v.data_ptr()
-        if want_extras:
-            parts = torch.empty(B, 4, **f32)
-            fprobs, eprobs = torch.empty(B, N, **f32), torch.empty(B, Z, **f32)
-            gmm = torch.empty(B, 3, self.num_gaussians, **f32)
-            coeff = torch.empty(B, 25, self.num_channels_per_element, 2, **f32)
-            log_z = torch.empty(B, **f32)
-            o.logp_parts, o.focus_probs, o.element_probs = parts.data_ptr(), fprobs.data_ptr(), eprobs.data_ptr()
-            o.gmm, o.coefficients, o.log_z = gmm.data_ptr(), coeff.data_ptr(), log_z.data_ptr()
-            extras = (parts, fprobs, eprobs, gmm, coeff, log_z)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        B = pos.shape[0]
+        shapes, offs, total = self._out_layout(B)
+        block = torch.empty(total, dtype=torch.float32, device=self.device)
+        o, _, _ = self._cov_outputs(block, B, want_extras)
+        outs = tuple(block[off:off + int(np.prod(sh))].view(sh) for sh, off in list(zip(shapes, offs))[:9 if want_extras else 3])
+        stream = self._rt.stream_ptr()
+        with self._rt.device_ctx():
             if policy_only_ws is not None:
                 ws = policy_only_ws
                 _cabi.check(lib, lib.mgb_cov_policy(self._plan, B, bags.data_ptr(), actions.data_ptr(), self._flat.data_ptr(),
@@ -299,51 +386,63 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                 _cabi.check(lib, lib.mgb_cov_forward(self._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
                                                      actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(),
                                                      ctypes.byref(o), stream))
-        return (logp, ent, v) + extras, ws
+        return outs, ws
 
     def _backward_raw(self, pos, charges, bags, actions, ws, g_logp, g_ent, g_v):
-        lib = _lib.load()
-        dev = self.device
+        lib = self._rt.lib()
         B = pos.shape[0]
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = self._rt.stream_ptr()
         keep = self._attach_grads()
         target, accumulate = self._grad_target(keep)
-        with torch.cuda.device(dev):
+        with self._rt.device_ctx():
             _cabi.check(lib, lib.mgb_cov_backward(self._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
                                                   actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(),
                                                   g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), target.data_ptr(),
                                                   accumulate, stream))
-            self._finish_grads(keep)
+
+    def _accumulate_scratch(self, scratch: torch.Tensor, scale: torch.Tensor, stream, keep=None):
+        """.grad (or, data-parallel, the shard-local gradient) (+)= scale * scratch: one kernel on `stream`."""
+        lib = self._rt.lib()
+        if keep is None:
+            keep = self._attach_grads()                  # may zero the flat gradient on the caller's stream
+        target, accumulate = self._grad_target(keep)
+        _cabi.check(lib, lib.mgb_scale_accumulate(target.data_ptr(), scratch.data_ptr(), scale.data_ptr(),
+                                                  1 if scale.dtype == torch.float64 else 0, target.numel(), accumulate,
+                                                  self._rt.stream_ptr(stream)))
+
+    def _check_actions(self, actions_np: np.ndarray):
+        """Discrete sub-actions index the canvas and the species list on the device; the reference raises from to_one_hot for
+        indices outside the range (modules.py:8-23, pinned by tests/test_modules.py:22-29)."""
+        if actions_np.shape[0] == 0:
+            return
+        focus, element = np.rint(actions_np[:, 0]), np.rint(actions_np[:, 1])
+        if not (np.all((focus >= 0) & (focus < self.canvas_size)) and np.all((element >= 0) & (element < len(self.zs)))):
+            raise RuntimeError(f'action index out of range: focus must be in [0, {self.canvas_size}), element in [0, {len(self.zs)})')
+
+    def _shard(self, n: int) -> Tuple[int, int]:
+        """The slice of a minibatch of n canvases this rank evaluates (everything when the agent is not data-parallel)."""
+        if not self._is_sharded():
+            return 0, n
+        from molgym_b200.parallel import shard_bounds
+        lo, hi = shard_bounds(n, torch.distributed.get_rank(), torch.distributed.get_world_size())
+        if hi <= lo:
+            raise RuntimeError(f'a minibatch of {n} canvases cannot be sharded over {torch.distributed.get_world_size()} ranks')
+        return lo, hi
 
     # ------------------------------------------------------------------------------------------------------
-    # fused PPO minibatch step: pack -> one H2D copy -> CUDA-graph replay of forward + PPO-clip loss, then of the backward
+    # persistent step state: pinned + device staging, workspace, outputs, CUDA graphs
     # ------------------------------------------------------------------------------------------------------
-    def _capture(self, fn):
-        dev = self.device
-        fn(torch.cuda.current_stream(dev).cuda_stream)   # eager warm-up: function attributes, lazy module loading
-        torch.cuda.current_stream(dev).synchronize()
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(dev, priority=-5)   # the critical chain outranks the plan's (default-priority) side streams
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(graph, stream=side):
-                fn(torch.cuda.current_stream(dev).cuda_stream)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        return graph
-
-    def _fused_state(self, B: int, clip_ratio: float, vf_coef: float, entropy_coef: float, slot: int) -> _FusedState:
-        key = (B, float(clip_ratio), float(vf_coef), float(entropy_coef), self._flat.data_ptr(), slot)
-        st = self._fused_cache.get(key)
-        if st is not None:
-            return st
-        lib = _lib.load()
+    def _new_step_state(self, B: int, with_targets: bool) -> _StepState:
+        lib, rt = self._rt.lib(), self._rt
         dev, N, Z = self.device, self.canvas_size, len(self.zs)
-        st = _FusedState()
-        sizes = [B * N * 3 * 4, B * N * 4, B * Z * 4, B * 6 * 4, B * 4, B * 8, B * 8]   # pos, charges, bags, act, old_logp, adv, ret
+        st = _StepState()
+        sizes = [B * N * 3 * 4, B * N * 4, B * Z * 4, B * 6 * 4]           # pos, charges, bags, act
+        if with_targets:
+            sizes += [B * 4, B * 8, B * 8]                                   # old_logp, adv, ret
         offs = [0]
         for sz in sizes:
             offs.append((offs[-1] + sz + 255) // 256 * 256)
-        st.host = torch.empty(offs[-1], dtype=torch.uint8, pin_memory=True)
+        st.host = rt.pinned(offs[-1])
         st.dev = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
         h = st.host.numpy()
         seg = lambda buf, i: buf[offs[i]:offs[i] + sizes[i]]
@@ -351,37 +450,52 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         st.h_charges = seg(h, 1).view(np.int32).reshape(B, N)
         st.h_bags = seg(h, 2).view(np.float32).reshape(B, Z)
         st.h_act = seg(h, 3).view(np.float32).reshape(B, 6)
-        st.h_old = seg(h, 4).view(np.float32)
-        st.h_adv = seg(h, 5).view(np.float64)
-        st.h_ret = seg(h, 6).view(np.float64)
         st.pos = seg(st.dev, 0).view(torch.float32).view(B, N, 3)
         st.charges = seg(st.dev, 1).view(torch.int32).view(B, N)
         st.bags = seg(st.dev, 2).view(torch.float32).view(B, Z)
         st.act = seg(st.dev, 3).view(torch.float32).view(B, 6)
-        st.old = seg(st.dev, 4).view(torch.float32)
-        st.adv = seg(st.dev, 5).view(torch.float64)
-        st.ret = seg(st.dev, 6).view(torch.float64)
+        if with_targets:
+            st.h_old = seg(h, 4).view(np.float32)
+            st.h_adv = seg(h, 5).view(np.float64)
+            st.h_ret = seg(h, 6).view(np.float64)
+            st.old = seg(st.dev, 4).view(torch.float32)
+            st.adv = seg(st.dev, 5).view(torch.float64)
+            st.ret = seg(st.dev, 6).view(torch.float64)
+        h[...] = 0
+        st.dev.copy_(st.host)
+        st.h2d_bytes = int(sum(sizes))
+        st.grad = torch.zeros_like(self._flat_grad)
+        st.ws = torch.empty(lib.mgb_cov_workspace_bytes(self._plan, B), dtype=torch.uint8, device=dev)
+        st.B = B
+        st.generation = 0
+        return st
+
+    def _fused_state(self, B: int, n_global: int, clip_ratio: float, vf_coef: float, entropy_coef: float, slot: int) -> _StepState:
+        key = (B, n_global, float(clip_ratio), float(vf_coef), float(entropy_coef), self._flat.data_ptr(), slot)
+        st = self._fused_cache.get(key)
+        if st is not None:
+            return st
+        lib, rt = self._rt.lib(), self._rt
+        dev = self.device
+        st = self._new_step_state(B, with_targets=True)
         f32 = dict(dtype=torch.float32, device=dev)
         st.out = torch.empty(6, B, **f32)   # logp, ent, v, g_logp, g_ent, g_v
         st.info = torch.zeros(8, dtype=torch.float64, device=dev)
-        st.info_host = torch.zeros(8, dtype=torch.float64, pin_memory=True)
-        st.grad = torch.zeros_like(self._flat_grad)
-        st.ws = torch.empty(lib.mgb_cov_workspace_bytes(self._plan, B), dtype=torch.uint8, device=dev)
-        st.event = torch.cuda.Event()
-        st.acc_event = torch.cuda.Event()
-        st.B = B
-        st.generation = 0
+        st.info_host = rt.pinned(64).view(torch.float64)
+        st.event = rt.new_event()
+        st.acc_event = rt.new_event()
         st.stream = self._fused_streams[slot]
         o = _cabi.CovOutputs()
         o.logp, o.ent, o.v = st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr()
         st.outputs = o
         plan, flat = self._plan, self._flat
+        inv_global = 1.0 / n_global   # the loss is the mean over the GLOBAL minibatch (ppo.py:36-52); a shard adds its part
 
         def forward_and_loss(stream):
             _cabi.check(lib, lib.mgb_cov_forward(plan, B, st.pos.data_ptr(), st.charges.data_ptr(), st.bags.data_ptr(), st.act.data_ptr(),
                                                  flat.data_ptr(), st.ws.data_ptr(), st.ws.numel(), ctypes.byref(o), stream))
             _cabi.check(lib, lib.mgb_ppo_loss(B, st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr(), st.old.data_ptr(),
-                                              st.adv.data_ptr(), st.ret.data_ptr(), clip_ratio, vf_coef, entropy_coef, 1.0 / B,
+                                              st.adv.data_ptr(), st.ret.data_ptr(), clip_ratio, vf_coef, entropy_coef, inv_global,
                                               st.info.data_ptr(), st.out[3].data_ptr(), st.out[4].data_ptr(), st.out[5].data_ptr(), stream))
 
         def backward(stream):
@@ -389,22 +503,58 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                                                   flat.data_ptr(), st.ws.data_ptr(), st.ws.numel(), st.out[3].data_ptr(),
                                                   st.out[4].data_ptr(), st.out[5].data_ptr(), st.grad.data_ptr(), 0, stream))
 
-        with torch.cuda.device(dev):
-            st.h_pos[...] = 0
-            st.h_charges[...] = 0
-            st.h_bags[...] = 0
-            st.h_act[...] = 0
-            st.h_old[...] = 0
-            st.h_adv[...] = 0
-            st.h_ret[...] = 0
-            st.dev.copy_(st.host)
-            st.g_forward = self._capture(forward_and_loss)
-            st.g_backward = self._capture(backward)
+        with rt.device_ctx():
+            st.g_forward = rt.capture(forward_and_loss)
+            st.g_backward = rt.capture(backward)
         if len(self._fused_cache) >= 8:   # (minibatch size + remainder size) x two pipeline slots (+ a change of coefficients)
             self._fused_cache.pop(next(iter(self._fused_cache)))
         self._fused_cache[key] = st
         return st
 
+    def _eval_slot(self, B: int) -> Optional[_StepState]:
+        """A free evaluation slot for minibatches of B canvases, or None when both are still waiting for their backward."""
+        slots = self._eval_cache.setdefault(B, [])
+        for st in slots:
+            if st.flat_ptr != self._flat.data_ptr():
+                continue
+            if st.done or st.live is None or st.live() is None:
+                return st
+        if len([s for s in slots if s.flat_ptr == self._flat.data_ptr()]) >= 2:
+            return None
+        if sum(len(v) for v in self._eval_cache.values()) >= 6:
+            self._eval_cache.pop(next(iter(self._eval_cache)))
+            slots = self._eval_cache.setdefault(B, [])
+        lib, rt = self._rt.lib(), self._rt
+        st = self._new_step_state(B, with_targets=False)
+        st.flat_ptr = self._flat.data_ptr()
+        st.out_shapes, st.out_offs, total = self._out_layout(B)
+        st.out_all = torch.empty(total, dtype=torch.float32, device=self.device)
+        st.cot = torch.zeros(3, B, dtype=torch.float32, device=self.device)
+        o, _, _ = self._cov_outputs(st.out_all, B, True)
+        st.outputs = o
+        st.live, st.done = None, True
+        st.copied = rt.new_event()
+        st.copied.record(rt.current_stream())
+        plan, flat = self._plan, self._flat
+
+        def forward(stream):
+            _cabi.check(lib, lib.mgb_cov_forward(plan, B, st.pos.data_ptr(), st.charges.data_ptr(), st.bags.data_ptr(), st.act.data_ptr(),
+                                                 flat.data_ptr(), st.ws.data_ptr(), st.ws.numel(), ctypes.byref(o), stream))
+
+        def backward(stream):
+            _cabi.check(lib, lib.mgb_cov_backward(plan, B, st.pos.data_ptr(), st.charges.data_ptr(), st.bags.data_ptr(), st.act.data_ptr(),
+                                                  flat.data_ptr(), st.ws.data_ptr(), st.ws.numel(), st.cot[0].data_ptr(),
+                                                  st.cot[1].data_ptr(), st.cot[2].data_ptr(), st.grad.data_ptr(), 0, stream))
+
+        with rt.device_ctx():
+            st.g_forward = rt.capture(forward)
+            st.g_backward = rt.capture(backward)
+        slots.append(st)
+        return st
+
+    # ------------------------------------------------------------------------------------------------------
+    # fused PPO minibatch step: pack -> one H2D copy -> CUDA-graph replay of forward + PPO-clip loss, then of the backward
+    # ------------------------------------------------------------------------------------------------------
     def fused_ppo_loss(self, observations: List, actions, old_logp, adv, ret, clip_ratio: float, vf_coef: float,
                        entropy_coef: float):
         """The arithmetic of ppo.compute_loss (ppo.py:18-63) on this agent, as one pinned staging copy and two CUDA-graph
@@ -415,70 +565,81 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         Consecutive calls alternate between two pipeline slots (own stream, staging buffers, workspace, graphs): within a PPO
         epoch the minibatches are independent — the parameters only move at optimizer.step() (ppo.py:122-146) — so the forward
         of minibatch i+1 runs beside the backward of minibatch i.  The slot's stream waits for the caller's stream only when the
-        parameters changed since the last fused call (version counter of the flat buffer; `fused_sync_params = True` forces the
-        wait every time, for code that edits parameters through `.data`); the caller's stream waits for the accumulated
-        gradient in loss.backward()."""
-        B = len(observations)
+        parameters changed since the last fused call (in-place version counters; `fused_sync_params = True` forces the wait
+        every time, for code that edits parameters through `.data`); the caller's stream waits for the accumulated gradient in
+        loss.backward().
+
+        Data-parallel (parallel.shard_agent): every rank is handed the SAME minibatch and evaluates its contiguous shard of
+        it; the loss terms are sums over the shard divided by the global minibatch size, and one all-reduce of the 8-double
+        info block makes loss / approx_kl / clip_fraction the global values on every rank, so that every rank takes the same
+        early-stop branch (ppo.py:138-140).  The shard's gradient is accumulated locally and reduced once per optimizer step
+        (FlatParamMixin.sync_grads)."""
+        n = len(observations)
+        rt = self._rt
         if not self._params_aliased():
             self._realias()
+        actions_np = _as_numpy_actions(actions, n, 6)
+        self._check_actions(actions_np)
+        lo, hi = self._shard(n)
+        B = hi - lo
+        sharded = self._is_sharded()
         if self._fused_streams is None:
-            self._fused_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            self._fused_streams = [rt.new_stream(), rt.new_stream()]
         slot = self._fused_turn
-        # two slots double the workspace (cat / dcat dominate: ~10 GB at C5 with 1024 canvases): keep one when that is too much
-        if 2 * _lib.load().mgb_cov_workspace_bytes(self._plan, B) > 0.25 * torch.cuda.get_device_properties(self.device).total_memory:
+        # two slots double the workspace: keep one when that is too much for the device
+        if 2 * rt.lib().mgb_cov_workspace_bytes(self._plan, B) > 0.25 * rt.total_memory():
             slot = 0
         else:
             self._fused_turn ^= 1
-        st = self._fused_state(B, clip_ratio, vf_coef, entropy_coef, slot)
+        st = self._fused_state(B, n, clip_ratio, vf_coef, entropy_coef, slot)
         st.generation += 1
-        actions_np = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
-        assert actions_np.shape == (B, 6)
-        pack_observations(observations, self.zs, self.canvas_size, cfg=self._cfg, out=(st.h_pos, st.h_charges, st.h_bags))
-        st.h_act[...] = actions_np
-        st.h_old[...] = old_logp
-        st.h_adv[...] = adv
-        st.h_ret[...] = ret
-        with torch.cuda.device(self.device):
-            current = torch.cuda.current_stream(self.device)
-            version = (self._flat._version, self._flat.data_ptr())
+        pack_observations(observations[lo:hi] if sharded else observations, self.zs, self.canvas_size, cfg=self._cfg,
+                          out=(st.h_pos, st.h_charges, st.h_bags), lib=rt.lib())
+        st.h_act[...] = actions_np[lo:hi]
+        st.h_old[...] = old_logp[lo:hi]
+        st.h_adv[...] = adv[lo:hi]
+        st.h_ret[...] = ret[lo:hi]
+        with rt.device_ctx():
+            current = rt.current_stream()
+            version = self._param_version()
             if self.fused_sync_params or version != self._fused_param_version:
                 for stream in self._fused_streams:   # parameter updates enqueued on the caller's stream come first
                     stream.wait_stream(current)
                 self._fused_param_version = version
-            with torch.cuda.stream(st.stream):
+            with rt.stream_ctx(st.stream):
                 st.dev.copy_(st.host, non_blocking=True)
                 st.g_forward.replay()
+                if sharded:
+                    torch.distributed.all_reduce(st.info, op=torch.distributed.ReduceOp.SUM)
                 st.info_host.copy_(st.info, non_blocking=True)
                 loss_dev = st.info[0].clone()
                 st.event.record(st.stream)
                 st.g_backward.replay()
-                if self._is_sharded():
-                    # the path's one exchange step; every rank's loss is the mean over ITS slice, like the op-by-op path
-                    torch.distributed.all_reduce(st.grad, op=torch.distributed.ReduceOp.SUM)
             st.event.synchronize()
             current.wait_event(st.event)   # loss_dev is consumed on the caller's stream
+            if rt.is_cuda:
+                loss_dev.record_stream(current)
         vals = st.info_host.numpy()
         info = dict(policy_loss=float(vals[1]), entropy_loss=float(vals[2]), vf_loss=float(vals[3]), total_loss=float(vals[0]),
                     approx_kl=float(vals[4]), clip_fraction=float(vals[5]))
         loss = _FusedPPOLoss.apply(self._param_list[-1], self, st, loss_dev)
         return loss, info
 
-    def _fused_backward(self, st: _FusedState, g: torch.Tensor):
-        lib = _lib.load()
-        with torch.cuda.device(self.device):
-            current = torch.cuda.current_stream(self.device)
-            keep = self._attach_grads()                      # may zero the flat gradient on the caller's stream
+    def _fused_backward(self, st: _StepState, g: torch.Tensor):
+        rt = self._rt
+        with rt.device_ctx():
+            current = rt.current_stream()
             scale = g.detach()
-            if scale.dtype not in (torch.float32, torch.float64) or not scale.is_cuda:
+            if scale.dtype not in (torch.float32, torch.float64) or scale.device != self._flat.device:
                 scale = scale.to(device=self.device, dtype=torch.float32)
+            keep = self._attach_grads()                      # may zero the flat gradient on the caller's stream ...
             st.stream.wait_stream(current)                   # ... and the cotangent is produced there
             if self._fused_acc_event is not None:
                 st.stream.wait_event(self._fused_acc_event)  # accumulations of the two slots into .grad stay ordered
             # .grad (+)= cotangent * scratch gradient: one kernel on the slot's stream, behind the backward graph
-            _cabi.check(lib, lib.mgb_scale_accumulate(self._flat_grad.data_ptr(), st.grad.data_ptr(), scale.data_ptr(),
-                                                      1 if scale.dtype == torch.float64 else 0, self._flat_grad.numel(),
-                                                      1 if keep else 0, st.stream.cuda_stream))
-            scale.record_stream(st.stream)
+            self._accumulate_scratch(st.grad, scale, st.stream, keep=keep)
+            if rt.is_cuda:
+                scale.record_stream(st.stream)
             st.acc_event.record(st.stream)
             self._fused_acc_event = st.acc_event
             current.wait_event(st.acc_event)                 # whoever reads .grad next on the caller's stream sees it complete
@@ -509,12 +670,12 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         offs = [0]
         for sz in sizes:
             offs.append((offs[-1] + sz + 255) // 256 * 256)
-        stage = torch.empty(max(offs[-1], 256), dtype=torch.uint8, pin_memory=True)
+        stage = self._rt.pinned(max(offs[-1], 256))
         host = stage.numpy()
         pos = host[offs[0]:offs[0] + sizes[0]].view(np.float32).reshape(B, N, 3)
         charges = host[offs[1]:offs[1] + sizes[1]].view(np.int32).reshape(B, N)
         bags = host[offs[2]:offs[2] + sizes[2]].view(np.float32).reshape(B, Z)
-        pack_observations(observations, self.zs, N, cfg=self._cfg, out=(pos, charges, bags))
+        pack_observations(observations, self.zs, N, cfg=self._cfg, out=(pos, charges, bags), lib=self._rt.lib())
         if actions is not None:
             host[offs[3]:offs[3] + sizes[3]].view(np.float32).reshape(B, 6)[...] = actions
         dev = stage.to(self.device, non_blocking=True)
@@ -526,13 +687,29 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         return data
 
     def step(self, observations: List, actions: Optional[np.ndarray] = None) -> dict:
+        """agent.py:209-334.  Data-parallel agents evaluate their shard of the minibatch and all-gather logp / ent / v (the
+        gather routes the cotangents back to the owning rank), so callers see the global vectors; `dists` then describes the
+        local shard only."""
         response: Dict[str, Any] = {}
         if actions is not None:
-            actions_np = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
-            assert actions_np.shape == (len(observations), 6)
-            data = self.parse_observations(observations, actions_np)
-            pos, charges, bags, act = data['positions'], data['charges'], data['bags'], data['actions']
-            outs = self._evaluate(pos, charges, bags, act)
+            n = len(observations)
+            actions_np = _as_numpy_actions(actions, n, 6)
+            self._check_actions(actions_np)
+            lo, hi = self._shard(n)
+            sharded = self._is_sharded()
+            if sharded:
+                observations, actions_np = observations[lo:hi], actions_np[lo:hi]
+            st = self._eval_slot(hi - lo) if (self.graph_evaluate and torch.is_grad_enabled()) else None
+            if st is not None:
+                outs, act, charges = self._evaluate_slot(st, observations, actions_np)
+            else:
+                data = self.parse_observations(observations, actions_np)
+                pos, charges, bags, act = data['positions'], data['charges'], data['bags'], data['actions']
+                outs = self._evaluate(pos, charges, bags, act)
+            if sharded:
+                from molgym_b200.parallel import gather_shards
+                outs = tuple(gather_shards(o, n) for o in outs[:3]) + tuple(outs[3:])
+                act = torch.as_tensor(_as_numpy_actions(actions, n, 6), device=self.device)
         else:
             data = self.parse_observations(observations)
             pos, charges, bags = data['positions'], data['charges'], data['bags']
@@ -550,3 +727,19 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             return _CovEvaluate.apply(self._param_list[-1], self, pos, charges, bags, act)
         outs, _ = self._forward_raw(pos, charges, bags, act, want_extras=True)
         return outs
+
+    def _evaluate_slot(self, st: _StepState, observations: List, actions_np: np.ndarray):
+        """Evaluate-mode step on a persistent slot: pack into the pinned staging buffer, one H2D copy, graph replay."""
+        if not self._params_aliased():
+            self._realias()
+        st.generation += 1
+        st.copied.synchronize()   # the previous staging copy of this slot has left the pinned buffer
+        pack_observations(observations, self.zs, self.canvas_size, cfg=self._cfg, out=(st.h_pos, st.h_charges, st.h_bags),
+                          lib=self._rt.lib())
+        st.h_act[...] = actions_np
+        with self._rt.device_ctx():
+            st.dev.copy_(st.host, non_blocking=True)
+            st.copied.record(self._rt.current_stream())
+            outs = _CovEvaluateSlot.apply(self._param_list[-1], self, st)
+        # the staging buffers are rewritten by the next step on this slot: hand out copies of the small inputs the response keeps
+        return outs, st.act.clone(), st.charges.clone()

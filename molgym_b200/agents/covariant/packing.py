@@ -53,10 +53,10 @@ def flatten_observations(observations: Sequence, canvas_size: int, num_species: 
     return labels, xyz, bags.reshape(B, num_species)
 
 
-def pack_observations(observations: Sequence, zs: Sequence[int], canvas_size: int, cfg=None, out=None):
+def pack_observations(observations: Sequence, zs: Sequence[int], canvas_size: int, cfg=None, out=None, lib=None):
     """-> positions[B,N,3] f32, charges[B,N] i32 (null-symbol items dropped, real atoms compacted to the front, zero
     padding), bags[B,Z] f32.  `out` = (positions, charges, bags) arrays to fill (e.g. views of a pinned staging buffer)."""
-    lib = _lib.load()
+    lib = lib if lib is not None else _lib.load()
     labels, xyz, bags = flatten_observations(observations, canvas_size, len(zs))
     B = len(observations)
     if out is not None:

@@ -14,8 +14,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from molgym_b200 import _cabi, _lib
+from molgym_b200 import _cabi
 from molgym_b200.agents._flat import FlatParamMixin
+from molgym_b200.agents._runtime import CudaRuntime
 from molgym_b200.agents.base import AbstractActorCritic
 from molgym_b200.agents.internal import zmat
 
@@ -45,9 +46,12 @@ class _IntEvaluate(torch.autograd.Function):
 
 
 class SchNetAC(FlatParamMixin, AbstractActorCritic):
+    _runtime_cls = CudaRuntime   # the test-suite's emulator-backed subclass substitutes a host runtime
+
     def __init__(self, observation_space, action_space, min_max_distance: Tuple[float, float], network_width: int, device=None):
         super().__init__(observation_space=observation_space, action_space=action_space)
-        self.device = _lib.require_cuda_device(device)
+        self._rt = self._runtime_cls(device)
+        self.device = self._rt.device
         self.zs = list(self.observation_space.zs)
         self.num_atoms = self.observation_space.canvas_space.size
         self.num_zs = len(self.zs)
@@ -63,10 +67,10 @@ class SchNetAC(FlatParamMixin, AbstractActorCritic):
 
     # ------------------------------------------------------------------------------------------------------
     def _init_native(self):
-        lib = _lib.load()
+        lib = self._rt.lib()
         self._cfg = _cabi.make_int_config(self.zs, self.num_atoms, (self.min_distance, self.max_distance), self.network_width)
         plan = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
+        with self._rt.device_ctx():
             _cabi.check(lib, lib.mgb_int_plan_create(ctypes.byref(self._cfg), ctypes.byref(plan)))
         self._plan = plan
         n = lib.mgb_int_param_count(plan)
@@ -132,25 +136,30 @@ class SchNetAC(FlatParamMixin, AbstractActorCritic):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ('_plan', '_cfg', '_flat', '_flat_grad', '_grad_scratch', '_views', '_grad_views', '_param_list'):
+        for k in ('_rt', '_plan', '_cfg', '_flat', '_flat_grad', '_grad_local', '_grad_pending', '_views', '_grad_views', '_param_list'):
             state.pop(k, None)
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
-        self.device = _lib.require_cuda_device(self.device)
+        where = next(iter(torch.nn.Module.parameters(self))).device   # torch.load(map_location=...) moved them
+        try:
+            self._rt = self._runtime_cls(where)
+        except Exception:
+            self._rt = self._runtime_cls(None)
+        self.device = self._rt.device
         self._init_native()
         self._rebuild_flat_after_unpickle()
 
     def __del__(self):
         try:
-            _lib.load().mgb_int_plan_destroy(self._plan)
+            self._rt.lib().mgb_int_plan_destroy(self._plan)
         except Exception:
             pass
 
     # ------------------------------------------------------------------------------------------------------
     def _forward_raw(self, numbers, positions, bags, actions):
-        lib = _lib.load()
+        lib = self._rt.lib()
         if not self._params_aliased():
             self._realias()
         B, dev = numbers.shape[0], self.device
@@ -162,27 +171,36 @@ class SchNetAC(FlatParamMixin, AbstractActorCritic):
                              focus_probs=fprobs.data_ptr(), element_probs=eprobs.data_ptr(), means=means.data_ptr(),
                              kappa_logits=klog.data_ptr())
         ws = torch.empty(lib.mgb_int_workspace_bytes(self._plan, B), dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        stream = self._rt.stream_ptr()
+        with self._rt.device_ctx():
             _cabi.check(lib, lib.mgb_int_forward(self._plan, B, numbers.data_ptr(), positions.data_ptr(), bags.data_ptr(),
                                                  actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(o),
                                                  stream))
         return (logp, ent, v, terms, fprobs, eprobs, means, klog), ws
 
     def _backward_raw(self, numbers, positions, bags, actions, ws, g_logp, g_ent, g_v):
-        lib = _lib.load()
-        dev, B = self.device, numbers.shape[0]
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib = self._rt.lib()
+        B = numbers.shape[0]
+        stream = self._rt.stream_ptr()
         keep = self._attach_grads()
         target, accumulate = self._grad_target(keep)
-        with torch.cuda.device(dev):
+        with self._rt.device_ctx():
             _cabi.check(lib, lib.mgb_int_backward(self._plan, B, numbers.data_ptr(), positions.data_ptr(), bags.data_ptr(),
                                                   actions.data_ptr(), self._flat.data_ptr(), ws.data_ptr(), ws.numel(),
                                                   g_logp.data_ptr(), g_ent.data_ptr(), g_v.data_ptr(), target.data_ptr(), accumulate,
                                                   stream))
-            self._finish_grads(keep)
+
+    def _check_actions(self, actions_np: np.ndarray):
+        """focus indexes the canvas, element the species list (zmat.build_molecules, the head kernels); the reference raises
+        from to_one_hot / zmat for indices outside the range (modules.py:8-23, zmat.py:106-107)."""
+        if actions_np.shape[0] == 0:
+            return
+        focus, element = np.rint(actions_np[:, 1]), np.rint(actions_np[:, 2])
+        if not (np.all((focus >= 0) & (focus < self.num_atoms)) and np.all((element >= 0) & (element < self.num_zs))):
+            raise RuntimeError(f'action index out of range: focus must be in [0, {self.num_atoms}), element in [0, {self.num_zs})')
 
     def _device_inputs(self, observations, actions_np):
+        self._check_actions(actions_np)
         numbers, positions, bags = zmat.build_molecules(observations, actions_np, self.zs, self.num_atoms)
         dev = self.device
         return (torch.from_numpy(numbers).to(dev), torch.from_numpy(positions).to(dev), torch.from_numpy(bags).to(dev),

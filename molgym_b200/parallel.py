@@ -1,13 +1,14 @@
-"""Data-parallel sharding of the PPO minibatch: one process per GPU, canvases are independent
-through forward and backward, the only exchange is one sum-all-reduce of the flat parameter gradient (NCCL over
-NVLink) issued by CovariantAC's backward when `agent.data_parallel` is set.
+"""Data-parallel sharding of the PPO minibatch: one process per GPU, every rank runs the same
+(unchanged) ppo.train loop on the same rollout buffer, and a data-parallel agent (`shard_agent`) evaluates only its
+contiguous shard of each minibatch:
 
-Two ways to use it, both keeping the reference's ppo.py arithmetic:
-  * `shard_agent(agent)` + every rank calls compute_loss on ITS OWN slice and divides the loss by the world size
-    (each rank's `mean()` is over its slice; with equal slices the summed gradients equal the global-mean gradient);
-  * `global_step(agent, observations, actions)`: every rank holds the whole minibatch, evaluates only its slice and
-    all-gathers logp / ent / v, so the loss, approx_kl and the early-stop branch (ppo.py:138-140) are identical on
-    every rank."""
+  * forward / backward: canvases are independent, no data-path collective;
+  * loss: each rank's PPO terms are sums over its shard divided by the GLOBAL minibatch size; one all-reduce of the 8-double
+    info block (fused step) or an autograd-aware all-gather of logp / ent / v (evaluate-mode step(), 12 bytes per canvas)
+    gives every rank the global loss, approx_kl and clip_fraction, so all ranks take the same early-stop branch
+    (molgym/ppo.py:138-140);
+  * gradient: the shard's gradient accumulates locally over the minibatches of an epoch and is summed over ranks ONCE per
+    optimizer step (agents/_flat.py::sync_grads, NCCL over NVLink) — the path's one exchange step."""
 from typing import List, Tuple
 
 import torch
@@ -61,7 +62,10 @@ def gather_shards(local: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def global_step(agent, observations: List, actions) -> dict:
-    """step() on the whole minibatch with the work sharded over ranks; returns global logp / ent / v."""
+    """step() on the whole minibatch with the work sharded over ranks; returns global logp / ent / v.  (A data-parallel
+    agent's own step() does exactly this; kept for callers that shard an agent they did not mark data-parallel.)"""
+    if getattr(agent, 'data_parallel', False):
+        return agent.step(observations, actions)
     n = len(observations)
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0

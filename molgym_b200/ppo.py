@@ -23,7 +23,9 @@ def compute_loss(ac, data: dict, clip_ratio: float, vf_coef: float, entropy_coef
     arithmetic in float64 on the device (k_ppo_loss, checked against this function by the tests) and the backward — as CUDA-graph
     replays when the buffers have the dtypes ppo.train hands over (buffer.py:106-116); set `ac.fused_ppo = False` for the
     op-by-op path below."""
-    if (getattr(ac, 'fused_ppo', False) and device is None and torch.is_grad_enabled() and isinstance(data['adv'], np.ndarray)
+    same_device = device is None or torch.device(device) == getattr(ac, 'device', None) or \
+        (torch.device(device).type == 'cuda' and torch.device(device).index is None and getattr(ac, 'device', torch.device('cpu')).type == 'cuda')
+    if (getattr(ac, 'fused_ppo', False) and same_device and torch.is_grad_enabled() and isinstance(data['adv'], np.ndarray)
             and data['adv'].dtype == np.float64 and isinstance(data['ret'], np.ndarray) and data['ret'].dtype == np.float64
             and isinstance(data['logp'], np.ndarray) and data['logp'].dtype == np.float32 and len(data['obs']) > 0):
         return ac.fused_ppo_loss(data['obs'], data['act'], data['logp'], data['adv'], data['ret'], clip_ratio, vf_coef, entropy_coef)

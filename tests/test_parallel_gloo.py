@@ -40,3 +40,33 @@ def test_gather_shards_gloo_world2_matches_single_process():
         assert abs(l - loss.item()) < 1e-7
         np.testing.assert_allclose(g, theta.grad.numpy(), rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(f, full.detach().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_sharded_agent_world2_matches_single_process():
+    """The product's CovariantAC (on the kernel emulator) sharded over two gloo ranks: fused step and evaluate-mode step()
+    return the GLOBAL loss / info on both ranks (bit-identical, so every rank takes the same early-stop branch of
+    molgym/ppo.py:138-140), and after the deferred all-reduce every rank holds the single-process gradient."""
+    from tests.cusim import emu_agent
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(emu_agent.sharded_worker, args=(2, port, out), nprocs=2, join=True)
+    cfg, agent, data = emu_agent.make_emu_case()
+    for fused in (True, False):
+        ref_infos, ref_grads = emu_agent.run_ppo_epoch(agent, data, fused)
+        gnorm = float(ref_grads.norm())
+        for (l0, i0), (la, ia), (lb, ib) in zip(ref_infos, out[0][fused][0], out[1][fused][0]):
+            assert la == lb and ia == ib                       # identical on both ranks, bit for bit
+            assert abs(la - l0) <= 1e-6 * max(1.0, abs(l0))
+            for key in i0:
+                assert abs(ia[key] - i0[key]) <= 1e-6 * max(1.0, abs(i0[key])), key
+        for rank in (0, 1):
+            err = float(np.linalg.norm(out[rank][fused][1] - ref_grads.numpy()))
+            assert err <= 1e-5 * gnorm, (fused, rank, err, gnorm)
+    for rank in (0, 1):
+        pending_before, pending_after, _ = out[rank]['hook']
+        assert pending_before and not pending_after
+    np.testing.assert_array_equal(out[0]['hook'][2], out[1]['hook'][2])   # the replicas stayed in lockstep
