@@ -1,16 +1,24 @@
 """bench.py — PPO-minibatch forward+backward throughput of the covariant agent (canvases / s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
-    (MOLGYM_B200_SLOTS=n: number of independent slots of the `two_slot` figure, default 2; MOLGYM_B200_NO_GRAPH=1: eager launches only)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference] [--no-per-config]
+    (MOLGYM_B200_NO_GRAPH=1: eager launches only)
 
-A "step" is one pass of the hot path over one minibatch of synthetic canvases: forward (Cormorant body + heads) ->
-PPO-clip loss -> backward -> (N > 1) gradient all-reduce.  Weak scaling: every rank processes its own minibatch of the
-workload's size; `value` = canvases processed by all ranks / max-over-ranks device time.
+A "step" is one pass of the hot path over one PPO minibatch of synthetic canvases: forward (Cormorant body + heads) ->
+PPO-clip loss -> backward -> (N > 1) the exchange (all-reduce of the 8-double loss info and of the flat gradient).
 
-  value : inputs resident in HBM, direct C-ABI calls (mgb_cov_forward, mgb_ppo_loss, mgb_cov_backward), CUDA events.
-  e2e   : the reference-facing call — CovariantAC.step(list of observation tuples, actions) driven by the restated
-          ppo.compute_loss, loss.backward(), and a device->host read of the loss info — host packing and H2D copies inside.
-  roofline / cpu_baseline : see DESIGN.md.
+Multi-GPU: the minibatch is SHARDED — every rank builds the same global minibatch and the data-parallel agent evaluates its
+contiguous shard (molgym_b200/parallel.py).  The headline workload (C2, which BASELINE.json quotes on one GPU) is scaled weakly:
+global minibatch = 140 x N, 140 canvases per rank.  The configurations BASELINE.json names for 8 GPUs (C3 1024, C4 4096,
+C5 8192 canvases) are reported in `per_config` with their FIXED global minibatch sharded over the N ranks (strong scaling;
+at N = 1 C5 runs its one-GPU shard of 1024 canvases).
+
+  value            : inputs resident in HBM, direct C-ABI calls (mgb_cov_forward, mgb_ppo_loss, mgb_cov_backward) replayed as one
+                     CUDA graph, CUDA events, L2 flushed between timed steps, max over ranks.
+  e2e              : ppo.train's inner loop (ppo.py:117-146) through the public API on HOST observation tuples: per epoch
+                     zero_grad, EPOCH_LEN x (compute_loss -> fused CUDA-graph step, loss.backward()), gradient norm, clipping and
+                     optimizer.step(); wall clock around the whole loop, L2 flush counted inside.
+  e2e_unchanged_ppo: the same loop with the arithmetic of the reference's own compute_loss (agent.step + torch ops + autograd).
+  roofline / cpu_baseline / per_config : see DESIGN.md.
 """
 import argparse
 import ctypes
@@ -28,7 +36,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CLIP, VF, ENT = 0.2, 0.5, 0.01   # arg_parser.py:84-86
+LR, GRAD_CLIP = 3e-4, 0.5         # arg_parser.py:80,88
 METRIC = 'ppo_minibatch_fwd_bwd_canvases_per_sec'
+EPOCH_LEN = 4                     # minibatches per optimizer step in the e2e loop
+FFMA_PEAK_TFLOPS = 72.3           # measured on this pool's B200 (tools/ffma_peak.cu, profiles/r1_ffma_peak.txt); nominal 74.4
 
 
 def parse_args():
@@ -40,6 +51,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=None, help='override the minibatch size (per rank)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-per-config', action='store_true')
     ap.add_argument('--profile-kernel', default='k_atom_bwd')
     return ap.parse_args()
 
@@ -52,14 +64,15 @@ def workload(name, batch=None):
     return cfg
 
 
-def config_json(cfg, world):
-    return {'workload': f'{cfg.name}: canvas_size={cfg.canvas_size} zs={cfg.zs} mini_batch_size={cfg.mini_batch_size} per rank, '
-                        f'occupancies 0..K-1 uniform (synthetic PPO buffer)',
-            'global_batch': cfg.mini_batch_size * world, 'canvas_size': cfg.canvas_size,
+def config_json(cfg, world, global_batch, scaling):
+    return {'workload': f'{cfg.name}: canvas_size={cfg.canvas_size} zs={cfg.zs}, global minibatch {global_batch} sharded over {world} rank(s) '
+                        f'({global_batch // world} per rank, {scaling} scaling), occupancies 0..K-1 uniform (synthetic PPO buffer)',
+            'global_batch': global_batch, 'canvas_size': cfg.canvas_size,
             'hyper': {'network_width': cfg.network_width, 'maxl': cfg.maxl, 'num_cg_levels': cfg.num_cg_levels,
                       'num_channels_hidden': cfg.num_channels_hidden, 'num_channels_per_element': cfg.num_channels_per_element,
                       'num_gaussians': cfg.num_gaussians, 'beta': cfg.beta},
-            'parallelism': f'dp{world}', 'l2': 'flushed between timed steps (256 MiB write)'}
+            'parallelism': f'dp{world} (minibatch sharded inside the agent)',
+            'l2': 'flushed between timed steps (256 MiB write; inside the timed region for e2e)'}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -156,34 +169,247 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# algorithmic work model (DESIGN.md "Work model")
+# algorithmic work model of the dominant kernel (DESIGN.md "Work model")
 # ----------------------------------------------------------------------------------------------------------------
-def atom_bwd_work(cfg, n_atoms, cat_sizes):
-    """Algorithmic HBM bytes and FLOPs of ALL k_atom_bwd launches of one step (one per CG level; two half kernels per level
-    for small minibatches), from the kernel's own decomposition.  Per valid atom i of a canvas with n atoms,
-    level k with nlm2 input components (1 at level 0, else 25), C channels and a cat vector of totA_k complex entries:
-      bytes = totA_k*8 (dcat slice) + nlm2*C*8 (A_i) + n * [nlm2*C*8 (A_j) + 5*C*8 (E_ij) + 5*C*8 (dE_ij) + 2*nlm2*C*8 (dA_j RMW)]
-      flops = n * 2 * 25*nlm2 * C * 8 (row + column Kronecker passes, complex MAC = 8 flop)
-              + 3 * n_pairs(k) * 5 * C * 4 (padded Clebsch-Gordan scatter: row, column, square; real coefficient x complex)"""
+def cg_term_counts(lib):
+    """Non-zero Clebsch-Gordan coefficients of the products the atom level evaluates, for l <= 4: (edge x A_k with the ells of
+    A_k limited to nlin) and (A_k x A_k)."""
+    def count(n1, n2):
+        tot = 0
+        for l1 in range(n1):
+            for l2 in range(n2):
+                for l in range(abs(l1 - l2), min(l1 + l2, 4) + 1):
+                    for m1 in range(-l1, l1 + 1):
+                        for m2 in range(-l2, l2 + 1):
+                            if abs(m1 + m2) <= l and lib.mgb_clebsch_gordan(l1, m1, l2, m2, l, m1 + m2) != 0.0:
+                                tot += 1
+        return tot
+    return {1: (count(5, 1), count(1, 1)), 5: (count(5, 5), count(5, 5))}
+
+
+def atom_bwd_work(cfg, n_atoms, cat_sizes, terms):
+    """FLOPs and algorithmic HBM bytes of ALL k_atom_bwd launches of one step (one per CG level; two half kernels per level for
+    small minibatches).  Per valid atom i of a canvas with n atoms, level k with nlm2 input components (1 at level 0, else 25),
+    C channels, Cout output channels:
+      flops  = 2 * n * 25 * nlm2 * C * 8              row + column Kronecker passes (complex MAC = 8 flop)
+             + (2 * T_ag + 2 * T_sq) * C * 4          Clebsch-Gordan scatter with the REAL term counts (row, column: T_ag non-zero
+                                                      coefficients each; square: T_sq for each of its two factors), real x complex
+             + nlm2 * nlm2 * C * 8                    own-atom square products
+      bytes  = 25 * Cout * 8 (dA_{k+1}[i], read once) + nlm2 * C * 8 (A_k[i]) + nlm2 * C * 8 (dA_k[i] written once)
+             + n * (5 * C * 8 (E_ij read) + 5 * C * 8 (dE_ij written))
+               -- SURVEY.md 8d: each layer-boundary tensor once; the cat / dcat vectors, A_j re-reads and the dA_j read-modify-write
+               are on-chip / cache traffic of this implementation, not algorithmic bytes."""
     C, nl = cfg.num_channels_hidden, cfg.maxl + 1
+    cout_last = len(cfg.zs) * cfg.num_channels_per_element
     bytes_, flops = 0, 0
     for k in range(cfg.num_cg_levels):
         nlm2 = 1 if k == 0 else 25
-        tot_a = sum(cat_sizes[(k * nl + l) * 2 + 1] * (2 * l + 1) for l in range(nl))
+        t_ag, t_sq = terms[1 if k == 0 else 5]
+        cout = cout_last if k == cfg.num_cg_levels - 1 else C
         for n in n_atoms:
             n = int(n)
-            bytes_ += n * (tot_a * 8 + nlm2 * C * 8 + n * (nlm2 * C * 8 + 5 * C * 8 + 5 * C * 8 + 2 * nlm2 * C * 8))
-            flops += n * (n * 2 * 25 * nlm2 * C * 8 + 3 * 25 * nlm2 * 5 * C * 4)
+            flops += n * (2 * n * 25 * nlm2 * C * 8 + (2 * t_ag + 2 * t_sq) * C * 4 + nlm2 * nlm2 * C * 8)
+            bytes_ += n * (25 * cout * 8 + 2 * nlm2 * C * 8 + n * (2 * 5 * C * 8))
     return bytes_, flops
 
 
 # ----------------------------------------------------------------------------------------------------------------
+class Case:
+    """One workload on this rank: the agent, the global minibatch (identical on every rank) and this rank's device-resident shard."""
+
+    def __init__(self, cfg, global_batch, world, rank, dev, seed_shift=0):
+        import torch
+        from molgym_b200 import _cabi, _lib, parallel, synth
+        from molgym_b200.agents.covariant.agent import CovariantAC
+        from molgym_b200.spaces import ActionSpace, ObservationSpace
+        self.cfg, self.world, self.rank, self.dev, self.n_global = cfg, world, rank, dev, global_batch
+        self.lib = lib = _lib.load()
+        torch.manual_seed(0)
+        self.agent = agent = CovariantAC(ObservationSpace(cfg.canvas_size, cfg.zs), ActionSpace(cfg.zs), device=dev, **cfg.agent_kwargs())
+        obs, n_atoms = synth.make_observations(cfg, batch=global_batch, seed=cfg.seed + seed_shift)
+        act = synth.make_actions(cfg, obs, n_atoms, seed=cfg.seed + seed_shift)
+        lo, hi = parallel.shard_bounds(global_batch, rank, world)
+        self.lo, self.hi, self.B = lo, hi, hi - lo
+        # old log-probabilities: this agent's own log-probabilities of the stored actions + noise.  Each rank only ever reads its
+        # shard of the buffer, so it evaluates just that part.
+        with torch.no_grad():
+            logp0 = np.zeros(global_batch, dtype=np.float32)
+            for c0 in range(lo, hi, 1024):
+                c1 = min(hi, c0 + 1024)
+                logp0[c0:c1] = agent.step(obs[c0:c1], act[c0:c1])['logp'].cpu().numpy()
+            agent._ws_cache.clear()
+        if world > 1:
+            parallel.shard_agent(agent)
+        old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0, seed=cfg.seed + seed_shift)
+        self.data = dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret)
+        self.n_atoms_local = n_atoms[lo:hi]
+        B = self.B
+        parsed = agent.parse_observations(obs[lo:hi])
+        self.pos, self.charges, self.bags = parsed['positions'], parsed['charges'], parsed['bags']
+        self.act_d = torch.as_tensor(act[lo:hi], dtype=torch.float32, device=dev)
+        self.old_d = torch.as_tensor(old_logp[lo:hi], device=dev)
+        self.adv_d = torch.as_tensor(adv[lo:hi], device=dev)
+        self.ret_d = torch.as_tensor(ret[lo:hi], device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.out = torch.empty(6, B, **f32)
+        self.info = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.grad = torch.zeros_like(agent._flat)
+        self.ws_bytes = lib.mgb_cov_workspace_bytes(agent._plan, B)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.outs = _cabi.CovOutputs()
+        self.outs.logp, self.outs.ent, self.outs.v = self.out[0].data_ptr(), self.out[1].data_ptr(), self.out[2].data_ptr()
+        self.h2d_bytes = (self.pos.numel() + self.charges.numel() + self.bags.numel() + self.act_d.numel() + self.old_d.numel()) * 4 + \
+            (self.adv_d.numel() + self.ret_d.numel()) * 8
+        self.graph = None
+
+    def launch(self, stream):
+        from molgym_b200 import _cabi
+        lib, a, B, o = self.lib, self.agent, self.B, self.out
+        _cabi.check(lib, lib.mgb_cov_forward(a._plan, B, self.pos.data_ptr(), self.charges.data_ptr(), self.bags.data_ptr(),
+                                             self.act_d.data_ptr(), a._flat.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                             ctypes.byref(self.outs), stream))
+        _cabi.check(lib, lib.mgb_ppo_loss(B, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), self.old_d.data_ptr(), self.adv_d.data_ptr(),
+                                          self.ret_d.data_ptr(), CLIP, VF, ENT, 1.0 / self.n_global, self.info.data_ptr(), o[3].data_ptr(),
+                                          o[4].data_ptr(), o[5].data_ptr(), stream))
+        _cabi.check(lib, lib.mgb_cov_backward(a._plan, B, self.pos.data_ptr(), self.charges.data_ptr(), self.bags.data_ptr(),
+                                              self.act_d.data_ptr(), a._flat.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                              o[3].data_ptr(), o[4].data_ptr(), o[5].data_ptr(), self.grad.data_ptr(), 0, stream))
+
+    def exchange(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.info, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    def eager_step(self):
+        import torch
+        self.launch(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.exchange()
+
+    def capture(self):
+        import torch
+        if os.environ.get('MOLGYM_B200_NO_GRAPH'):
+            return None
+        try:
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(self.dev, priority=-5)   # main-chain kernels outrank the weight-gradient side streams
+            cap.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(g, stream=cap):
+                    self.launch(torch.cuda.current_stream(self.dev).cuda_stream)
+            torch.cuda.current_stream(self.dev).wait_stream(cap)
+            self.graph = g
+        except Exception as exc:   # pragma: no cover
+            sys.stderr.write(f'CUDA graph capture failed ({exc}); eager launches only\n')
+            self.graph = None
+        return self.graph
+
+    def graph_step(self):
+        self.graph.replay()
+        self.exchange()
+
+
+class Timer:
+    def __init__(self, dev, world):
+        import torch
+        self.dev, self.world = dev, world
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync(self):
+        import torch
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def events(self, fn, steps, warmup, sampler=None):
+        """Device time of `steps` calls of fn (CUDA events around each, L2 flushed between them), max over ranks."""
+        import torch
+        for _ in range(warmup):
+            fn()
+        self.sync()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        if sampler:
+            sampler.start()
+        for s in range(steps):
+            self.flush_buf.zero_()              # evict L2 between timed steps (outside the event pair)
+            starts[s].record()
+            fn()
+            stops[s].record()
+        self.sync()
+        clocks = sampler.stop() if sampler else None
+        total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+        return self.max_over_ranks(total_ms), clocks
+
+    def wall(self, fn, calls, warmup, flush=True):
+        """Wall clock of `calls` calls of fn with a device synchronisation (and a barrier) on both sides, max over ranks; the L2
+        flush between calls is inside the timed region."""
+        for _ in range(warmup):
+            fn()
+        self.sync()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            if flush:
+                self.flush_buf.zero_()
+            fn()
+        self.sync()
+        return self.max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+
+def e2e_epoch_fn(case, fused):
+    """One pass of ppo.train's loop body (ppo.py:117-146) over EPOCH_LEN minibatches, through the public API."""
+    import torch
+    from molgym_b200 import ppo
+    agent, data = case.agent, case.data
+    if not hasattr(case, 'optimizer'):
+        case.optimizer = torch.optim.Adam(agent.parameters(), lr=LR, amsgrad=False)   # tools/util.py:197-205
+    optimizer = case.optimizer
+
+    def epoch():
+        agent.fused_ppo = fused
+        optimizer.zero_grad()
+        infos = []
+        for _ in range(EPOCH_LEN):
+            loss, info = ppo.compute_loss(agent, data, CLIP, VF, ENT)
+            loss.backward()
+            infos.append(info)
+        params = list(agent.parameters())      # data-parallel: the one gradient all-reduce of the optimizer step happens here
+        norm = torch.norm(torch.stack([torch.norm(p.grad.detach(), 2) for p in params]), 2).item()   # compute_gradient_norm (util.py:61-69)
+        torch.nn.utils.clip_grad_norm_(params, max_norm=GRAD_CLIP)
+        optimizer.step()
+        optimizer.zero_grad()
+        return norm, infos
+    return epoch
+
+
+def measure_case(case, timer, steps, warmup, sampler=None):
+    """Device-resident ms per step of a case (graph replay when capture works, else eager launches)."""
+    for _ in range(3):
+        case.eager_step()
+    timer.sync()
+    mode = 'eager launches'
+    fn = case.eager_step
+    if case.capture() is not None:
+        fn, mode = case.graph_step, 'CUDA graph replay of the captured step'
+    total_ms, clocks = timer.events(fn, steps, max(3, warmup), sampler)
+    return total_ms / steps, mode, clocks
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from molgym_b200 import _cabi, _lib, parallel, ppo, synth
-    from molgym_b200.agents.covariant.agent import CovariantAC
-    from molgym_b200.spaces import ActionSpace, ObservationSpace
+    from molgym_b200 import _lib, synth
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -194,217 +420,102 @@ def run_ours(args):
     dev = torch.device('cuda', local_rank)
     lib = _lib.load()
     cfg = workload(args.workload, args.batch)
-    B = cfg.mini_batch_size
+    weak = cfg.name.startswith('C2') or args.batch is not None   # the headline workload keeps its per-rank minibatch
+    n_global = cfg.mini_batch_size * world if weak else cfg.mini_batch_size
+    scaling = 'weak' if weak else 'strong'
+    timer = Timer(dev, world)
+    case = Case(cfg, n_global, world, rank, dev)
+    B = case.B
 
-    torch.manual_seed(0)
-    agent = CovariantAC(ObservationSpace(cfg.canvas_size, cfg.zs), ActionSpace(cfg.zs), device=dev, **cfg.agent_kwargs())
-    if world > 1:
-        parallel.shard_agent(agent)
-    obs, n_atoms = synth.make_observations(cfg, batch=B, seed=cfg.seed + 17 * rank, start_index=rank)
-    act = synth.make_actions(cfg, obs, n_atoms, seed=cfg.seed + 17 * rank)
-    with torch.no_grad():
-        logp0 = agent.step(obs, act)['logp'].cpu().numpy()
-    old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0, seed=cfg.seed + 17 * rank)
-    data = dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret)
-
-    # ---- device-resident inputs for the `value` measurement
-    parsed = agent.parse_observations(obs)
-    pos, charges, bags = parsed['positions'], parsed['charges'], parsed['bags']
-    act_d = torch.as_tensor(act, dtype=torch.float32, device=dev)
-    old_d = torch.as_tensor(old_logp, device=dev)
-    adv_d = torch.as_tensor(adv, device=dev)
-    ret_d = torch.as_tensor(ret, device=dev)
-    f32 = dict(dtype=torch.float32, device=dev)
-    logp, ent, v = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
-    g_logp, g_ent, g_v = torch.empty(B, **f32), torch.empty(B, **f32), torch.empty(B, **f32)
-    info = torch.zeros(8, dtype=torch.float64, device=dev)
-    grad = torch.zeros_like(agent._flat)
-    ws = torch.empty(lib.mgb_cov_workspace_bytes(agent._plan, B), dtype=torch.uint8, device=dev)
-    outs = _cabi.CovOutputs()
-    outs.logp, outs.ent, outs.v = logp.data_ptr(), ent.data_ptr(), v.data_ptr()
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    inv_global = 1.0 / (B * world)
-
-    def device_step():
-        _cabi.check(lib, lib.mgb_cov_forward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(), act_d.data_ptr(),
-                                             agent._flat.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(outs), stream))
-        _cabi.check(lib, lib.mgb_ppo_loss(B, logp.data_ptr(), ent.data_ptr(), v.data_ptr(), old_d.data_ptr(), adv_d.data_ptr(),
-                                          ret_d.data_ptr(), CLIP, VF, ENT, inv_global, info.data_ptr(), g_logp.data_ptr(),
-                                          g_ent.data_ptr(), g_v.data_ptr(), stream))
-        _cabi.check(lib, lib.mgb_cov_backward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(), act_d.data_ptr(),
-                                              agent._flat.data_ptr(), ws.data_ptr(), ws.numel(), g_logp.data_ptr(),
-                                              g_ent.data_ptr(), g_v.data_ptr(), grad.data_ptr(), 0, stream))
-        if world > 1:
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-
-    # The device-resident step works on fixed buffers, so its launches + memsets can be captured once into a CUDA graph and
-    # replayed (the gradient all-reduce stays outside the graph).  MOLGYM_B200_NO_GRAPH=1 keeps only the eager launches.
-    def capture(ws_, outs_, logp_, ent_, v_, g3_, info_, grad_):
-        g = torch.cuda.CUDAGraph()
-        cap_stream = torch.cuda.Stream(dev, priority=-5)   # main-chain kernels outrank the weight-gradient side streams
-        cap_stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(cap_stream):
-            with torch.cuda.graph(g, stream=cap_stream):
-                s_ptr = torch.cuda.current_stream(dev).cuda_stream
-                _cabi.check(lib, lib.mgb_cov_forward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
-                                                     act_d.data_ptr(), agent._flat.data_ptr(), ws_.data_ptr(), ws_.numel(),
-                                                     ctypes.byref(outs_), s_ptr))
-                _cabi.check(lib, lib.mgb_ppo_loss(B, logp_.data_ptr(), ent_.data_ptr(), v_.data_ptr(), old_d.data_ptr(),
-                                                  adv_d.data_ptr(), ret_d.data_ptr(), CLIP, VF, ENT, inv_global, info_.data_ptr(),
-                                                  g3_[0].data_ptr(), g3_[1].data_ptr(), g3_[2].data_ptr(), s_ptr))
-                _cabi.check(lib, lib.mgb_cov_backward(agent._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(),
-                                                      act_d.data_ptr(), agent._flat.data_ptr(), ws_.data_ptr(), ws_.numel(),
-                                                      g3_[0].data_ptr(), g3_[1].data_ptr(), g3_[2].data_ptr(), grad_.data_ptr(), 0, s_ptr))
-        torch.cuda.current_stream(dev).wait_stream(cap_stream)
-        return g
-
-    graph, graph2, grad2, extra = None, None, None, []
-    if not os.environ.get('MOLGYM_B200_NO_GRAPH'):
-        try:
-            graph = capture(ws, outs, logp, ent, v, (g_logp, g_ent, g_v), info, grad)
-            # more independent slots (own workspace / outputs / gradient) for the multi-slot throughput figure below
-            extra = []
-            n_extra = int(os.environ.get('MOLGYM_B200_SLOTS', '2')) - 1
-            if ws.numel() * (n_extra + 3) > 0.5 * torch.cuda.get_device_properties(dev).total_memory:
-                n_extra = 0   # the agent's own fused slots need their workspaces too
-            for _ in range(n_extra):
-                ws2 = torch.empty_like(ws)
-                o2 = [torch.empty(B, **f32) for _ in range(6)]
-                outs2 = _cabi.CovOutputs()
-                outs2.logp, outs2.ent, outs2.v = o2[0].data_ptr(), o2[1].data_ptr(), o2[2].data_ptr()
-                info2, grad2 = torch.zeros_like(info), torch.zeros_like(grad)
-                graph2 = capture(ws2, outs2, o2[0], o2[1], o2[2], o2[3:], info2, grad2)
-                extra.append((graph2, grad2, (ws2, o2, outs2, info2)))
-        except Exception as exc:   # pragma: no cover
-            sys.stderr.write(f'CUDA graph capture failed ({exc}); eager launches only\n')
-            graph = graph2 = None
-
-    def graph_step():
-        graph.replay()
-        if world > 1:
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-
-    # ppo.train's inner loop (ppo.py:118-131): optimizer.zero_grad() once per epoch, then every minibatch of the epoch runs
-    # compute_loss + backward and the gradients accumulate; EPOCH_LEN minibatches per epoch here
-    EPOCH_LEN = 4
-    e2e_count = [0]
-
-    def e2e_step():
-        if e2e_count[0] % EPOCH_LEN == 0:
-            agent.zero_grad()
-        e2e_count[0] += 1
-        loss, info_d = ppo.compute_loss(agent, data, CLIP, VF, ENT)
-        (loss / world).backward()
-        return info_d
-
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        if sampler:
-            sampler.start()
-        wall0 = time.perf_counter()
-        for s in range(steps):
-            flush_buf.zero_()              # evict L2 between timed steps (outside the event pair)
-            starts[s].record()
-            fn()
-            stops[s].record()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        wall = time.perf_counter() - wall0
-        clocks = sampler.stop() if sampler else None
-        total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms, wall, clocks
-
-    # ---- value (device-resident): eager pass with the dominant kernel timed live, then the CUDA-graph replay of the same step
-    # every launch of the eager pass is bracketed by CUDA events on the stream it is launched on (mgb_profile_kernel('k_')):
-    # the dominant kernel's average launch duration and its share of the summed kernel time come from this timed region
+    # ---- eager pass with every launch bracketed by CUDA events on its own stream (mgb_profile_kernel('k_')): the dominant
+    # kernel's average launch duration and its share of the summed kernel time come from this timed region
     lib.mgb_profile_kernel(b'k_')
-    for _ in range(args.warmup):
-        device_step()
+    for _ in range(max(3, args.warmup)):
+        case.eager_step()
     torch.cuda.synchronize(dev)
-    report = ctypes.create_string_buffer(8 << 20)
+    report = ctypes.create_string_buffer(16 << 20)
     lib.mgb_profile_report(report, len(report))   # drop warm-up timings
+    prof_steps = min(args.steps, 50)
     launches_before = lib.mgb_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    eager_ms, wall, clocks = timed(device_step, args.steps, 0, sampler)
-    launches = lib.mgb_launch_count() - launches_before
+    eager_ms, _ = timer.events(case.eager_step, prof_steps, 0)
+    launches_per_step = (lib.mgb_launch_count() - launches_before) / prof_steps
     lib.mgb_profile_report(report, len(report))
     lib.mgb_profile_kernel(None)
-    k_total_ms, k_count, all_kernels_ms = 0.0, 0, 0.0
+    per_kernel = {}
     for line in report.value.decode().splitlines():
         name, ms = line.rsplit(' ', 1)
-        all_kernels_ms += float(ms)
-        if args.profile_kernel in name:
-            k_total_ms += float(ms)
-            k_count += 1
-    total_ms, mode = eager_ms, 'eager launches'
-    graph_ms = None
-    if graph is not None:
-        sampler2 = ClockSampler(local_rank) if rank == 0 else None
-        graph_ms, wall_g, clocks_g = timed(graph_step, args.steps, max(3, args.warmup), sampler2)
-        if graph_ms < eager_ms:
-            total_ms, wall, clocks, mode = graph_ms, wall_g, clocks_g, 'CUDA graph replay of the captured step'
-    ms_per_step = total_ms / args.steps
-    value = B * world / (ms_per_step * 1e-3)
+        short = name.split('<')[0].strip('( ')
+        t = per_kernel.setdefault(short, [0.0, 0])
+        t[0] += float(ms)
+        t[1] += 1
+    all_kernels_ms = sum(t[0] for t in per_kernel.values())
+    k_total_ms, k_count = per_kernel.get(args.profile_kernel, [0.0, 0])
 
-    # ---- the same device-resident step with TWO independent slots replayed alternately on two streams (what the e2e path
-    # does with consecutive minibatches of an epoch): whole region timed, no L2 flush inside it (reported beside `value`)
-    two_slot_ms = None
-    if extra:
-        slots = [(graph, grad, torch.cuda.Stream(dev))] + [(g_, gr_, torch.cuda.Stream(dev)) for g_, gr_, _ in extra]
+    # ---- value: CUDA-graph replay of the device-resident step
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_per_step, mode, clocks = measure_case(case, timer, args.steps, args.warmup, sampler)
+    if eager_ms / prof_steps < ms_per_step:
+        ms_per_step, mode = eager_ms / prof_steps, 'eager launches'
+    value = n_global / (ms_per_step * 1e-3)
 
-        def two_slot_region(n):
-            cur = torch.cuda.current_stream(dev)
-            for _, _, st_ in slots:
-                st_.wait_stream(cur)
-            for s_ in range(n):
-                g_, gr_, st_ = slots[s_ % len(slots)]
-                with torch.cuda.stream(st_):
-                    g_.replay()
-                    if world > 1:
-                        dist.all_reduce(gr_, op=dist.ReduceOp.SUM)
-            for _, _, st_ in slots:
-                cur.wait_stream(st_)
+    # ---- e2e through the public API: wall clock over whole epochs (>= 50 minibatches)
+    epochs = max(13, args.steps // EPOCH_LEN // 2)
+    e2e = {}
+    for key, fused in (('e2e', True), ('e2e_unchanged_ppo', False)):
+        fn = e2e_epoch_fn(case, fused)
+        ms = timer.wall(fn, epochs, 3, flush=True)
+        ms_nf = timer.wall(fn, epochs, 1, flush=False)
+        per_mb, per_mb_nf = ms / (epochs * EPOCH_LEN), ms_nf / (epochs * EPOCH_LEN)
+        e2e[key] = {'value': n_global / (per_mb * 1e-3), 'unit': 'canvases/s', 'ms_per_step': per_mb, 'steps': epochs * EPOCH_LEN,
+                    'no_flush_value': n_global / (per_mb_nf * 1e-3), 'no_flush_ms_per_step': per_mb_nf}
+    e2e['e2e'].update({
+        'h2d_bytes_per_step': int(case.h2d_bytes), 'd2h_bytes_per_step': 64,
+        'timing': 'time.perf_counter() around the loop, device synchronised (+ barrier) on both sides, max over ranks; the 256 MiB L2 '
+                  'flush between minibatches is INSIDE the timed region (no_flush_*: the same loop without it)',
+        'note': f'ppo.train loop body (ppo.py:117-146) on host observation tuples: per optimizer step zero_grad, {EPOCH_LEN} x '
+                '(compute_loss -> pack into pinned staging, one H2D copy, CUDA-graph replays of forward + PPO loss and of the backward, '
+                '64-byte D2H of the loss info; loss.backward()), gradient norm, clip_grad_norm_, Adam step; consecutive minibatches '
+                'alternate between two pipeline slots; data-parallel: one all-reduce of the info block per minibatch and ONE gradient '
+                'all-reduce per optimizer step'})
+    e2e['e2e_unchanged_ppo'].update({
+        'note': 'the same loop with the arithmetic of the reference\'s own compute_loss (ppo.py:18-63): agent.step(obs, act) (pack, H2D, '
+                'CUDA-graph replay on a persistent evaluation slot), the loss as torch ops, six .item() syncs, autograd backward '
+                '(graph replay + one accumulate kernel)'})
 
-        two_slot_region(max(4, args.warmup))
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t_host = time.perf_counter()
-        two_slot_region(args.steps)
-        t_host = time.perf_counter() - t_host   # host time spent enqueuing (cudaGraphLaunch): the floor of any replay-based loop
-        e1.record()
-        torch.cuda.synchronize(dev)
-        two_slot_ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([two_slot_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            two_slot_ms = float(t.item())
-
-    # ---- e2e through the public API (host observations, packing, H2D, torch loss, D2H of the loss info)
-    e2e_steps = max(10, args.steps // 4)
-    e2e_ms, e2e_wall, _ = timed(e2e_step, e2e_steps, max(3, args.warmup // 4))
-    # the e2e step has host work outside the event pairs' GPU time only if the GPU idles; events bracket the call, so
-    # host time shows up as the gap between start.record() and the first kernel: elapsed_time includes it.
-    e2e_value = B * world / (e2e_ms / e2e_steps * 1e-3)
-    h2d = pos.numel() * 4 + charges.numel() * 4 + bags.numel() * 4 + act_d.numel() * 4 + old_d.numel() * 4 + adv_d.numel() * 8 + ret_d.numel() * 8
-    d2h = 8 * 8   # the loss-info block (8 doubles) read back every step
+    # ---- the configurations BASELINE.json names for 8 GPUs: fixed global minibatch sharded over the ranks
+    per_config = {}
+    if not args.no_per_config and args.workload == 'C2' and args.batch is None:
+        del case.ws, case.graph
+        case.agent._fused_cache.clear()
+        case.agent._eval_cache.clear()
+        torch.cuda.empty_cache()
+        for name in ('C3', 'C4', 'C5'):
+            c = synth.CONFIGS[name]
+            g_batch = c.mini_batch_size
+            note = None
+            if name == 'C5' and world == 1:
+                g_batch, note = 1024, 'one GPU runs the 1024-canvas shard an 8-GPU job gives it (the 8192-canvas minibatch is an 8-GPU configuration)'
+            try:
+                pc = Case(c, g_batch, world, rank, dev)
+                n_steps = max(3, min(args.steps, 10 if name == 'C3' else 5))
+                ms, pc_mode, _ = measure_case(pc, timer, n_steps, 3)
+                entry = {'workload': c.name, 'global_batch': g_batch, 'per_rank_batch': pc.B, 'scaling': 'strong', 'n_gpus': world,
+                         'ms_per_step': ms, 'value': g_batch / (ms * 1e-3), 'unit': 'canvases/s', 'steps': n_steps, 'launch_mode': pc_mode,
+                         'workspace_gb': pc.ws_bytes / 1e9}
+                # e2e for the same config: one epoch loop, fused step
+                fn = e2e_epoch_fn(pc, True)
+                e_epochs = 2
+                e_ms = timer.wall(fn, e_epochs, 1, flush=False)
+                entry['e2e'] = {'value': g_batch / (e_ms / (e_epochs * EPOCH_LEN) * 1e-3), 'unit': 'canvases/s',
+                                'ms_per_step': e_ms / (e_epochs * EPOCH_LEN), 'steps': e_epochs * EPOCH_LEN,
+                                'note': 'working set larger than L2: no flush needed'}
+                if note:
+                    entry['note'] = note
+                per_config[name] = entry
+                del pc
+            except Exception as exc:   # pragma: no cover
+                per_config[name] = {'error': repr(exc)[:300]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -418,48 +529,42 @@ def run_ours(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     n_timed = max(k_count, 1)
     k_ms = k_total_ms / n_timed
-    launches_per_step_of_kernel = n_timed / args.steps
-    # per-launch algorithmic work: the step's total over the kernel's launches in one step (levels x half kernels)
-    step_bytes, step_flops = atom_bwd_work(cfg, n_atoms, agent._cat_sizes)
-    alg_bytes = step_bytes / max(launches_per_step_of_kernel, 1.0)
-    alg_flops = step_flops / max(launches_per_step_of_kernel, 1.0)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    k_launches_per_step = n_timed / prof_steps
+    step_bytes, step_flops = atom_bwd_work(cfg, case.n_atoms_local, case.agent._cat_sizes, cg_term_counts(lib))
+    alg_bytes = step_bytes / max(k_launches_per_step, 1.0)
+    alg_flops = step_flops / max(k_launches_per_step, 1.0)
+    tflops = alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    gbs = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.profile_kernel, {}).get(cfg.name)
     except Exception:
         pass
+    top = sorted(per_kernel.items(), key=lambda kv: -kv[1][0])[:8]
     line = {
         'metric': METRIC, 'value': value, 'unit': 'canvases/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': config_json(cfg, world), 'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'canvases/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
-                'note': 'ppo.train inner loop (ppo.py:118-131): zero_grad once per epoch of 4 minibatches, then compute_loss + '
-                        'loss.backward() per minibatch on host observation tuples; consecutive minibatches alternate between two '
-                        'pipeline slots, so the forward of step i+1 overlaps the backward of step i (the parameters are fixed within '
-                        'a PPO epoch); `value` is the strictly sequential device-resident step'},
-        'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': args.profile_kernel, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': achieved / hbm_peak, 'traffic': traffic,
-                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s',
-                     'kernel_ms_per_launch': k_ms, 'kernel_launches_per_step': launches_per_step_of_kernel,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': config_json(cfg, world, n_global, scaling), 'clocks': clocks,
+        'e2e': e2e['e2e'], 'e2e_unchanged_ppo': e2e['e2e_unchanged_ppo'],
+        'gpu_launches': int(round(launches_per_step * args.steps)), 'gpu_launches_per_step': launches_per_step,
+        'roofline': {'bound': 'fp32', 'kernel': args.profile_kernel, 'achieved': tflops, 'peak': FFMA_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                     'frac': tflops / FFMA_PEAK_TFLOPS, 'traffic': traffic,
+                     'peak_source': 'FFMA-chain microbenchmark on this pool\'s B200 (tools/ffma_peak.cu -> profiles/r1_ffma_peak.txt, 72.3 TFLOP/s '
+                                    'of nominal 74.4); MEASURED_PEAKS.json carries no fp32 figure (its bf16 tensor peak does not bound this kernel)',
+                     'kernel_ms_per_launch': k_ms, 'kernel_launches_per_step': k_launches_per_step,
                      'kernel_share_of_step': k_total_ms / all_kernels_ms if all_kernels_ms > 0 else None,
                      'timed_in': 'eager pass of the timed region: CUDA events around every launch on its own stream; the share is the '
                                  "kernel's part of the summed kernel time (side-stream kernels overlap the main stream)",
-                     'algorithmic_bytes_per_launch': alg_bytes, 'algorithmic_flops_per_launch': alg_flops,
-                     'fp32_achieved_tflops': alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
-                     'fp32_peak_tflops': 72.3, 'fp32_frac': (alg_flops / (k_ms * 1e-3) / 1e12 / 72.3) if k_ms > 0 else None,
-                     'note': 'the CG kernels are FP32-FMA bound (arithmetic intensity >> ridge 11 flop/B): the binding roof is the '
-                             'measured FFMA peak (profiles/r1_ffma_peak.txt), reported beside the HBM figure BASELINE.json asks for; '
-                             'see DESIGN.md section 3'},
-        'wall_ms_per_step': wall / args.steps * 1e3, 'launch_mode': mode, 'eager_ms_per_step': eager_ms / args.steps,
-        'graph_ms_per_step': graph_ms / args.steps if graph_ms is not None else None,
-        'two_slot': None if two_slot_ms is None else {
-            'ms_per_step': two_slot_ms / args.steps, 'value': B * world / (two_slot_ms / args.steps * 1e-3), 'unit': 'canvases/s',
-            'host_enqueue_ms_per_step': t_host / args.steps * 1e3,
-            'note': 'device-resident steps of two independent slots replayed alternately on two streams (forward of one beside the '
-                    'backward of the other), whole region timed without L2 flushes; `value` above is the strictly sequential step'},
+                     'algorithmic_flops_per_launch': alg_flops, 'algorithmic_bytes_per_launch': alg_bytes,
+                     'hbm': {'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                             'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s',
+                             'traffic_over_algorithmic': (traffic / alg_bytes) if (traffic and alg_bytes) else None},
+                     'note': 'SURVEY.md 8d: the Clebsch-Gordan atom kernels are FP32-FMA bound (arithmetic intensity >> ridge 11 flop/B); FLOPs '
+                             'count the real (non-zero) Clebsch-Gordan terms, bytes count each layer-boundary tensor once (DESIGN.md section 3)'},
+        'top_kernels': [{'kernel': k, 'share': v[0] / all_kernels_ms, 'ms_per_step': v[0] / prof_steps, 'launches_per_step': v[1] / prof_steps}
+                        for k, v in top],
+        'launch_mode': mode, 'eager_ms_per_step': eager_ms / prof_steps,
+        'per_config': per_config,
     }
     if not args.no_cpu_baseline and world == 1:
         cpu = run_cpu(cfg, steps=5, warmup=1, budget_s=20.0)
@@ -477,12 +582,87 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = workload(args.workload, args.batch)
+    weak = cfg.name.startswith('C2') or args.batch is not None
+    n_global = cfg.mini_batch_size * world if weak else cfg.mini_batch_size
     cpu = run_cpu(cfg, steps=args.steps, warmup=args.warmup, budget_s=60.0)
     line = {'impl': 'reference', 'metric': METRIC, 'value': cpu['value'], 'unit': 'canvases/s', 'n_gpus': world, 'steps': cpu['steps'],
-            'warmup': cpu['warmup'], 'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': config_json(cfg, world),
+            'warmup': cpu['warmup'], 'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak' if weak else 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config_json(cfg, world, n_global, 'weak' if weak else 'strong'),
             'cpu_baseline': {'value': cpu['value'], 'unit': 'canvases/s', 'cores': cpu['cores'], 'kind': 'port', 'sample': cpu['sample']},
             'e2e': {'value': cpu['value'], 'unit': 'canvases/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_internal(args):
+    """--workload C1: the internal-coordinate (SchNet cfconv) agent, one GPU; same JSON shape, roofline for k_sch_bwd."""
+    import torch
+    from molgym_b200 import _lib, ppo, synth
+    from molgym_b200.agents.internal.agent import SchNetAC
+    from molgym_b200.spaces import ActionSpace, ObservationSpace
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    cfg = workload('C1', args.batch)
+    B = cfg.mini_batch_size
+    torch.manual_seed(0)
+    agent = SchNetAC(ObservationSpace(cfg.canvas_size, cfg.zs), ActionSpace(cfg.zs), device=dev, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=B)
+    act = synth.make_actions(cfg, obs, n)
+    with torch.no_grad():
+        logp0 = agent.step(obs, act)['logp'].cpu().numpy()
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0)
+    data = dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret)
+    timer = Timer(dev, 1)
+
+    def step():
+        agent.zero_grad()
+        loss, _ = ppo.compute_loss(agent, data, CLIP, VF, ENT)
+        loss.backward()
+
+    lib.mgb_profile_kernel(b'k_')
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    report = ctypes.create_string_buffer(8 << 20)
+    lib.mgb_profile_report(report, len(report))
+    prof_steps = min(args.steps, 50)
+    before = lib.mgb_launch_count()
+    total_ms, clocks = timer.events(step, prof_steps, 0, ClockSampler(dev.index))
+    launches = (lib.mgb_launch_count() - before) / prof_steps
+    lib.mgb_profile_report(report, len(report))
+    lib.mgb_profile_kernel(None)
+    per_kernel = {}
+    for line in report.value.decode().splitlines():
+        name, ms = line.rsplit(' ', 1)
+        t = per_kernel.setdefault(name.split('<')[0].strip('( '), [0.0, 0])
+        t[0] += float(ms)
+        t[1] += 1
+    allk = sum(t[0] for t in per_kernel.values())
+    wall_ms = timer.wall(step, args.steps, 3, flush=True)
+    # work model of the cfconv kernels (SURVEY.md 8d): per molecule of n atoms and interaction: filter MLP 25->128->128 per ordered
+    # pair (2 * (25*128 + 128*128) flop), in2f / f2out / dense per atom; three molecules per canvas (n, n+1, n+1 atoms); backward 2x
+    flops = 0
+    for k in n:
+        for m in (int(k), int(k) + 1, int(k) + 1):
+            flops += 3 * 3 * (m * max(m - 1, 0) * 2 * (25 * 128 + 128 * 128) + m * 2 * (64 * 128 + 128 * 64 + 64 * 64))
+    sch = per_kernel.get('k_sch_bwd', [0.0, 1])
+    sch_f = per_kernel.get('k_sch_fwd', [0.0, 1])
+    sch_ms = (sch[0] + sch_f[0]) / prof_steps
+    tflops = flops / (sch_ms * 1e-3) / 1e12 if sch_ms > 0 else 0.0
+    line = {'metric': METRIC, 'value': B / (total_ms / prof_steps * 1e-3), 'unit': 'canvases/s', 'n_gpus': 1, 'steps': prof_steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms / prof_steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{cfg.name}: internal-coordinate (SchNet) agent, canvas_size={cfg.canvas_size}, mini_batch_size={B}',
+                       'l2': 'flushed between timed steps'},
+            'clocks': clocks, 'gpu_launches': int(launches * prof_steps), 'gpu_launches_per_step': launches,
+            'e2e': {'value': B / (wall_ms / args.steps * 1e-3), 'unit': 'canvases/s', 'ms_per_step': wall_ms / args.steps,
+                    'h2d_bytes_per_step': int(B * cfg.canvas_size * 3 * (4 + 12) + B * 7 * 4), 'd2h_bytes_per_step': 48,
+                    'note': 'agent.step(obs, act) + torch PPO loss + backward on host observation tuples (z-matrix placement on the host)'},
+            'roofline': {'bound': 'fp32', 'kernel': 'k_sch_fwd + k_sch_bwd', 'achieved': tflops, 'peak': FFMA_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                         'frac': tflops / FFMA_PEAK_TFLOPS, 'traffic': None, 'kernel_ms_per_step': sch_ms,
+                         'kernel_share_of_step': (sch[0] + sch_f[0]) / allk if allk else None, 'algorithmic_flops_per_step': flops,
+                         'note': 'C1 is the reference\'s CPU plumbing configuration: 28 canvases x 3 molecules of <= 7 atoms, one CTA per molecule; '
+                                 'latency-bound at this size'},
+            'top_kernels': [{'kernel': k, 'share': v[0] / allk, 'ms_per_step': v[0] / prof_steps} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])[:6]]}
     print(json.dumps(line), flush=True)
 
 
@@ -490,5 +670,7 @@ if __name__ == '__main__':
     a = parse_args()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.workload == 'C1':
+        run_internal(a)
     else:
         run_ours(a)

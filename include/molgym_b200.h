@@ -60,6 +60,10 @@ const char* mgb_last_error(void);
 int mgb_version(void);
 /* 1 when the library was built by nvcc for sm_100a, 0 for the CPU kernel emulator used by the test-suite. */
 int mgb_is_cuda_build(void);
+/* <j1 m1 j2 m2 | j m> exactly as the plan builder evaluates it for its Clebsch-Gordan tables (host arithmetic, Racah's formula;
+ * replaces cormorant.cg_lib.CGDict, molgym/agents/covariant/agent.py:59).  Exported so that the tables can be pinned against an
+ * independent implementation (tests/test_clebsch_gordan.py compares with sympy.physics.quantum.cg.CG for all l <= 4). */
+double mgb_clebsch_gordan(int32_t j1, int32_t m1, int32_t j2, int32_t m2, int32_t j, int32_t m);
 
 /* Plan: immutable per-(config, device) state — Clebsch-Gordan term tables, Lebedev-71 quadrature harmonics.
  * lebedev_xyz[G*3], lebedev_w[G] (weights summing to 1) are HOST arrays (quadpy lebedev_071 ==

@@ -41,7 +41,7 @@ class IntOutputs(ctypes.Structure):
     _fields_ = [(name, c_void_p) for name in ('logp', 'ent', 'v', 'logp_terms', 'focus_probs', 'element_probs', 'means', 'kappa_logits')]
 
 
-EXPORTS = ('mgb_last_error', 'mgb_version', 'mgb_is_cuda_build', 'mgb_cov_plan_create', 'mgb_cov_plan_destroy',
+EXPORTS = ('mgb_last_error', 'mgb_version', 'mgb_is_cuda_build', 'mgb_clebsch_gordan', 'mgb_cov_plan_create', 'mgb_cov_plan_destroy',
            'mgb_cov_param_count', 'mgb_cov_param_layout', 'mgb_cov_cat_sizes', 'mgb_cov_workspace_bytes',
            'mgb_cov_forward', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_scale_accumulate', 'mgb_launch_count',
            'mgb_profile_kernel', 'mgb_profile_read', 'mgb_profile_report', 'mgb_int_plan_create', 'mgb_int_plan_destroy', 'mgb_int_param_count',
@@ -53,6 +53,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.mgb_last_error.argtypes = []
     lib.mgb_version.restype = ctypes.c_int
     lib.mgb_is_cuda_build.restype = ctypes.c_int
+    lib.mgb_clebsch_gordan.restype = c_double
+    lib.mgb_clebsch_gordan.argtypes = [c_int32] * 6
     lib.mgb_cov_plan_create.restype = ctypes.c_int
     lib.mgb_cov_plan_create.argtypes = [POINTER(CovConfig), POINTER(c_double), POINTER(c_double), c_int32, POINTER(c_void_p)]
     lib.mgb_cov_plan_destroy.restype = None

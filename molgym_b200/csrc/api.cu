@@ -152,6 +152,8 @@ int mgb_is_cuda_build(void) {
 #endif
 }
 
+double mgb_clebsch_gordan(int32_t j1, int32_t m1, int32_t j2, int32_t m2, int32_t j, int32_t m) { return clebsch_gordan(j1, m1, j2, m2, j, m); }
+
 int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const double* leb_w, int32_t n_grid,
                         mgb_cov_plan** out) {
   if (!cfg || !out) return fail(MGB_ERR_INVALID, "null argument");

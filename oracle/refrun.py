@@ -32,7 +32,7 @@ def enable(require_reference=True):
     enable_thirdparty()
     if reference_available():
         if REFERENCE not in sys.path:
-            sys.path.insert(0, REFERENCE)
+            sys.path.append(REFERENCE)   # at the END: only `molgym` is wanted from it (its `tests` package must not shadow this repo's)
         return True
     if require_reference:
         raise RuntimeError(f'reference tree not found at {REFERENCE}')

@@ -85,6 +85,45 @@ def test_fresh_canvases_against_oracle(which, batch):
     assert_grads_close(grads_of(agent), ref_grads)
 
 
+@pytest.mark.parametrize('which,batch,start,large', [('C5', 16, 24, True), ('C5', 16, 24, False), ('C4', 30, 0, True), ('C5', 24, 0, True)])
+def test_large_decomposition_and_high_occupancy_against_oracle(which, batch, start, large, monkeypatch):
+    """The decomposition the full-size C3-C5 minibatches run on (MGB_EDGE_MODE=0 + MGB_SMALL_ATOMS=0: thread-per-pair edge
+    kernels, combined atom kernels, single-kernel policy backward, tiled InputLinear gradient) at N = 22 and N = 40, and the
+    C5 occupancies 24..39 (three to five neighbour chunks per atom) that a batch counted from zero never reaches."""
+    from oracle.molgym_oracle import CovariantOracle, ppo_loss
+    from molgym_b200 import ppo
+    if large:
+        monkeypatch.setenv('MGB_EDGE_MODE', '0')
+        monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
+    cfg = synth.CONFIGS[which]
+    torch.manual_seed(13)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    # the float64 oracle is the arbiter (SURVEY.md 8c): at 20-40 atoms per canvas the float32 torch formulation itself is a few
+    # 1e-4 off in some gradients, the kernels are not
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, dtype=torch.float64, **cfg.agent_kwargs())
+    oracle.load_state_dict({k: v.detach().cpu().double() for k, v in agent.state_dict().items()})
+    obs, n = synth.make_observations(cfg, batch=batch, start_index=start)
+    if start:
+        assert n.min() >= start and n.max() == cfg.canvas_size - 1
+    act = synth.make_actions(cfg, obs, n)
+    ref = oracle.step(obs, act)
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, ref['logp'].detach().numpy())
+    ref_loss, _ = ppo_loss(ref['logp'], ref['ent'], ref['v'], old_logp, adv, ret, 0.2, 0.5, 0.01)
+    ref_loss.backward()
+    ref_grads = {k: (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape))) for k, p in oracle.named_parameters()}
+    for fused in (True, False):
+        agent.fused_ppo = fused
+        agent.zero_grad()
+        loss, _ = ppo.compute_loss(agent, dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret), 0.2, 0.5, 0.01)
+        loss.backward()
+        assert abs(loss.item() - ref_loss.item()) <= 1e-5 * max(1.0, abs(ref_loss.item()))
+        assert_grads_close(grads_of(agent), ref_grads)
+    with torch.no_grad():
+        pred = agent.step(obs, act)
+    for key in ('logp', 'ent', 'v'):
+        assert_outputs_close(pred[key].cpu().numpy(), ref[key].detach().numpy(), rel=OUT_REL, what=key)
+
+
 def test_six_species_24_output_channels_against_oracle():
     """Z = 6 species x 4 channels = 24 output channels: the widest register tile of the row mix (CO = 32) and two channel
     passes of the atom-mix weight gradient, paths the benchmark configurations (Z <= 5) never take."""
@@ -352,3 +391,153 @@ def test_bad_inputs_raise():
     bad = [(((-1, (0.0, 0.0, 0.0)), ) + obs[0][0][1:], obs[0][1])]
     with pytest.raises(RuntimeError):
         agent.step(bad, np.zeros((1, 6), np.float32))
+
+
+def test_bad_action_indices_raise_before_any_launch():
+    """Discrete sub-actions index device arrays; the reference raises RuntimeError from to_one_hot (modules.py:8-23)."""
+    from molgym_b200 import ppo
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=4)
+    act = synth.make_actions(cfg, obs, n)
+    for column, value in ((0, -1.0), (0, float(cfg.canvas_size)), (1, -1.0), (1, float(len(cfg.zs))), (0, float('nan'))):
+        bad = act.copy()
+        bad[2, column] = value
+        with pytest.raises(RuntimeError):
+            agent.step(obs, bad)
+        with pytest.raises(RuntimeError):
+            ppo.compute_loss(agent, dict(obs=obs, act=bad, logp=np.zeros(4, np.float32), adv=np.zeros(4), ret=np.zeros(4)), 0.2, 0.5, 0.01)
+
+
+def test_unpickled_agent_sees_optimizer_updates_in_the_fused_step():
+    """tools/model_util.py:93-117 reloads whole modules; the resumed agent's fused step (own streams) must be ordered behind the
+    optimizer's in-place updates on the caller's stream exactly like a freshly built one."""
+    from molgym_b200 import ppo
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    torch.manual_seed(6)
+    agent = pickle.loads(pickle.dumps(make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())))
+    assert agent._shared_version
+    obs, n = synth.make_observations(cfg, batch=24)
+    act = synth.make_actions(cfg, obs, n)
+    with torch.no_grad():
+        logp0 = agent.step(obs, act)['logp'].cpu().numpy()
+    old_logp, adv, ret = synth.make_ppo_targets(cfg, logp0)
+    data = dict(obs=obs, act=act, logp=old_logp, adv=adv, ret=ret)
+    opt = torch.optim.Adam(agent.parameters(), lr=1e-2)
+    for _ in range(4):
+        agent.fused_ppo = True
+        agent.zero_grad()
+        loss_f, info_f = ppo.compute_loss(agent, data, 0.2, 0.5, 0.01)
+        loss_f.backward()
+        fused = {k: v.copy() for k, v in grads_of(agent).items()}
+        agent.fused_ppo = False
+        agent.zero_grad()
+        loss_u, info_u = ppo.compute_loss(agent, data, 0.2, 0.5, 0.01)
+        loss_u.backward()
+        assert abs(loss_f.item() - loss_u.item()) <= 1e-6 * max(1.0, abs(loss_u.item()))
+        assert_grads_close(fused, grads_of(agent))
+        version = agent._param_version()
+        opt.step()
+        assert agent._param_version() != version
+
+
+def test_evaluate_slots_fall_back_when_busy_and_agree_with_eager_launches():
+    """Evaluate-mode step() under autograd replays CUDA graphs on two persistent slots; a third live evaluation takes the eager
+    path.  All three must give the same numbers and gradients as agent.graph_evaluate = False."""
+    cfg = dataclasses.replace(synth.CONFIGS['C2'], network_width=64)
+    torch.manual_seed(8)
+    agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    obs, n = synth.make_observations(cfg, batch=12)
+    act = synth.make_actions(cfg, obs, n)
+    w = torch.linspace(-1, 1, 12, device='cuda')
+
+    def objective(p):
+        return (p['logp'] * w).sum() + p['v'].sum() - 0.3 * p['ent'].sum()
+
+    agent.graph_evaluate = False
+    agent.zero_grad()
+    ref = agent.step(obs, act)
+    (3 * objective(ref)).backward()
+    want = grads_of(agent)
+    agent.graph_evaluate = True
+    agent.zero_grad()
+    preds = [agent.step(obs, act) for _ in range(3)]
+    assert len(agent._eval_cache[12]) == 2
+    for p in preds:
+        for key in ('logp', 'ent', 'v'):
+            assert torch.equal(p[key], ref[key]), key
+    sum(objective(p) for p in preds).backward()
+    assert_grads_close(grads_of(agent), want, rel=2e-5)
+    # slots are free again: the next evaluations replay the graphs
+    agent.zero_grad()
+    objective(agent.step(obs, act)).backward()
+    assert len(agent._eval_cache[12]) == 2
+
+
+def test_c_abi_forward_backward_with_raw_device_pointers():
+    """The contract a non-Python host binds (include/molgym_b200.h): plan, layout, workspace, forward, loss, backward called with
+    raw device pointers through ctypes only, checked against the oracle."""
+    import ctypes
+    from molgym_b200 import _cabi, _lib
+    from oracle.molgym_oracle import CovariantOracle, pack_observations, ppo_loss
+    from scipy.integrate import lebedev_rule
+    lib = _lib.load()
+    cfg = dataclasses.replace(synth.CONFIGS['C3'], network_width=64)
+    torch.manual_seed(21)
+    oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    c = _cabi.make_config(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
+    pts, wts = lebedev_rule(71)
+    xyz, w = np.ascontiguousarray(pts.T, np.float64), np.ascontiguousarray(wts / (4 * np.pi), np.float64)
+    plan = ctypes.c_void_p()
+    dp = ctypes.POINTER(ctypes.c_double)
+    _cabi.check(lib, lib.mgb_cov_plan_create(ctypes.byref(c), xyz.ctypes.data_as(dp), w.ctypes.data_as(dp), len(w), ctypes.byref(plan)))
+    try:
+        k = lib.mgb_cov_param_count(plan)
+        off, num, tot = (ctypes.c_int64 * k)(), (ctypes.c_int64 * k)(), ctypes.c_int64()
+        _cabi.check(lib, lib.mgb_cov_param_layout(plan, off, num, ctypes.byref(tot)))
+        names = _cabi.param_names(cfg.num_cg_levels)
+        state = oracle.state_dict()
+        flat = np.zeros(tot.value, np.float32)
+        for name, o, m in zip(names, off, num):
+            flat[o:o + m] = state[name].numpy().ravel()
+        B = 20
+        obs, n = synth.make_observations(cfg, batch=B)
+        act = synth.make_actions(cfg, obs, n)
+        pos, charges, bags = pack_observations(obs, cfg.zs, cfg.canvas_size)
+        ref = oracle.evaluate(pos, charges, bags, act)
+        old_logp, adv, ret = synth.make_ppo_targets(cfg, ref['logp'].detach().numpy())
+        dev = torch.device('cuda:0')
+        d = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+        d_pos, d_ch, d_bags, d_act, d_flat = d(pos.astype(np.float32)), d(charges.astype(np.int32)), d(bags.astype(np.float32)), d(act), d(flat)
+        d_old, d_adv, d_ret = d(old_logp), d(adv), d(ret)
+        out = torch.zeros(6, B, device=dev)
+        info = torch.zeros(8, dtype=torch.float64, device=dev)
+        grad = torch.full((tot.value, ), 7.0, device=dev)     # accumulate = 0 must overwrite
+        nbytes = lib.mgb_cov_workspace_bytes(plan, B)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        o = _cabi.CovOutputs()
+        o.logp, o.ent, o.v = out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()
+        stream = torch.cuda.current_stream().cuda_stream
+        assert lib.mgb_cov_forward(plan, B, d_pos.data_ptr(), d_ch.data_ptr(), d_bags.data_ptr(), d_act.data_ptr(), d_flat.data_ptr(),
+                                   ws.data_ptr(), nbytes - 1, ctypes.byref(o), stream) == -3       # MGB_ERR_WORKSPACE
+        assert b'workspace' in lib.mgb_last_error()
+        _cabi.check(lib, lib.mgb_cov_forward(plan, B, d_pos.data_ptr(), d_ch.data_ptr(), d_bags.data_ptr(), d_act.data_ptr(),
+                                             d_flat.data_ptr(), ws.data_ptr(), nbytes, ctypes.byref(o), stream))
+        _cabi.check(lib, lib.mgb_ppo_loss(B, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), d_old.data_ptr(), d_adv.data_ptr(),
+                                          d_ret.data_ptr(), 0.2, 0.5, 0.01, 1.0 / B, info.data_ptr(), out[3].data_ptr(), out[4].data_ptr(),
+                                          out[5].data_ptr(), stream))
+        _cabi.check(lib, lib.mgb_cov_backward(plan, B, d_pos.data_ptr(), d_ch.data_ptr(), d_bags.data_ptr(), d_act.data_ptr(),
+                                              d_flat.data_ptr(), ws.data_ptr(), nbytes, out[3].data_ptr(), out[4].data_ptr(),
+                                              out[5].data_ptr(), grad.data_ptr(), 0, stream))
+        torch.cuda.synchronize()
+        for idx, key in enumerate(('logp', 'ent', 'v')):
+            assert_outputs_close(out[idx].cpu().numpy(), ref[key].detach().numpy(), rel=OUT_REL, what=key)
+        ref_loss, _ = ppo_loss(ref['logp'], ref['ent'], ref['v'], old_logp, adv, ret, 0.2, 0.5, 0.01)
+        ref_loss.backward()
+        assert abs(float(info[0]) - ref_loss.item()) <= 1e-5 * max(1.0, abs(ref_loss.item()))
+        g = grad.cpu().numpy()
+        got = {name: g[o_:o_ + m].reshape(tuple(state[name].shape)) for name, o_, m in zip(names, off, num)}
+        ref_grads = {k_: (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k_, p in oracle.named_parameters()}
+        assert_grads_close(got, ref_grads)
+    finally:
+        lib.mgb_cov_plan_destroy(plan)
