@@ -367,29 +367,33 @@ class Timer:
         return self.max_over_ranks((time.perf_counter() - t0) * 1e3)
 
 
-def e2e_epoch_fn(case, fused):
-    """One pass of ppo.train's loop body (ppo.py:117-146) over EPOCH_LEN minibatches, through the public API."""
+def e2e_epoch_fn(case, fused, tail=True):
+    """One optimizer step of the PPO update through the public API: molgym_b200.ppo.train (the restatement of ppo.py:99-160) over
+    EPOCH_LEN minibatches of host observation tuples.  fused: compute_loss takes the fused CUDA-graph step and the optimizer is
+    molgym_b200.optim.FlatAdam (gradient norm + clipping + Adam as two kernels); else the arithmetic of the reference's own
+    compute_loss (agent.step + torch ops + autograd) with torch.optim.Adam, compute_gradient_norm and clip_grad_norm_ exactly as the
+    unchanged ppo.py runs them.  tail=False: only the minibatch loop (compute_loss + backward)."""
     import torch
     from molgym_b200 import ppo
+    from molgym_b200.optim import FlatAdam
     agent, data = case.agent, case.data
-    if not hasattr(case, 'optimizer'):
-        case.optimizer = torch.optim.Adam(agent.parameters(), lr=LR, amsgrad=False)   # tools/util.py:197-205
-    optimizer = case.optimizer
+    if not hasattr(case, 'epoch_data'):
+        case.epoch_data = {k: (v * EPOCH_LEN if isinstance(v, list) else np.concatenate([v] * EPOCH_LEN)) for k, v in data.items()}
+        case.optimizers = {True: FlatAdam(agent, lr=LR, amsgrad=False),                                   # tools/util.py:197-205
+                           False: torch.optim.Adam(torch.nn.Module.parameters(agent), lr=LR, amsgrad=False)}
+    optimizer = case.optimizers[fused]
+    n = case.n_global
 
     def epoch():
         agent.fused_ppo = fused
+        np.random.seed(1234)   # get_batch_generator permutes with numpy's global generator: the same minibatches on every rank
+        if tail:
+            return ppo.train(agent, optimizer, case.epoch_data, mini_batch_size=n, clip_ratio=CLIP, target_kl=1e9, vf_coef=VF,
+                             entropy_coef=ENT, gradient_clip=GRAD_CLIP, max_num_steps=1)
         optimizer.zero_grad()
-        infos = []
-        for _ in range(EPOCH_LEN):
-            loss, info = ppo.compute_loss(agent, data, CLIP, VF, ENT)
+        for idx in ppo.get_batch_generator(np.arange(len(case.epoch_data['obs'])), n):
+            loss, _ = ppo.compute_loss(agent, ppo.collect_data_batch(case.epoch_data, idx), CLIP, VF, ENT)
             loss.backward()
-            infos.append(info)
-        params = list(agent.parameters())      # data-parallel: the one gradient all-reduce of the optimizer step happens here
-        norm = torch.norm(torch.stack([torch.norm(p.grad.detach(), 2) for p in params]), 2).item()   # compute_gradient_norm (util.py:61-69)
-        torch.nn.utils.clip_grad_norm_(params, max_norm=GRAD_CLIP)
-        optimizer.step()
-        optimizer.zero_grad()
-        return norm, infos
     return epoch
 
 
@@ -458,29 +462,32 @@ def run_ours(args):
         ms_per_step, mode = eager_ms / prof_steps, 'eager launches'
     value = n_global / (ms_per_step * 1e-3)
 
-    # ---- e2e through the public API: wall clock over whole epochs (>= 50 minibatches)
+    # ---- e2e through the public API: wall clock over whole optimizer steps (>= 50 minibatches)
     epochs = max(13, args.steps // EPOCH_LEN // 2)
     e2e = {}
     for key, fused in (('e2e', True), ('e2e_unchanged_ppo', False)):
         fn = e2e_epoch_fn(case, fused)
         ms = timer.wall(fn, epochs, 3, flush=True)
         ms_nf = timer.wall(fn, epochs, 1, flush=False)
+        ms_loop = timer.wall(e2e_epoch_fn(case, fused, tail=False), epochs, 1, flush=False)
         per_mb, per_mb_nf = ms / (epochs * EPOCH_LEN), ms_nf / (epochs * EPOCH_LEN)
         e2e[key] = {'value': n_global / (per_mb * 1e-3), 'unit': 'canvases/s', 'ms_per_step': per_mb, 'steps': epochs * EPOCH_LEN,
-                    'no_flush_value': n_global / (per_mb_nf * 1e-3), 'no_flush_ms_per_step': per_mb_nf}
+                    'no_flush_value': n_global / (per_mb_nf * 1e-3), 'no_flush_ms_per_step': per_mb_nf,
+                    'minibatch_loop_only_ms_per_step': ms_loop / (epochs * EPOCH_LEN)}
     e2e['e2e'].update({
         'h2d_bytes_per_step': int(case.h2d_bytes), 'd2h_bytes_per_step': 64,
         'timing': 'time.perf_counter() around the loop, device synchronised (+ barrier) on both sides, max over ranks; the 256 MiB L2 '
-                  'flush between minibatches is INSIDE the timed region (no_flush_*: the same loop without it)',
-        'note': f'ppo.train loop body (ppo.py:117-146) on host observation tuples: per optimizer step zero_grad, {EPOCH_LEN} x '
-                '(compute_loss -> pack into pinned staging, one H2D copy, CUDA-graph replays of forward + PPO loss and of the backward, '
-                '64-byte D2H of the loss info; loss.backward()), gradient norm, clip_grad_norm_, Adam step; consecutive minibatches '
-                'alternate between two pipeline slots; data-parallel: one all-reduce of the info block per minibatch and ONE gradient '
-                'all-reduce per optimizer step'})
+                  'flush per optimizer step is INSIDE the timed region (no_flush_*: the same loop without it)',
+        'note': f'molgym_b200.ppo.train (ppo.py:99-160 restated) on host observation tuples, one optimizer step per call: zero_grad, {EPOCH_LEN} '
+                'x (compute_loss -> pack into pinned staging, one H2D copy, CUDA-graph replays of forward + PPO loss and of the backward, '
+                '64-byte D2H of the loss info; loss.backward()), then FlatAdam: gradient norm (read back for the loss info), clipping + Adam '
+                'update as two kernels; consecutive minibatches alternate between two pipeline slots; data-parallel: one all-reduce of the '
+                'info block per minibatch and ONE gradient all-reduce per optimizer step; ms_per_step = time per minibatch'})
     e2e['e2e_unchanged_ppo'].update({
-        'note': 'the same loop with the arithmetic of the reference\'s own compute_loss (ppo.py:18-63): agent.step(obs, act) (pack, H2D, '
-                'CUDA-graph replay on a persistent evaluation slot), the loss as torch ops, six .item() syncs, autograd backward '
-                '(graph replay + one accumulate kernel)'})
+        'note': 'the same loop as the unchanged reference runs it: compute_loss = agent.step(obs, act) (pack, H2D, CUDA-graph replay on a '
+                'persistent evaluation slot) + the loss as torch ops + six .item() syncs, autograd backward (graph replay + one accumulate '
+                'kernel); per optimizer step compute_gradient_norm (one torch.norm per parameter tensor, tools/util.py:61-69), '
+                'clip_grad_norm_ and torch.optim.Adam; minibatch_loop_only_* leaves the optimizer tail out'})
 
     # ---- the configurations BASELINE.json names for 8 GPUs: fixed global minibatch sharded over the ranks
     per_config = {}

@@ -187,6 +187,18 @@ int mgb_int_backward(mgb_int_plan* plan, int32_t batch, const int32_t* d_numbers
  * molgym/ppo.py:131).  dst / src 16-byte aligned. */
 int mgb_scale_accumulate(float* dst, const float* src, const void* scale, int32_t scale_is_double, int64_t n, int32_t accumulate,
                          void* stream);
+/* Optimizer tail of one PPO epoch on the flat buffers (replaces tools/util.py:61-69 compute_gradient_norm,
+ * torch.nn.utils.clip_grad_norm_ at ppo.py:144 and the torch.optim.Adam step of tools/util.py:197-205 / ppo.py:145):
+ *   mgb_grad_norm : norm[0] = ||grad||_2, norm[1] = ||grad||_2^2 (float64, deterministic), one launch; `scratch` = device buffer of
+ *                   mgb_optim_scratch_bytes() bytes, zeroed once by the caller before the first use;
+ *   mgb_adam_step : torch.optim.Adam(amsgrad, weight_decay, maximize) on float32 state, gradients scaled by
+ *                   min(1, max_norm / (norm[0] + 1e-6)) when max_norm > 0 (clip_grad_norm_ semantics, norm read on the device);
+ *                   `step` is the 1-based update count of this call.  All pointers are device pointers. */
+size_t mgb_optim_scratch_bytes(void);
+int mgb_grad_norm(const float* d_grad, int64_t n, void* d_scratch, double* d_norm, void* stream);
+int mgb_adam_step(float* d_params, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, float* d_max_exp_avg_sq, int64_t n,
+                  double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, int32_t amsgrad,
+                  int32_t maximize, const double* d_norm, double max_norm, void* stream);
 int64_t mgb_launch_count(void);
 int mgb_profile_kernel(const char* substr);
 int mgb_profile_read(double* total_ms, int64_t* launches);

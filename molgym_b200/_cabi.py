@@ -43,7 +43,7 @@ class IntOutputs(ctypes.Structure):
 
 EXPORTS = ('mgb_last_error', 'mgb_version', 'mgb_is_cuda_build', 'mgb_clebsch_gordan', 'mgb_cov_plan_create', 'mgb_cov_plan_destroy',
            'mgb_cov_param_count', 'mgb_cov_param_layout', 'mgb_cov_cat_sizes', 'mgb_cov_workspace_bytes',
-           'mgb_cov_forward', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_scale_accumulate', 'mgb_launch_count',
+           'mgb_cov_forward', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_scale_accumulate', 'mgb_optim_scratch_bytes', 'mgb_grad_norm', 'mgb_adam_step', 'mgb_launch_count',
            'mgb_profile_kernel', 'mgb_profile_read', 'mgb_profile_report', 'mgb_int_plan_create', 'mgb_int_plan_destroy', 'mgb_int_param_count',
            'mgb_int_param_layout', 'mgb_int_workspace_bytes', 'mgb_int_forward', 'mgb_int_backward')
 
@@ -107,6 +107,13 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.mgb_profile_read.argtypes = [POINTER(c_double), POINTER(c_int64)]
     lib.mgb_scale_accumulate.restype = ctypes.c_int
     lib.mgb_scale_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p]
+    lib.mgb_optim_scratch_bytes.restype = c_size_t
+    lib.mgb_optim_scratch_bytes.argtypes = []
+    lib.mgb_grad_norm.restype = ctypes.c_int
+    lib.mgb_grad_norm.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.mgb_adam_step.restype = ctypes.c_int
+    lib.mgb_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
+                                  c_double, c_int64, c_int32, c_int32, c_void_p, c_double, c_void_p]
     lib.mgb_profile_report.restype = ctypes.c_int
     lib.mgb_profile_report.argtypes = [c_char_p, c_int64]
     return lib

@@ -351,7 +351,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         offs, o = [], 0
         for sh in shapes:
             offs.append(o)
-            o += int(np.prod(sh))
+            o += (int(np.prod(sh)) + 3) // 4 * 4   # every segment starts on a 16-byte boundary (the kernels store float2 / float4)
         return shapes, offs, o
 
     def _slot_outputs(self, st, block: torch.Tensor):

@@ -3,6 +3,7 @@
 #include "plan.cuh"
 #include "cov_backward.cuh"
 #include "internal.cuh"
+#include "optim.cuh"
 
 using namespace mgb;
 

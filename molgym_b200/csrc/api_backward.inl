@@ -231,6 +231,36 @@ int mgb_scale_accumulate(float* dst, const float* src, const void* scale, int32_
   return MGB_OK;
 }
 
+size_t mgb_optim_scratch_bytes(void) { return sizeof(double) * (kNormMaxBlocks + 4); }
+
+int mgb_grad_norm(const float* grad, int64_t n, void* scratch, double* norm, void* stream) {
+  if (!grad || !scratch || !norm) return fail(MGB_ERR_INVALID, "null argument");
+  if (n <= 0) return fail(MGB_ERR_INVALID, "n must be positive");
+  if ((uintptr_t)grad & 15) return fail(MGB_ERR_INVALID, "grad must be 16-byte aligned");
+  const int grid = (int)std::min<int64_t>((n / 4 + kNormThreads - 1) / kNormThreads + 1, kNormMaxBlocks);
+  MGB_LAUNCH(k_grad_norm, grid, kNormThreads, 0, (cudaStream_t)stream, grad, (long long)n, (double*)scratch, norm);
+  MGB_LAUNCH_OK("k_grad_norm");
+  return MGB_OK;
+}
+
+int mgb_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int64_t step, int32_t amsgrad, int32_t maximize,
+                  const double* norm, double max_norm, void* stream) {
+  if (!params || !grad || !exp_avg || !exp_avg_sq) return fail(MGB_ERR_INVALID, "null argument");
+  if (amsgrad && !max_exp_avg_sq) return fail(MGB_ERR_INVALID, "amsgrad needs max_exp_avg_sq");
+  if (n <= 0 || step <= 0) return fail(MGB_ERR_INVALID, "n and step must be positive");
+  if (max_norm > 0 && !norm) return fail(MGB_ERR_INVALID, "clipping needs the device norm (mgb_grad_norm)");
+  AdamArgs a;
+  a.lr = (float)lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.weight_decay = (float)weight_decay;
+  a.step_size = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+  a.bias2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
+  a.max_norm = (float)max_norm; a.amsgrad = amsgrad; a.maximize = maximize;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  MGB_LAUNCH(k_adam_step, grid, 256, 0, (cudaStream_t)stream, params, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, (long long)n, norm, a);
+  MGB_LAUNCH_OK("k_adam_step");
+  return MGB_OK;
+}
+
 int64_t mgb_launch_count(void) { return g_prof.launches; }
 
 int mgb_profile_kernel(const char* substr) {

@@ -1,7 +1,9 @@
 """Host-side mirror of the PPO minibatch step that calls the hot path (reference: molgym/ppo.py:18-63 compute_loss,
-:66-89 batch generation, :99-160 train).  The reference's own ppo.py runs unchanged on top of molgym_b200's agents; this
-restatement exists so the benchmark and the tests can drive the same arithmetic on machines where the reference tree
-is not present (the GPU box)."""
+:66-89 batch generation, :99-160 train).  The reference's own ppo.py runs unchanged on top of molgym_b200's agents
+(tests/test_dropin_reference_loop.py); this restatement exists so the benchmark and the tests can drive the same arithmetic
+on machines where the reference tree is not present (the GPU box), and so that `train` can take the fused step and the fused
+optimizer tail (molgym_b200.optim.FlatAdam) when the caller hands them over."""
+import time
 from typing import Dict, Tuple
 
 import numpy as np
@@ -69,3 +71,48 @@ def collect_data_batch(data: dict, indices: np.ndarray) -> dict:
     for k, v in data.items():
         batch[k] = [v[i] for i in indices] if isinstance(v, list) else v[indices]
     return batch
+
+
+def compute_gradient_norm(parameters, norm_type: int = 2) -> float:
+    """tools/util.py:61-69."""
+    parameters = [p for p in parameters if p.grad is not None]
+    if len(parameters) == 0:
+        return 0.0
+    device = parameters[0].grad.device
+    return torch.norm(torch.stack([torch.norm(p.grad.detach(), norm_type).to(device) for p in parameters]), norm_type).item()
+
+
+def train(ac, optimizer, data: dict, mini_batch_size: int, clip_ratio: float, target_kl: float, vf_coef: float, entropy_coef: float,
+          gradient_clip: float, max_num_steps: int, device=None) -> dict:
+    """ppo.py:99-160, same control flow and the same returned info.  With a `molgym_b200.optim.FlatAdam` optimizer the gradient
+    norm, the clipping and the Adam update run as two kernels on the flat buffers; any other optimizer takes the reference's
+    sequence (compute_gradient_norm, clip_grad_norm_, optimizer.step)."""
+    from molgym_b200.optim import FlatAdam
+    infos: Dict[str, float] = {}
+    start_time = time.time()
+    num_epochs = 0
+    flat = isinstance(optimizer, FlatAdam)
+    for i in range(max_num_steps):
+        optimizer.zero_grad()
+        batch_infos = []
+        for batch_indices in get_batch_generator(indices=np.arange(len(data['obs'])), batch_size=mini_batch_size):
+            data_batch = collect_data_batch(data, indices=batch_indices)
+            batch_loss, batch_info = compute_loss(ac, data=data_batch, clip_ratio=clip_ratio, vf_coef=vf_coef, entropy_coef=entropy_coef,
+                                                  device=device)
+            batch_loss.backward(retain_graph=False)
+            batch_infos.append(batch_info)
+        loss_info = {key: np.mean([d[key] for d in batch_infos]) for key in batch_infos[0].keys()}
+        loss_info['grad_norm'] = float(optimizer.grad_norm().item()) if flat else compute_gradient_norm(ac.parameters())
+        if loss_info['approx_kl'] > 1.5 * target_kl:
+            break
+        if flat:
+            optimizer.step(max_grad_norm=gradient_clip, reuse_norm=True)
+        else:
+            torch.nn.utils.clip_grad_norm_(ac.parameters(), max_norm=gradient_clip)
+            optimizer.step()
+        optimizer.zero_grad()
+        num_epochs += 1
+        infos.update(loss_info)
+    infos['num_opt_steps'] = num_epochs
+    infos['time'] = time.time() - start_time
+    return infos

@@ -275,6 +275,7 @@ static inline double atomicAdd(double* p, double v) {
     if (__atomic_compare_exchange_n(ip, &cur, ni, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return f;
   }
 }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
