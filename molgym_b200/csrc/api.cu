@@ -199,6 +199,8 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   d.p_inb = param(C2);
   TableArena arena;
   std::vector<PendingTable> pending;
+  struct PendingGather { GatherTables* dst; size_t o_ag, o_sq, o_ag_slot, o_sq_slot; };
+  std::vector<PendingGather> pending_g;
   HostCgTable sq_full = build_cg_table(kNL, kNL);
   for (int k = 0; k < d.K; ++k) {
     LevelDesc& L = d.lv[k];
@@ -261,6 +263,15 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
     }
     pending.push_back(stage_table(arena, ag, &L.ag));
     pending.push_back(stage_table(arena, sq, &L.sq));
+    std::memset(&L.gt, 0, sizeof(L.gt));
+    if (L.nLin == kNL) {
+      HostGather h;
+      if (!build_gather_tables(ag, sq, C, h)) return fail(MGB_ERR_INVALID, "internal: gather tables do not fit their encoding");
+      pending_g.push_back(PendingGather{&L.gt, arena.add(h.ag_flat8.data(), h.ag_flat8.size() * sizeof(int)),
+                                        arena.add(h.sq_flat8.data(), h.sq_flat8.size() * sizeof(int)),
+                                        arena.add(h.ag_slot.data(), h.ag_slot.size() * sizeof(int)),
+                                        arena.add(h.sq_slot.data(), h.sq_slot.size() * sizeof(int))});
+    }
   }
   {  // mixer
     int ao = 0, wo = 0;
@@ -323,6 +334,11 @@ int mgb_cov_plan_create(const mgb_cov_config* cfg, const double* leb_xyz, const 
   plan->table_bytes = arena.host.size();
   MGB_CUDA_OK(cudaMemcpy(plan->d_tables, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice));
   for (auto& pt : pending) resolve_table(pt, (const unsigned char*)plan->d_tables);
+  for (auto& pg : pending_g) {
+    const unsigned char* base = (const unsigned char*)plan->d_tables;
+    pg.dst->ag_flat8 = (const int2*)(base + pg.o_ag); pg.dst->ag_slot = (const int*)(base + pg.o_ag_slot);
+    pg.dst->sq_flat8 = (const int2*)(base + pg.o_sq); pg.dst->sq_slot = (const int*)(base + pg.o_sq_slot);
+  }
   if (d.has_beta) {
     d.leb_y = (const float*)((const unsigned char*)plan->d_tables + o_leb_y);
     d.leb_logw = (const float*)((const unsigned char*)plan->d_tables + o_leb_w);

@@ -31,6 +31,7 @@ static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const flo
   // dcat = W^H dA_{level+1}, row-parallel, into HBM; the atom kernel stages its atom's slice in shared memory
   int rc = launch_mix_rows<true>(plan, level, B, w, w.dA[(level + 1) & 1], w.dcat, st);
   if (rc != MGB_OK) return rc;
+
   return plan->desc.lv[level].C == 10 ? launch_atom_bwd_ct<NLM2, 10>(plan, level, B, pos, w, accumulate_dE, st)
                                       : launch_atom_bwd_ct<NLM2, 0>(plan, level, B, pos, w, accumulate_dE, st);
 }

@@ -263,6 +263,19 @@ struct CgTable {
 };
 constexpr int kCgPad = 5;    // max number of l values a pair (l1 m1, l2 m2) couples to for l <= 4
 
+// Forward CG gather tables of the levels whose input carries all ells (cov_forward.cuh::gather25): output-major, 8 bytes per term,
+//   aggregate (a | last << 13 | dst << 14, coef), a = offset of the Kronecker sum T[lm1][lm2] (channel 0) in shared memory;
+//   square    (a | b << 8 | last << 16 | dst << 17, coef), a / b = offsets of the two factors of A_i;
+// dst = offset inside the atom's cat vector; `last` closes the run of one output.  ag_slot / sq_slot [kGatherSlots + 1] cut the
+// lists into ranges of whole outputs of about equal length (one range per group of C threads of the 256-thread CTA).
+constexpr int kGatherSlots = 25;
+struct GatherTables {
+  const int2* ag_flat8;
+  const int2* sq_flat8;
+  const int* ag_slot;
+  const int* sq_slot;
+};
+
 // One Cormorant level (edge network + atom network), everything the kernels need by value.
 struct LevelDesc {
   int nLin;          // ells present in the input atom reps (1 at level 0, else 5)
@@ -285,6 +298,7 @@ struct LevelDesc {
   int sq_block[kNL]; // first block index of the CG-square paths inside cat_l
   long long p_scales, p_phases, p_radW, p_radb, p_edgeW, p_atomW;  // float offsets into the flat parameter buffer
   CgTable ag, sq;
+  GatherTables gt;   // valid when nLin == 5
 };
 
 }  // namespace mgb

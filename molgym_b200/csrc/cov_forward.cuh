@@ -284,6 +284,44 @@ __device__ __forceinline__ void cg_gather(const CgTable& t, int C, const float2*
   }
 }
 
+// CG gather out of shared memory into the atom's cat vector (HBM), thread = (slot, channel); the slot's terms are fetched
+// kGatherBatch at a time (independent, L1-resident loads) before they are consumed.
+constexpr int kGatherBatch = 8;   // table entries fetched together
+template <bool SQUARE>
+__device__ __forceinline__ void gather25(const int2* __restrict__ tab, const int* __restrict__ slots, int C, const float2* __restrict__ src,
+                                         float2* __restrict__ cat) {
+  const int s0 = threadIdx.x / C, c = threadIdx.x - s0 * C;
+  if (s0 >= kGatherSlots) return;
+  const int q0 = slots[s0], q1 = slots[s0 + 1];
+  float2 acc = make_float2(0.f, 0.f);
+  for (int qb = q0; qb < q1; qb += kGatherBatch) {
+    int2 e[kGatherBatch];
+    MGB_UNROLL
+    for (int k = 0; k < kGatherBatch; ++k) e[k] = __ldg(tab + (qb + k < q1 ? qb + k : q1 - 1));
+    MGB_UNROLL
+    for (int k = 0; k < kGatherBatch; ++k) {
+      if (qb + k < q1) {
+        const float cf = __int_as_float(e[k].y);
+        float2 v;
+        int dst, last;
+        if (SQUARE) {
+          v = cmul(src[(e[k].x & 0xff) + c], src[((e[k].x >> 8) & 0xff) + c]);
+          last = (e[k].x >> 16) & 1; dst = (e[k].x >> 17) & 0x1fff;
+        } else {
+          v = src[(e[k].x & 0x1fff) + c];
+          last = (e[k].x >> 13) & 1; dst = (e[k].x >> 14) & 0x1fff;
+        }
+        acc.x = fmaf(cf, v.x, acc.x);
+        acc.y = fmaf(cf, v.y, acc.y);
+        if (last) {
+          cat[dst + c] = acc;
+          acc = make_float2(0.f, 0.f);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Atom level (cormorant CormorantAtomLevel): for atom i
 //   T[c, lm1, lm2] = sum_j E_ij[l1, c] Y_lm1(r_ij) A_j[lm2, c]           (registers, thread = (lm1, c))
@@ -359,7 +397,7 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) sAi[idx] = Ab[(long long)i * NLM2 * C + idx];
   if (!(phases & kAtomPhaseA)) {   // only the blocks that depend on A_i alone
     __syncthreads();
-    cg_gather<true>(L.sq, C, sAi, co);
+    if (NLM2 == kM) gather25<true>(L.gt.sq_flat8, L.gt.sq_slot, C, sAi, co); else cg_gather<true>(L.sq, C, sAi, co);
     for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) {
       const int lm = idx / C, cc = idx % C, l = ell_of_lm(lm);
       co[L.offA[l] + (lm - l * l) * L.catA[l] + L.in_block[l] * C + cc] = sAi[idx];
@@ -401,9 +439,9 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
     for (int q = 0; q < NLM2; ++q) sT[(lm1 * NLM2 + q) * C + c] = acc[q];
   }
   __syncthreads();
-  cg_gather<false>(L.ag, C, sT, co);
+  if (NLM2 == kM) gather25<false>(L.gt.ag_flat8, L.gt.ag_slot, C, sT, co); else cg_gather<false>(L.ag, C, sT, co);
   if (!(phases & kAtomPhaseB)) return;
-  cg_gather<true>(L.sq, C, sAi, co);
+  if (NLM2 == kM) gather25<true>(L.gt.sq_flat8, L.gt.sq_slot, C, sAi, co); else cg_gather<true>(L.sq, C, sAi, co);
   for (int idx = threadIdx.x; idx < NLM2 * C; idx += blockDim.x) {
     const int lm = idx / C, cc = idx % C, l = ell_of_lm(lm);
     co[L.offA[l] + (lm - l * l) * L.catA[l] + L.in_block[l] * C + cc] = sAi[idx];

@@ -218,6 +218,42 @@ inline HostCgTable build_cg_table(int n1, int n2) {
   return t;
 }
 
+// Forward gather tables (see GatherTables in common.cuh).
+struct HostGather {
+  std::vector<int> ag_flat8, sq_flat8;   // 2 ints per term
+  std::vector<int> ag_slot, sq_slot;     // [kGatherSlots + 1]
+};
+inline bool build_gather_tables(const HostCgTable& ag, const HostCgTable& sq, int C, HostGather& out) {
+  auto flat8 = [&](const HostCgTable& t, bool square, std::vector<int>& flat, std::vector<int>& slots) {
+    const int nt = (int)t.term_lm1.size();
+    for (int o = 0; o < t.n_out; ++o)
+      for (int q = t.term_start[o]; q < t.term_start[o + 1]; ++q) {
+        const int last = q == t.term_start[o + 1] - 1 ? 1 : 0, dst = t.out_dst[o];
+        int w0;
+        if (square) w0 = (t.term_lm1[q] * C) | ((t.term_lm2[q] * C) << 8) | (last << 16) | (dst << 17);
+        else w0 = ((t.term_lm1[q] * t.nlm2 + t.term_lm2[q]) * C) | (last << 13) | (dst << 14);
+        int bits;
+        std::memcpy(&bits, &t.term_coef[q], 4);
+        flat.push_back(w0);
+        flat.push_back(bits);
+      }
+    slots.assign(kGatherSlots + 1, nt);
+    slots[0] = 0;
+    int o = 0;
+    for (int s = 1; s < kGatherSlots; ++s) {
+      const long long target = (long long)nt * s / kGatherSlots;
+      while (o < t.n_out && t.term_start[o] < target) ++o;
+      slots[s] = o < t.n_out ? t.term_start[o] : nt;
+    }
+  };
+  if (kM * kM * C >= (1 << 13) || kM * C >= (1 << 8)) return false;
+  for (int o = 0; o < ag.n_out; ++o) if (ag.out_dst[o] >= (1 << 13)) return false;
+  for (int o = 0; o < sq.n_out; ++o) if (sq.out_dst[o] >= (1 << 13)) return false;
+  flat8(ag, false, out.ag_flat8, out.ag_slot);
+  flat8(sq, true, out.sq_flat8, out.sq_slot);
+  return true;
+}
+
 // Greedy split of the 25 (l, m) rows into warp units of <= 3 consecutive m of the same l.
 inline int build_mix_units(MixUnit* units, int max_nm) {
   int n = 0;

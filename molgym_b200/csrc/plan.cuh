@@ -43,7 +43,7 @@ inline int fail(int code, const char* fmt, ...) {
 struct TableArena {
   std::vector<unsigned char> host;
   size_t add(const void* p, size_t bytes) {
-    size_t off = (host.size() + 15) & ~size_t(15);
+    size_t off = (host.size() + 127) & ~size_t(127);   // whole 128-byte lines: some tables are read one line per warp load
     host.resize(off + bytes);
     std::memcpy(host.data() + off, p, bytes);
     return off;
