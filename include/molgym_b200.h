@@ -112,6 +112,14 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t batch, const float* d_positions,
  * recomputed).  Used by rollout mode (agent.py:229-292), where the element head needs the sampled focus, the distance
  * head the sampled element and the orientation head the sampled distance: the caller re-evaluates the heads after
  * each sub-action is drawn.  Same outputs as mgb_cov_forward except `covariats`. */
+/* Rollout mode of CovariantAC.step (actions=None, agent.py:229-292): the body, then one kernel that draws focus, element, distance
+ * and orientation on the device — mode 1: samples (self.training; Categorical / mixture / rejection sampling on the sphere,
+ * spherical_dists.py:116-150,227-262), mode 2: greedy (argmax, gmm.py:20-27, spherical_dists.py:152-158,264-271) — with Philox random
+ * numbers keyed by `seed`, writes the chosen actions [batch, 6] and evaluates them (logp / ent / v and the optional outputs are
+ * exactly what mgb_cov_forward returns for those actions).  No host round trip between the sub-actions. */
+int mgb_cov_rollout(mgb_cov_plan* plan, int32_t batch, const float* d_positions, const int32_t* d_charges, const float* d_bags,
+                    const float* d_params, void* d_workspace, size_t workspace_bytes, int32_t mode, uint64_t seed,
+                    float* d_actions, const mgb_cov_outputs* outputs, void* stream);
 int mgb_cov_policy(mgb_cov_plan* plan, int32_t batch, const float* d_bags, const float* d_actions, const float* d_params,
                    void* d_workspace, size_t workspace_bytes, const mgb_cov_outputs* out, void* stream);
 

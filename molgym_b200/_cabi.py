@@ -43,7 +43,7 @@ class IntOutputs(ctypes.Structure):
 
 EXPORTS = ('mgb_last_error', 'mgb_version', 'mgb_is_cuda_build', 'mgb_clebsch_gordan', 'mgb_cov_plan_create', 'mgb_cov_plan_destroy',
            'mgb_cov_param_count', 'mgb_cov_param_layout', 'mgb_cov_cat_sizes', 'mgb_cov_workspace_bytes',
-           'mgb_cov_forward', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_scale_accumulate', 'mgb_optim_scratch_bytes', 'mgb_grad_norm', 'mgb_adam_step', 'mgb_launch_count',
+           'mgb_cov_forward', 'mgb_cov_rollout', 'mgb_cov_policy', 'mgb_cov_backward', 'mgb_ppo_loss', 'mgb_pack_observations', 'mgb_scale_accumulate', 'mgb_optim_scratch_bytes', 'mgb_grad_norm', 'mgb_adam_step', 'mgb_launch_count',
            'mgb_profile_kernel', 'mgb_profile_read', 'mgb_profile_report', 'mgb_int_plan_create', 'mgb_int_plan_destroy', 'mgb_int_param_count',
            'mgb_int_param_layout', 'mgb_int_workspace_bytes', 'mgb_int_forward', 'mgb_int_backward')
 
@@ -70,6 +70,9 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.mgb_cov_forward.restype = ctypes.c_int
     lib.mgb_cov_forward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                     POINTER(CovOutputs), c_void_p]
+    lib.mgb_cov_rollout.restype = ctypes.c_int
+    lib.mgb_cov_rollout.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int32, ctypes.c_uint64,
+                                    c_void_p, POINTER(CovOutputs), c_void_p]
     lib.mgb_cov_policy.restype = ctypes.c_int
     lib.mgb_cov_policy.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(CovOutputs), c_void_p]
     if hasattr(lib, 'mgb_cov_backward'):

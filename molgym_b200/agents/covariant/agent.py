@@ -388,6 +388,24 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                                                      ctypes.byref(o), stream))
         return outs, ws
 
+    def _rollout_raw(self, pos, charges, bags, mode: int, seed: int):
+        """Body + on-device sampling of the four sub-actions + evaluation of the chosen action (mgb_cov_rollout)."""
+        lib = self._rt.lib()
+        if not self._params_aliased():
+            self._realias()
+        B = pos.shape[0]
+        shapes, offs, total = self._out_layout(B)
+        block = torch.empty(total, dtype=torch.float32, device=self.device)
+        o, _, _ = self._cov_outputs(block, B, True)
+        outs = tuple(block[off:off + int(np.prod(sh))].view(sh) for sh, off in zip(shapes, offs))
+        act = torch.empty(B, 6, dtype=torch.float32, device=self.device)
+        ws = self._workspace(B, fresh=False)
+        with self._rt.device_ctx():
+            _cabi.check(lib, lib.mgb_cov_rollout(self._plan, B, pos.data_ptr(), charges.data_ptr(), bags.data_ptr(), self._flat.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), mode, seed, act.data_ptr(), ctypes.byref(o),
+                                                 self._rt.stream_ptr()))
+        return act, outs
+
     def _backward_raw(self, pos, charges, bags, actions, ws, g_logp, g_ent, g_v):
         lib = self._rt.lib()
         B = pos.shape[0]

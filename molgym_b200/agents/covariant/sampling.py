@@ -1,9 +1,10 @@
-"""Rollout-mode (actions=None) sub-action sampling and the `dists` objects of the response dict.
+"""Rollout mode (actions=None) and the `dists` objects of the response dict.
 
 Reference: agent.py:229-292 (sample when self.training else argmax), spherical_dists.py:44-286 (rejection samplers on
-S^2), gmm.py:8-27, so3_tools.py:8-58.  Rollout batches are `num_envs` observations (2-10) and the reward step on the
-host CPU dominates them, so this stays torch on the device: the CUDA kernels evaluate the
-heads (mgb_cov_policy) after each sub-action is drawn, torch draws the sub-action.
+S^2), gmm.py:8-27, so3_tools.py:8-58.  The sub-actions of a rollout step are drawn on the device by one kernel
+(`rollout` below -> mgb_cov_rollout).  The distribution objects handed out in `response['dists']` keep the reference's
+surface (`probs`, `coefficients`, `log_prob`, `sample`, `argmax`) as plain torch code for callers that inspect them; the
+hot path does not run through them.
 """
 import math
 
@@ -170,26 +171,9 @@ class LazyDists:
 
 @torch.no_grad()
 def rollout(agent, pos, charges, bags, training: bool):
-    """agent.py:229-292 with actions=None: draw focus, element, distance, orientation in turn, re-evaluating the heads
-    on the device after each draw (the Cormorant body runs once)."""
-    B = pos.shape[0]
-    act = torch.zeros(B, 6, dtype=torch.float32, device=pos.device)
-    act[:, 2] = 0.5 * (agent.min_distance + agent.max_distance)
-    act[:, 5] = 1.0
-    bag_first = (bags > 0).float().argmax(dim=1).float()   # any selectable element keeps the heads finite
-    act[:, 1] = bag_first
-    outs, ws = agent._forward_raw(pos, charges, bags, act)
-    dists = LazyDists(agent, *outs[4:9], charges)
-    focus_dist = dists[0]
-    act[:, 0] = (focus_dist.sample() if training else torch.argmax(outs[4], dim=-1)).float()
-    outs, _ = agent._forward_raw(pos, charges, bags, act, policy_only_ws=ws)
-    dists = LazyDists(agent, *outs[4:9], charges)
-    act[:, 1] = (dists[1].sample() if training else torch.argmax(outs[5], dim=-1)).float()
-    outs, _ = agent._forward_raw(pos, charges, bags, act, policy_only_ws=ws)
-    dists = LazyDists(agent, *outs[4:9], charges)
-    act[:, 2] = dists[2].sample().clamp(0.001) if training else dists[2].argmax()
-    outs, _ = agent._forward_raw(pos, charges, bags, act, policy_only_ws=ws)
-    dists = LazyDists(agent, *outs[4:9], charges)
-    act[:, 3:6] = dists[3].sample() if training else dists[3].argmax()
-    outs, _ = agent._forward_raw(pos, charges, bags, act, policy_only_ws=ws)
-    return act, outs
+    """agent.py:229-292 with actions=None: one C-ABI call — the Cormorant body, then ONE kernel that draws focus, element,
+    distance and orientation on the device (k_policy_sample: Philox, Categorical inversion, mixture samples, rejection sampling
+    on the sphere) and evaluates the chosen action.  The seed comes from torch's global generator (tools/util.py:90-92 seeds it),
+    so rollouts are reproducible under set_seeds."""
+    seed = int(torch.randint(0, 2**62, (1, ), dtype=torch.int64).item())
+    return agent._rollout_raw(pos, charges, bags, mode=1 if training else 2, seed=seed)

@@ -416,16 +416,12 @@ size_t mgb_cov_workspace_bytes(const mgb_cov_plan* plan, int32_t batch) {
   return carve_workspace(plan->desc, batch, nullptr).bytes;
 }
 
-int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32_t* charges, const float* bags,
-                    const float* actions, const float* P, void* workspace, size_t workspace_bytes,
-                    const mgb_cov_outputs* out, void* stream) {
-  if (!plan || !pos || !charges || !bags || !actions || !P || !workspace || !out) return fail(MGB_ERR_INVALID, "null argument");
-  if (!out->logp || !out->ent || !out->v) return fail(MGB_ERR_INVALID, "logp/ent/v outputs are required");
-  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
+}  // extern "C"
+
+// The Cormorant body + per-atom heads (everything that does not depend on the action): fills the workspace up to inv / flogit / trans.
+static int forward_body(mgb_cov_plan* plan, int32_t B, const float* pos, const int32_t* charges, const float* bags, const float* P,
+                        const CovWs& w, const mgb_cov_outputs* out, cudaStream_t st) {
   const CovDesc& d = plan->desc;
-  const CovWs w = carve_workspace(d, B, workspace);
-  if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
-  cudaStream_t st = (cudaStream_t)stream;
   const int N = d.N;
   // the weight transposes (+ L2 prefetch of parameters and tables) run on the side stream beside the input kernels; the first
   // reader of Wt is the level-0 edge kernel
@@ -488,16 +484,48 @@ int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32
   }
   MGB_LAUNCH(k_scalars_fwd, B * N, 64, 0, st, plan->d_desc, w.n_atoms, w.A[d.K], w.inv);
   MGB_LAUNCH_OK("k_scalars_fwd");
-  {
-    int rc = launch_rows_mlp_fwd(plan, B, P, w, st);
-    if (rc != MGB_OK) return rc;
-  }
-  {
-    int rc = launch_policy_fwd(plan, B, bags, actions, P, w, out, st);
-    if (rc != MGB_OK) return rc;
-  }
+  return launch_rows_mlp_fwd(plan, B, P, w, st);
+}
+
+extern "C" {
+
+int mgb_cov_forward(mgb_cov_plan* plan, int32_t B, const float* pos, const int32_t* charges, const float* bags,
+                    const float* actions, const float* P, void* workspace, size_t workspace_bytes,
+                    const mgb_cov_outputs* out, void* stream) {
+  if (!plan || !pos || !charges || !bags || !actions || !P || !workspace || !out) return fail(MGB_ERR_INVALID, "null argument");
+  if (!out->logp || !out->ent || !out->v) return fail(MGB_ERR_INVALID, "logp/ent/v outputs are required");
+  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
+  const CovDesc& d = plan->desc;
+  const CovWs w = carve_workspace(d, B, workspace);
+  if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_body(plan, B, pos, charges, bags, P, w, out, st);
+  if (rc != MGB_OK) return rc;
+  rc = launch_policy_fwd(plan, B, bags, actions, P, w, out, st);
+  if (rc != MGB_OK) return rc;
   if (out->covariats)
-    MGB_CUDA_OK(cudaMemcpyAsync(out->covariats, w.A[d.K], sizeof(float) * (size_t)B * N * kM * d.Cout * 2, cudaMemcpyDeviceToDevice, st));
+    MGB_CUDA_OK(cudaMemcpyAsync(out->covariats, w.A[d.K], sizeof(float) * (size_t)B * d.N * kM * d.Cout * 2, cudaMemcpyDeviceToDevice, st));
+  return MGB_OK;
+}
+
+int mgb_cov_rollout(mgb_cov_plan* plan, int32_t B, const float* pos, const int32_t* charges, const float* bags, const float* P,
+                    void* workspace, size_t workspace_bytes, int32_t mode, uint64_t seed, float* actions, const mgb_cov_outputs* out,
+                    void* stream) {
+  if (!plan || !pos || !charges || !bags || !P || !workspace || !actions || !out) return fail(MGB_ERR_INVALID, "null argument");
+  if (!out->logp || !out->ent || !out->v) return fail(MGB_ERR_INVALID, "logp/ent/v outputs are required");
+  if (B <= 0) return fail(MGB_ERR_INVALID, "batch must be positive");
+  if (mode != 1 && mode != 2) return fail(MGB_ERR_INVALID, "mode must be 1 (sample) or 2 (greedy)");
+  const CovDesc& d = plan->desc;
+  const CovWs w = carve_workspace(d, B, workspace);
+  if (w.bytes > workspace_bytes) return fail(MGB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_body(plan, B, pos, charges, bags, P, w, out, st);
+  if (rc != MGB_OK) return rc;
+  const size_t sm = sizeof(float) * policy_smem_floats(d);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  MGB_LAUNCH(k_policy_sample, std::min(B, 148 * 4), kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, w.A[d.K], w.inv,
+             w.flogit, w.trans, mode, (unsigned long long)seed, actions, reinterpret_cast<float2*>(w.lse), *out);
+  MGB_LAUNCH_OK("k_policy_sample");
   return MGB_OK;
 }
 

@@ -772,6 +772,31 @@ __device__ inline void policy_forward(const CovDesc& d, const float* __restrict_
   }
 }
 
+// optional outputs of a canvas (probabilities, mixture parameters, normalised coefficients) from the shared-memory state
+__device__ __forceinline__ void policy_write_extras(const CovDesc& d, const float* __restrict__ P, int b, const PolicySmem& s,
+                                                    const PolicyScalars& ps, const mgb_cov_outputs& out) {
+    if (out.focus_probs) for (int i = threadIdx.x; i < d.N; i += blockDim.x) out.focus_probs[(long long)b * d.N + i] = s.fl[i];
+  if (out.element_probs) for (int z = threadIdx.x; z < d.Z; z += blockDim.x) out.element_probs[(long long)b * d.Z + z] = s.el[z];
+  if (out.coefficients)
+    for (int idx = threadIdx.x; idx < kM * d.CPE; idx += blockDim.x) {
+      reinterpret_cast<float2*>(out.coefficients)[(long long)b * kM * d.CPE + idx] =
+          make_float2(s.cond[idx].x * ps.inv_sqrt_k, s.cond[idx].y * ps.inv_sqrt_k);
+    }
+  if (out.gmm && threadIdx.x == 0) {
+    const int G = d.G;
+    float lse = -3.0e38f;
+    for (int k = 0; k < G; ++k) lse = fmaxf(lse, s.yd[k]);
+    float sg = 0.f;
+    for (int k = 0; k < G; ++k) sg += expf(s.yd[k] - lse);
+    lse += logf(sg);
+    for (int k = 0; k < G; ++k) {
+      out.gmm[((long long)b * 3 + 0) * G + k] = s.yd[k] - lse;
+      out.gmm[((long long)b * 3 + 1) * G + k] = tanhf(s.yd[G + k]) * 0.5f * (d.dmax - d.dmin) + 0.5f * (d.dmin + d.dmax);
+      out.gmm[((long long)b * 3 + 2) * G + k] = fmaxf(expf(P[d.p_logstd + k]), 1e-6f);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kPolicyThreads)
 k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
@@ -802,26 +827,296 @@ k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const 
       }
       if (out.log_z) out.log_z[b] = ps.log_z;
     }
-    if (out.focus_probs) for (int i = threadIdx.x; i < d.N; i += blockDim.x) out.focus_probs[(long long)b * d.N + i] = s.fl[i];
-    if (out.element_probs) for (int z = threadIdx.x; z < d.Z; z += blockDim.x) out.element_probs[(long long)b * d.Z + z] = s.el[z];
-    if (out.coefficients)
-      for (int idx = threadIdx.x; idx < kM * d.CPE; idx += blockDim.x) {
-        reinterpret_cast<float2*>(out.coefficients)[(long long)b * kM * d.CPE + idx] =
-            make_float2(s.cond[idx].x * ps.inv_sqrt_k, s.cond[idx].y * ps.inv_sqrt_k);
-      }
-    if (out.gmm && threadIdx.x == 0) {
-      const int G = d.G;
-      float lse = -3.0e38f;
+    policy_write_extras(d, P, b, s, ps, out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Rollout mode (actions=None, agent.py:229-292): the four sub-actions are drawn on the device, one CTA per canvas, then the
+// chosen action is evaluated by policy_forward — the same code an evaluate-mode step() runs, so its logp is reproduced exactly
+// when the stored action is re-evaluated by ppo.compute_loss.
+//   mode 1 (self.training): Categorical samples for focus / element, a mixture sample for the distance (clamped at 0.001),
+//                           rejection sampling against the uniform proposal for the orientation (spherical_dists.py:116-150,227-262)
+//   mode 2 (greedy):        argmax of the categoricals, best of 128 mixture samples (gmm.py:20-27), best of 128 (beta) / 256
+//                           accepted orientation samples (spherical_dists.py:152-158,264-271)
+// Random numbers: Philox4x32-10 keyed by the seed the host draws from torch's generator, counter = (canvas, thread, draw, stream).
+// ------------------------------------------------------------------------------------------------------------
+struct Philox {
+  unsigned k0, k1, c0, c1, c2, c3;
+  __device__ Philox(unsigned long long seed, unsigned canvas, unsigned thread, unsigned stream)
+      : k0((unsigned)seed), k1((unsigned)(seed >> 32)), c0(canvas), c1(thread), c2(0u), c3(stream) {}
+  __device__ static void mulhilo(unsigned a, unsigned b, unsigned& hi, unsigned& lo) {
+    const unsigned long long p = (unsigned long long)a * b;
+    hi = (unsigned)(p >> 32); lo = (unsigned)p;
+  }
+  // four uniforms in (0, 1); every call advances the draw counter
+  __device__ void next4(float* u) {
+    unsigned x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+    for (int r = 0; r < 10; ++r) {
+      unsigned hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, x0, hi0, lo0);
+      mulhilo(0xCD9E8D57u, x2, hi1, lo1);
+      const unsigned y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    ++c2;
+    const unsigned x[4] = {x0, x1, x2, x3};
+    for (int q = 0; q < 4; ++q) u[q] = ((float)(x[q] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  }
+};
+
+// index drawn from the probabilities p[0..n) by inversion (single thread)
+__device__ inline int categorical_draw(const float* p, int n, float u) {
+  float cum = 0.f;
+  int last = 0;
+  for (int i = 0; i < n; ++i) {
+    if (p[i] > 0.f) {
+      cum += p[i];
+      last = i;
+      if (u < cum) return i;
+    }
+  }
+  return last;
+}
+__device__ inline int argmax_first(const float* p, int n) {
+  int best = 0;
+  for (int i = 1; i < n; ++i) if (p[i] > p[best]) best = i;
+  return best;
+}
+
+// block-wide (max value, smallest index attaining it); scratch >= 64 floats
+__device__ __forceinline__ void block_argmax(float& val, int& idx, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { scratch[w] = val; reinterpret_cast<int*>(scratch)[32 + w] = idx; }
+  __syncthreads();
+  float v = lane < nw ? scratch[lane] : -3.0e38f;
+  int i = lane < nw ? reinterpret_cast<int*>(scratch)[32 + lane] : 0x7fffffff;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  val = v; idx = i;
+  __syncthreads();
+}
+
+__device__ __forceinline__ void sphere_point(float u1, float u2, float* x) {   // spherical_dists.py:49-61
+  const float ct = 1.f - 2.f * u1, st = sqrtf(fmaxf(0.f, 1.f - ct * ct)), phi = kTwoPi * u2;
+  x[0] = st * cosf(phi); x[1] = st * sinf(phi); x[2] = ct;
+}
+__device__ __forceinline__ void fibonacci_point(int i, int n, float* x) {      // so3_tools.py:8-20
+  const float ct = 1.f - 2.f * ((float)i + 0.5f) / (float)n, st = sqrtf(fmaxf(0.f, 1.f - ct * ct));
+  const float phi = kTwoPi * (float)i / 1.618033988749895f;
+  x[0] = st * cosf(phi); x[1] = st * sinf(phi); x[2] = ct;
+}
+// |s(x)|^2 with s = sum_lm a_lm Y_lm(x) ('qm' harmonics of the unit vector x)
+__device__ __forceinline__ float s2_of(const float2* a_loc, const float* x) {
+  float2 y[kM];
+  sph_harm_l4(x[0], x[1], x[2], false, false, y);
+  const float2 sv = sph_sum(a_loc, y);
+  return sv.x * sv.x + sv.y * sv.y;
+}
+
+__global__ void __launch_bounds__(kPolicyThreads)
+k_policy_sample(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
+                const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ A_last,
+                const float* __restrict__ inv, const float* __restrict__ flogit, const float* __restrict__ trans, int mode,
+                unsigned long long seed, float* __restrict__ actions, float2* __restrict__ lse_out, mgb_cov_outputs out) {
+  const CovDesc& d = *dp;
+  MGB_DYN_SMEM(float, sm);
+  PolicySmem s = policy_smem_carve(d, sm);
+  const int N = d.N, Z = d.Z, CPE = d.CPE, Wd = d.Wd, G = d.G, tau = d.Cout;
+  const bool greedy = mode == 2;
+  __shared__ int s_pick[2];
+  __shared__ float s_val[4];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const int n = n_atoms[b], nact = n > 1 ? n : 1;
+    float* act = actions + (long long)b * 6;
+    Philox rng(seed, (unsigned)b, threadIdx.x, 0u);
+    float u4[4];
+    // ---- focus (agent.py:223-234)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s.fl[i] = i < nact ? flogit[(long long)b * N + i] : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bool mask[64];
+      for (int i = 0; i < N; ++i) mask[i] = i < nact;
+      categorical_fwd(s.fl, s.flog, mask, N, nullptr);
+      rng.next4(u4);
+      s_pick[0] = greedy ? argmax_first(s.fl, N) : categorical_draw(s.fl, N, u4[0]);
+    }
+    __syncthreads();
+    const int focus = s_pick[0];
+    const bool focus_valid = focus < n;
+    // ---- element (agent.py:243-253)
+    for (int k = threadIdx.x; k < d.lat; k += blockDim.x) s.finv[k] = inv[((long long)b * N + focus) * d.lat + k];
+    __syncthreads();
+    gemv_rows(P + d.element.W0, P + d.element.b0, s.finv, d.lat, Wd, true, s.he);
+    __syncthreads();
+    gemv_rows(P + d.element.W1, P + d.element.b1, s.he, Wd, Z, false, s.el);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bool mask[MGB_MAX_SPECIES];
+      for (int z = 0; z < Z; ++z) mask[z] = bags[(long long)b * Z + z] > 0.f;
+      categorical_fwd(s.el, s.elog, mask, Z, nullptr);
+      rng.next4(u4);
+      s_pick[1] = greedy ? argmax_first(s.el, Z) : categorical_draw(s.el, Z, u4[0]);
+    }
+    __syncthreads();
+    const int element = s_pick[1];
+    // ---- distance (agent.py:256-276)
+    for (int idx = threadIdx.x; idx < kM * CPE; idx += blockDim.x) {
+      const int lm = idx / CPE, c = idx % CPE;
+      float2 v = make_float2(0.f, 0.f);
+      if (focus_valid) v = reinterpret_cast<const float2*>(A_last)[(((long long)b * N + focus) * kM + lm) * tau + element * CPE + c];
+      s.ecov[idx] = v;
+    }
+    __syncthreads();
+    atomic_scalars_row(s.ecov, CPE, CPE, s.einv, threadIdx.x, blockDim.x);
+    __syncthreads();
+    gemv_rows(P + d.dist.W0, P + d.dist.b0, s.einv, d.latE, Wd, true, s.hd);
+    __syncthreads();
+    gemv_rows(P + d.dist.W1, P + d.dist.b1, s.hd, Wd, 2 * G, false, s.yd);
+    __syncthreads();
+    {
+      // mixture parameters (gmm.py:8-18): every thread holds them
+      float lw[8], mu[8], sd[8], lse = -3.0e38f;
       for (int k = 0; k < G; ++k) lse = fmaxf(lse, s.yd[k]);
       float sg = 0.f;
       for (int k = 0; k < G; ++k) sg += expf(s.yd[k] - lse);
       lse += logf(sg);
+      const float hw = 0.5f * (d.dmax - d.dmin), ctr = 0.5f * (d.dmin + d.dmax);
       for (int k = 0; k < G; ++k) {
-        out.gmm[((long long)b * 3 + 0) * G + k] = s.yd[k] - lse;
-        out.gmm[((long long)b * 3 + 1) * G + k] = tanhf(s.yd[G + k]) * 0.5f * (d.dmax - d.dmin) + 0.5f * (d.dmin + d.dmax);
-        out.gmm[((long long)b * 3 + 2) * G + k] = fmaxf(expf(P[d.p_logstd + k]), 1e-6f);
+        lw[k] = s.yd[k] - lse;
+        mu[k] = tanhf(s.yd[G + k]) * hw + ctr;
+        sd[k] = fmaxf(expf(P[d.p_logstd + k]), 1e-6f);
+      }
+      // one mixture sample per thread: component by inversion, Box-Muller normal
+      rng.next4(u4);
+      int comp = G - 1;
+      float cum = 0.f;
+      for (int k = 0; k < G; ++k) { cum += expf(lw[k]); if (u4[0] < cum) { comp = k; break; } }
+      const float z = sqrtf(-2.f * logf(u4[1])) * cosf(kTwoPi * u4[2]);
+      const float sample = mu[comp] + sd[comp] * z;
+      if (!greedy) {
+        if (threadIdx.x == 0) s_val[0] = fmaxf(sample, 0.001f);   // agent.py:273: ensure the sampled distance is > 0
+      } else {
+        float tm = -3.0e38f, t[8];
+        for (int k = 0; k < G; ++k) {
+          const float df = sample - mu[k];
+          t[k] = -(df * df) / (2.f * sd[k] * sd[k]) - logf(sd[k]) - kLogSqrt2Pi + lw[k];
+          tm = fmaxf(tm, t[k]);
+        }
+        float st = 0.f;
+        for (int k = 0; k < G; ++k) st += expf(t[k] - tm);
+        float score = (int)threadIdx.x < 128 ? tm + logf(st) : -3.0e38f;   // best of 128 samples (gmm.py:20-27)
+        int who = threadIdx.x;
+        block_argmax(score, who, s.red);
+        if ((int)threadIdx.x == who) s_val[0] = sample;
       }
     }
+    __syncthreads();
+    const float dist = s_val[0];
+    // ---- condition on the distance and normalise (agent.py:279-284, so3_tools.py:73-79)
+    mixer_build_cat(d, s.ecov, dist, s.cond /* scratch for ag */, s.cat);
+    mix_rows<4, 2>(d.units_hidden, d.n_units_hidden, d.catM, d.offM, d.offWM, CPE, reinterpret_cast<const float2*>(P + d.p_mixW), s.cat, s.cond);
+    __syncthreads();
+    if (threadIdx.x < kM) {
+      float2 a = make_float2(0.f, 0.f);
+      for (int c = 0; c < CPE; ++c) { a.x += s.cond[threadIdx.x * CPE + c].x; a.y += s.cond[threadIdx.x * CPE + c].y; }
+      s.alm[threadIdx.x] = a;
+    }
+    __syncthreads();
+    float k_raw = 0.f;
+    for (int q = 0; q < kM; ++q) k_raw += s.alm[q].x * s.alm[q].x + s.alm[q].y * s.alm[q].y;
+    const float inv_sqrt_k = 1.f / sqrtf(fmaxf(k_raw, 1e-10f));
+    float2 a_loc[kM];
+    MGB_UNROLL
+    for (int q = 0; q < kM; ++q) a_loc[q] = make_float2(s.alm[q].x * inv_sqrt_k, s.alm[q].y * inv_sqrt_k);
+    __syncthreads();
+    // ---- orientation (agent.py:284-292): log p(x) up to the constant log Z, which cancels in the acceptance ratio
+    //   beta: log p = -beta |s|^2;  beta None: p = |s|^2 (1 / 4 pi on the empty canvas)
+    const bool empty = n == 0;
+    auto score_of = [&](const float* x) {
+      const float s2 = s2_of(a_loc, x);
+      if (d.has_beta) return -d.beta * s2;
+      return empty ? 1.f / kFourPi : s2;
+    };
+    float gmax = -3.0e38f;   // maximum of the score over the Fibonacci grid (4096 points with beta, else 1024)
+    {
+      const int ngrid = d.has_beta ? 4096 : 1024;
+      for (int g = threadIdx.x; g < ngrid; g += blockDim.x) {
+        float x[3];
+        fibonacci_point(g, ngrid, x);
+        gmax = fmaxf(gmax, score_of(x));
+      }
+      gmax = block_max(gmax, s.red);
+    }
+    const int want = greedy ? (d.has_beta ? 128 : 256) : 1;
+    int have = 0;
+    float best = -3.0e38f, best_x[3] = {0.f, 0.f, 1.f};
+    int best_rank = 0x7fffffff;
+    for (int round = 0; round < 4096 && have < want; ++round) {
+      rng.next4(u4);
+      float x[3];
+      sphere_point(u4[0], u4[1], x);
+      const float sc = score_of(x);
+      // acceptance: u < p(x) / (M * uniform) with M = max_grid p / uniform  ->  u < p(x) / max_grid p
+      const float thr = d.has_beta ? expf(sc - gmax) : (gmax > 0.f ? sc / gmax : 1.f);
+      const bool acc = u4[2] < thr;
+      // rank of this thread's candidate among the accepted ones of the round (candidate order = thread order)
+      const unsigned bal = __ballot_sync(0xffffffffu, acc);
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      __syncthreads();
+      if (lane == 0) reinterpret_cast<int*>(s.red)[w] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int q = 0; q < nw; ++q) { const int cq = reinterpret_cast<int*>(s.red)[q]; if (q < w) before += cq; total += cq; }
+      const int rank = have + before + __popc(bal & ((1u << lane) - 1u));
+      if (acc && rank < want) {
+        const float key = greedy ? sc : 0.f;   // sampling keeps the first accepted candidate; greedy the best of the first `want`
+        if (key > best || (key == best && rank < best_rank)) { best = key; best_rank = rank; best_x[0] = x[0]; best_x[1] = x[1]; best_x[2] = x[2]; }
+      }
+      have += total;
+    }
+    {
+      float val = best_rank == 0x7fffffff ? -3.0e38f : best;
+      int who = best_rank == 0x7fffffff ? 0x7fffffff : best_rank;
+      // the winner: greedy -> highest score (ties: lowest rank); sampling -> rank 0
+      float v2 = val;
+      int key = who;
+      block_argmax(v2, key, s.red);
+      if (who == key && val == v2 && who != 0x7fffffff) { s_val[1] = best_x[0]; s_val[2] = best_x[1]; s_val[3] = best_x[2]; }
+      if (key == 0x7fffffff && threadIdx.x == 0) { s_val[1] = 0.f; s_val[2] = 0.f; s_val[3] = 1.f; }   // nothing accepted (cannot happen with a finite score)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      act[0] = (float)focus; act[1] = (float)element; act[2] = dist;
+      act[3] = s_val[1]; act[4] = s_val[2]; act[5] = s_val[3];
+    }
+    __syncthreads();
+    // ---- evaluate the chosen action with the code of the evaluate-mode step
+    PolicyScalars ps;
+    policy_forward(d, P, Wt, b, n_atoms, bags, actions, A_last, inv, flogit, trans, s, ps, nullptr);
+    if (threadIdx.x == 0) {
+      lse_out[b] = make_float2(ps.lse_max, ps.lse_sum);
+      out.logp[b] = ((ps.logp_f + ps.logp_e) + ps.logp_d) + ps.logp_o;
+      out.ent[b] = ps.ent_f + ps.ent_e;
+      out.v[b] = ps.v;
+      if (out.logp_parts) {
+        out.logp_parts[b * 4 + 0] = ps.logp_f; out.logp_parts[b * 4 + 1] = ps.logp_e;
+        out.logp_parts[b * 4 + 2] = ps.logp_d; out.logp_parts[b * 4 + 3] = ps.logp_o;
+      }
+      if (out.log_z) out.log_z[b] = ps.log_z;
+    }
+    policy_write_extras(d, P, b, s, ps, out);
   }
 }
 

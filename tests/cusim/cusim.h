@@ -249,6 +249,13 @@ template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d,
   return cusim::shfl_idx(m, v, src);
 }
 
+static inline unsigned __ballot_sync(unsigned m, int pred) {
+  unsigned r = 0;
+  for (int l = 0; l < 32; ++l) r |= (unsigned)(cusim::shfl_idx(m, pred ? 1 : 0, l) & 1) << l;
+  return r;
+}
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
 template <class T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d, int = 32) {
   int lane = cusim::g_block->current % 32;
   int src = lane - (int)d;
