@@ -1,6 +1,7 @@
 // api.cu — the C ABI (include/molgym_b200.h): plan construction, workspace carving, kernel launch sequences.
 // Compiled by nvcc for sm_100a (product) or by g++ -DMGB_CUSIM against tests/cusim/cusim.h (kernel-logic tests).
 #include "plan.cuh"
+#include "mlp_tc.cuh"
 #include "cov_backward.cuh"
 #include "internal.cuh"
 #include "optim.cuh"
@@ -94,9 +95,38 @@ static int launch_rows_mlp_fwd_rt(const mgb_cov_plan* plan, int B, const float* 
   MGB_LAUNCH_OK("k_rows_mlp_fwd_smem");
   return MGB_OK;
 }
+// tensor-core row MLPs (mlp_tc.cuh): the default widths; anything else takes the FFMA kernels above
+static bool rows_mlp_tc_ok(const CovDesc& d) {
+  const char* e = std::getenv("MGB_MLP_TC");
+  if (e && e[0] == '0') return false;
+  return d.lat % 8 == 0 && d.Wd % 64 == 0 && d.Wd <= 256 && d.lat <= 256 && d.focus.in == d.trans.in && d.focus.hidden == d.trans.hidden &&
+         d.trans.out == d.Wd && d.focus.out == 1 && (d.focus.W0 % 4) == 0 && (d.trans.W0 % 4) == 0 && (d.trans.W1 % 4) == 0 &&
+         rows_mlp_tc_fwd_smem_bytes(d.lat, d.Wd, true) <= kMaxDynSmem && rows_mlp_tc_bwd_smem_bytes(d.lat, d.Wd, true) <= kMaxDynSmem;
+}
+template <int NT>
+static int launch_rows_mlp_fwd_tc(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const size_t sm = rows_mlp_tc_fwd_smem_bytes(d.lat, d.Wd, true);
+  MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_fwd_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const long long tiles = ((long long)B * d.N + kTcRows - 1) / kTcRows;
+  dim3 grid((unsigned)std::min<long long>(tiles, 148), 2);   // one CTA per SM and role keeps the weights for its row tiles
+  MGB_LAUNCH(k_rows_mlp_fwd_tc<NT>, grid, kTcThreads, sm, st, plan->d_desc, P, B, w.act_off, w.act_list, w.atom_off, w.atom_list, w.inv, w.hf,
+             w.flogit, w.ht0, w.trans);
+  MGB_LAUNCH_OK("k_rows_mlp_fwd_tc");
+  return MGB_OK;
+}
 static int launch_rows_mlp_fwd(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const long long rows = (long long)B * d.N;
+  if (rows_mlp_tc_ok(d)) {
+    switch (d.Wd / 64) {
+      case 1: return launch_rows_mlp_fwd_tc<1>(plan, B, P, w, st);
+      case 2: return launch_rows_mlp_fwd_tc<2>(plan, B, P, w, st);
+      case 3: return launch_rows_mlp_fwd_tc<3>(plan, B, P, w, st);
+      case 4: return launch_rows_mlp_fwd_tc<4>(plan, B, P, w, st);
+      default: break;
+    }
+  }
   if (rows_mlp_smem_ok(d)) return rows <= 8ll * 148 * 4 ? launch_rows_mlp_fwd_rt<8>(plan, B, P, w, st) : launch_rows_mlp_fwd_rt<32>(plan, B, P, w, st);
   dim3 grid((unsigned)((rows + kRowTile - 1) / kRowTile), 2);
   const size_t sm = sizeof(float) * kRowTile * (d.lat + d.Wd);
@@ -117,9 +147,28 @@ static int launch_rows_mlp_bwd_rt(const mgb_cov_plan* plan, int B, const float* 
   MGB_LAUNCH_OK("k_rows_mlp_bwd_smem");
   return MGB_OK;
 }
+template <int NT, int NTX>
+static int launch_rows_mlp_bwd_tc(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const size_t sm = rows_mlp_tc_bwd_smem_bytes(d.lat, d.Wd, true);
+  MGB_CUDA_OK(cudaFuncSetAttribute((k_rows_mlp_bwd_tc<NT, NTX>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const long long tiles = ((long long)B * d.N + kTcRows - 1) / kTcRows;
+  dim3 grid((unsigned)std::min<long long>(tiles, 148), 2);
+  MGB_LAUNCH((k_rows_mlp_bwd_tc<NT, NTX>), grid, kTcThreads, sm, st, plan->d_desc, P, B, w.act_off, w.act_list, w.atom_off, w.atom_list, w.hf,
+             w.dflogit, w.dhf, w.ht0, w.dvf, w.dtrans, w.dht0, w.dinv);
+  MGB_LAUNCH_OK("k_rows_mlp_bwd_tc");
+  return MGB_OK;
+}
 static int launch_rows_mlp_bwd(const mgb_cov_plan* plan, int B, const float* P, const CovWs& w, cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const long long rows = (long long)B * d.N;
+  if (rows_mlp_tc_ok(d)) {
+    // input n-tiles per warp: ceil(lat / 64) <= 4 for lat <= 256
+    if (d.Wd / 64 == 2) return launch_rows_mlp_bwd_tc<2, 4>(plan, B, P, w, st);
+    if (d.Wd / 64 == 1) return launch_rows_mlp_bwd_tc<1, 4>(plan, B, P, w, st);
+    if (d.Wd / 64 == 3) return launch_rows_mlp_bwd_tc<3, 4>(plan, B, P, w, st);
+    if (d.Wd / 64 == 4) return launch_rows_mlp_bwd_tc<4, 4>(plan, B, P, w, st);
+  }
   if (rows_mlp_smem_ok(d)) return rows <= 8ll * 148 * 4 ? launch_rows_mlp_bwd_rt<8>(plan, B, P, w, st) : launch_rows_mlp_bwd_rt<32>(plan, B, P, w, st);
   const size_t sm = sizeof(float) * kRowTile * d.Wd * 3;
   MGB_CUDA_OK(cudaFuncSetAttribute(k_rows_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

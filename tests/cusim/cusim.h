@@ -249,6 +249,8 @@ template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d,
   return cusim::shfl_idx(m, v, src);
 }
 
+static inline unsigned __float_as_uint(float x) { unsigned u; std::memcpy(&u, &x, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline unsigned __ballot_sync(unsigned m, int pred) {
   unsigned r = 0;
   for (int l = 0; l < 32; ++l) r |= (unsigned)(cusim::shfl_idx(m, pred ? 1 : 0, l) & 1) << l;

@@ -68,10 +68,14 @@ def _check_rollout_statistics(make_agent, golden, replicas, calls, atol_freq, at
         ref = so3.sample(torch.Size((int(4 * near.sum()), )))[:, 0].cpu().numpy()
         th_d, ph_d = _angles(a[near, 3:6])
         th_r, ph_r = _angles(ref)
-        assert abs(th_d.mean() - th_r.mean()) <= atol_angle
-        lp_d = so3.log_prob(torch.as_tensor(a[near, 3:6], device=so3.device).unsqueeze(1)).mean().item()
-        lp_r = so3.log_prob(torch.as_tensor(ref, device=so3.device).unsqueeze(1)).mean().item()
-        assert abs(lp_d - lp_r) <= 2.5 * atol_angle, (lp_d, lp_r)   # same expected log-density under both samplers
+        # the reference's tolerance (atol 0.1 on mean angles) is for its sample counts; here the standard error of the two means
+        # (the conditioning on the distance thins the device sample) is added: 3 sigma
+        tol = atol_angle + 3.0 * (th_d.std() / np.sqrt(len(th_d)) + th_r.std() / np.sqrt(len(th_r)))
+        assert abs(th_d.mean() - th_r.mean()) <= tol, (th_d.mean(), th_r.mean(), tol, len(th_d))
+        lp_dv = so3.log_prob(torch.as_tensor(a[near, 3:6], device=so3.device).unsqueeze(1)).cpu().numpy().ravel()
+        lp_rv = so3.log_prob(torch.as_tensor(ref, device=so3.device).unsqueeze(1)).cpu().numpy().ravel()
+        tol = atol_angle + 3.0 * (lp_dv.std() / np.sqrt(len(lp_dv)) + lp_rv.std() / np.sqrt(len(lp_rv)))
+        assert abs(lp_dv.mean() - lp_rv.mean()) <= tol, (lp_dv.mean(), lp_rv.mean(), tol)   # same expected log-density under both samplers
     # greedy mode: argmax of the categoricals, a high-density distance and orientation
     agent.training = False
     with torch.no_grad():
@@ -109,7 +113,7 @@ def test_device_rollout_statistics_on_the_gpu(golden):
 
     def make(zs, canvas_size, **kw):
         return CovariantAC(ObservationSpace(canvas_size, zs), ActionSpace(zs), device=torch.device('cuda:0'), **kw)
-    _check_rollout_statistics(make, golden, replicas=1024, calls=4, atol_freq=0.04, atol_angle=0.1)
+    _check_rollout_statistics(make, golden, replicas=1024, calls=4, atol_freq=0.04, atol_angle=0.05)
     # one rollout step = one C-ABI call, no host round trip between the sub-actions
     lib = _lib.load()
     g = load_golden(golden)
