@@ -114,6 +114,72 @@ class _StepState:
     pass
 
 
+_INFO_KEYS = ('total_loss', 'policy_loss', 'entropy_loss', 'vf_loss', 'approx_kl', 'clip_fraction')
+
+
+class LazyLossInfo(dict):
+    """The loss info of ppo.compute_loss (ppo.py:54-61: policy_loss, entropy_loss, vf_loss, total_loss, approx_kl, clip_fraction)
+    whose six numbers are fetched from the device when they are first READ.  ppo.train only reads them after the minibatch loop
+    (compute_mean_dict, ppo.py:133), so the host does not wait for every forward pass and consecutive minibatches really overlap.
+    A plain dict once resolved; every reading access resolves."""
+
+    def __init__(self, state, event):
+        super().__init__()
+        self._pending = (state, event)
+        state.lazy_info = self
+
+    def _resolve(self):
+        pending, self._pending = self._pending, None
+        if pending is not None:
+            state, event = pending
+            event.synchronize()
+            vals = state.info_host.numpy()
+            for i, key in enumerate(_INFO_KEYS):
+                dict.__setitem__(self, key, float(vals[i]))
+            if getattr(state, 'lazy_info', None) is self:
+                state.lazy_info = None
+        return self
+
+    def __getitem__(self, key):
+        return dict.__getitem__(self._resolve(), key)
+
+    def __iter__(self):
+        return dict.__iter__(self._resolve())
+
+    def __len__(self):
+        return dict.__len__(self._resolve())
+
+    def __contains__(self, key):
+        return dict.__contains__(self._resolve(), key)
+
+    def __eq__(self, other):
+        return dict.__eq__(self._resolve(), other._resolve() if isinstance(other, LazyLossInfo) else other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __repr__(self):
+        return dict.__repr__(self._resolve())
+
+    def keys(self):
+        return dict.keys(self._resolve())
+
+    def values(self):
+        return dict.values(self._resolve())
+
+    def items(self):
+        return dict.items(self._resolve())
+
+    def get(self, key, default=None):
+        return dict.get(self._resolve(), key, default)
+
+    def copy(self):
+        return dict(self._resolve())
+
+    def __reduce__(self):
+        return (dict, (dict(self._resolve()), ))
+
+
 def _as_numpy_actions(actions, n: int, width: int) -> np.ndarray:
     a = np.asarray(actions.detach().cpu().numpy() if torch.is_tensor(actions) else actions, dtype=np.float32)
     assert a.shape == (n, width)
@@ -159,6 +225,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         self.fused_ppo = True        # molgym_b200.ppo.compute_loss may use fused_ppo_loss (CUDA-graph replay of the whole step)
         self.fused_sync_params = False   # True: the fused step waits for the caller's stream every time (see fused_ppo_loss)
         self.graph_evaluate = True   # evaluate-mode step() under autograd replays CUDA graphs on persistent slots
+        self.fused_lazy_info = True  # fused_ppo_loss returns a loss-info dict that reads the device when first accessed
         self._check_supported()
         self._init_native()
         self._init_parameters()
@@ -313,6 +380,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
     def __setstate__(self, state):
         self.__dict__.update(state)
         self.__dict__.setdefault('graph_evaluate', True)
+        self.__dict__.setdefault('fused_lazy_info', True)
         # torch.load(map_location=...) moves the unpickled parameters: follow them when they sit on a usable device
         # (tools/model_util.py:93-117 loads whole modules), else keep the pickled device, else the current one
         where = next(iter(torch.nn.Module.parameters(self))).device
@@ -500,8 +568,10 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         st.out = torch.empty(6, B, **f32)   # logp, ent, v, g_logp, g_ent, g_v
         st.info = torch.zeros(8, dtype=torch.float64, device=dev)
         st.info_host = rt.pinned(64).view(torch.float64)
-        st.event = rt.new_event()
         st.acc_event = rt.new_event()
+        st.copied = rt.new_event()
+        st.copied.record(rt.current_stream())
+        st.lazy_info = None
         st.stream = self._fused_streams[slot]
         o = _cabi.CovOutputs()
         o.logp, o.ent, o.v = st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr()
@@ -611,6 +681,9 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             self._fused_turn ^= 1
         st = self._fused_state(B, n, clip_ratio, vf_coef, entropy_coef, slot)
         st.generation += 1
+        if st.lazy_info is not None:
+            st.lazy_info._resolve()    # the slot's previous loss info is read out before its pinned block is overwritten
+        st.copied.synchronize()        # ... and its previous staging copy has left the pinned buffer (two steps ago: no wait in practice)
         pack_observations(observations[lo:hi] if sharded else observations, self.zs, self.canvas_size, cfg=self._cfg,
                           out=(st.h_pos, st.h_charges, st.h_bags), lib=rt.lib())
         st.h_act[...] = actions_np[lo:hi]
@@ -626,20 +699,21 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                 self._fused_param_version = version
             with rt.stream_ctx(st.stream):
                 st.dev.copy_(st.host, non_blocking=True)
+                st.copied.record(st.stream)
                 st.g_forward.replay()
                 if sharded:
                     torch.distributed.all_reduce(st.info, op=torch.distributed.ReduceOp.SUM)
                 st.info_host.copy_(st.info, non_blocking=True)
                 loss_dev = st.info[0].clone()
-                st.event.record(st.stream)
+                event = rt.new_event()       # per call: the lazy info may be read after the slot has moved on
+                event.record(st.stream)
                 st.g_backward.replay()
-            st.event.synchronize()
-            current.wait_event(st.event)   # loss_dev is consumed on the caller's stream
+            current.wait_event(event)        # loss_dev is consumed on the caller's stream (device-side wait: the host goes on)
             if rt.is_cuda:
                 loss_dev.record_stream(current)
-        vals = st.info_host.numpy()
-        info = dict(policy_loss=float(vals[1]), entropy_loss=float(vals[2]), vf_loss=float(vals[3]), total_loss=float(vals[0]),
-                    approx_kl=float(vals[4]), clip_fraction=float(vals[5]))
+        info = LazyLossInfo(st, event)
+        if not self.fused_lazy_info:
+            info._resolve()
         loss = _FusedPPOLoss.apply(self._param_list[-1], self, st, loss_dev)
         return loss, info
 
