@@ -114,6 +114,7 @@ class _StepState:
     pass
 
 
+_INFO_RING = 16   # loss-info blocks in flight per pipeline slot before the oldest must be read out
 _INFO_KEYS = ('total_loss', 'policy_loss', 'entropy_loss', 'vf_loss', 'approx_kl', 'clip_fraction')
 
 
@@ -121,23 +122,40 @@ class LazyLossInfo(dict):
     """The loss info of ppo.compute_loss (ppo.py:54-61: policy_loss, entropy_loss, vf_loss, total_loss, approx_kl, clip_fraction)
     whose six numbers are fetched from the device when they are first READ.  ppo.train only reads them after the minibatch loop
     (compute_mean_dict, ppo.py:133), so the host does not wait for every forward pass and consecutive minibatches really overlap.
-    A plain dict once resolved; every reading access resolves."""
+    A plain dict once resolved; every reading access resolves.
 
-    def __init__(self, state, event):
+    Data-parallel agents: each rank's block holds its shard's share of the global means; reading ANY pending info sums all
+    pending blocks of the agent over the ranks in one all-reduce (a collective: every rank reads its infos at the same point of
+    the same loop, as ppo.train does), so the ranks meet once per optimizer step instead of once per minibatch."""
+
+    def __init__(self, agent, host_block, event, sharded):
         super().__init__()
-        self._pending = (state, event)
-        state.lazy_info = self
+        self._pending = (agent, host_block, event, sharded)
+        if sharded:
+            agent._pending_infos.append(self)
+
+    def _fill(self, vals):
+        self._pending = None
+        for i, key in enumerate(_INFO_KEYS):
+            dict.__setitem__(self, key, float(vals[i]))
 
     def _resolve(self):
-        pending, self._pending = self._pending, None
-        if pending is not None:
-            state, event = pending
+        if self._pending is None:
+            return self
+        agent, host_block, event, sharded = self._pending
+        if not sharded:
             event.synchronize()
-            vals = state.info_host.numpy()
-            for i, key in enumerate(_INFO_KEYS):
-                dict.__setitem__(self, key, float(vals[i]))
-            if getattr(state, 'lazy_info', None) is self:
-                state.lazy_info = None
+            self._fill(host_block.numpy())
+            return self
+        todo, agent._pending_infos = agent._pending_infos, []
+        for info in todo:
+            info._pending[2].synchronize()
+        blocks = torch.stack([info._pending[1] for info in todo])            # [k, 8] float64 (host)
+        dev = blocks.to(agent.device) if agent._rt.is_cuda else blocks.clone()
+        torch.distributed.all_reduce(dev, op=torch.distributed.ReduceOp.SUM)
+        vals = dev.cpu().numpy()
+        for info, row in zip(todo, vals):
+            info._fill(row)
         return self
 
     def __getitem__(self, key):
@@ -289,6 +307,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         self._fused_turn = 0
         self._fused_param_version = None
         self._fused_acc_event = None
+        self._pending_infos = []
         self._one = torch.ones(1, dtype=torch.float32, device=self.device)
 
     def _param_shapes(self) -> Dict[str, tuple]:
@@ -372,7 +391,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ('_rt', '_plan', '_cfg', '_ws_cache', '_fused_cache', '_eval_cache', '_fused_streams', '_fused_acc_event', '_one',
+        for k in ('_rt', '_plan', '_cfg', '_ws_cache', '_fused_cache', '_eval_cache', '_fused_streams', '_fused_acc_event', '_one', '_pending_infos',
                   '_flat', '_flat_grad', '_grad_local', '_grad_pending', '_views', '_grad_views', '_param_list'):
             state.pop(k, None)
         return state
@@ -567,11 +586,12 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         f32 = dict(dtype=torch.float32, device=dev)
         st.out = torch.empty(6, B, **f32)   # logp, ent, v, g_logp, g_ent, g_v
         st.info = torch.zeros(8, dtype=torch.float64, device=dev)
-        st.info_host = rt.pinned(64).view(torch.float64)
+        st.info_ring = rt.pinned(64 * _INFO_RING).view(torch.float64).view(_INFO_RING, 8)   # pinned blocks the lazy infos read from
+        st.ring_infos = [None] * _INFO_RING
+        st.ring_pos = 0
         st.acc_event = rt.new_event()
         st.copied = rt.new_event()
         st.copied.record(rt.current_stream())
-        st.lazy_info = None
         st.stream = self._fused_streams[slot]
         o = _cabi.CovOutputs()
         o.logp, o.ent, o.v = st.out[0].data_ptr(), st.out[1].data_ptr(), st.out[2].data_ptr()
@@ -658,10 +678,12 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         loss.backward().
 
         Data-parallel (parallel.shard_agent): every rank is handed the SAME minibatch and evaluates its contiguous shard of
-        it; the loss terms are sums over the shard divided by the global minibatch size, and one all-reduce of the 8-double
-        info block makes loss / approx_kl / clip_fraction the global values on every rank, so that every rank takes the same
-        early-stop branch (ppo.py:138-140).  The shard's gradient is accumulated locally and reduced once per optimizer step
-        (FlatParamMixin.sync_grads)."""
+        it; the loss terms are sums over the shard divided by the global minibatch size.  The returned info is global on every
+        rank (identical bits: every rank takes the same early-stop branch, ppo.py:138-140): with `fused_lazy_info` the pending
+        8-double blocks of an epoch are summed over ranks in ONE all-reduce when the info is first read, else each block is
+        all-reduced on the stream right behind its forward pass.  The returned loss TENSOR carries the exact gradient; in the
+        lazy data-parallel mode its value is this rank's share of the global loss (the shares sum to info['total_loss']).
+        The shard's gradient is accumulated locally and reduced once per optimizer step (FlatParamMixin.sync_grads)."""
         n = len(observations)
         rt = self._rt
         if not self._params_aliased():
@@ -681,8 +703,10 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             self._fused_turn ^= 1
         st = self._fused_state(B, n, clip_ratio, vf_coef, entropy_coef, slot)
         st.generation += 1
-        if st.lazy_info is not None:
-            st.lazy_info._resolve()    # the slot's previous loss info is read out before its pinned block is overwritten
+        k = st.ring_pos
+        st.ring_pos = (k + 1) % _INFO_RING
+        if st.ring_infos[k] is not None:
+            st.ring_infos[k]._resolve()   # a block is read out before it is overwritten (sixteen steps later: a no-op in practice)
         st.copied.synchronize()        # ... and its previous staging copy has left the pinned buffer (two steps ago: no wait in practice)
         pack_observations(observations[lo:hi] if sharded else observations, self.zs, self.canvas_size, cfg=self._cfg,
                           out=(st.h_pos, st.h_charges, st.h_bags), lib=rt.lib())
@@ -701,9 +725,9 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
                 st.dev.copy_(st.host, non_blocking=True)
                 st.copied.record(st.stream)
                 st.g_forward.replay()
-                if sharded:
+                if sharded and not self.fused_lazy_info:
                     torch.distributed.all_reduce(st.info, op=torch.distributed.ReduceOp.SUM)
-                st.info_host.copy_(st.info, non_blocking=True)
+                st.info_ring[k].copy_(st.info, non_blocking=True)
                 loss_dev = st.info[0].clone()
                 event = rt.new_event()       # per call: the lazy info may be read after the slot has moved on
                 event.record(st.stream)
@@ -711,7 +735,8 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             current.wait_event(event)        # loss_dev is consumed on the caller's stream (device-side wait: the host goes on)
             if rt.is_cuda:
                 loss_dev.record_stream(current)
-        info = LazyLossInfo(st, event)
+        info = LazyLossInfo(self, st.info_ring[k], event, sharded and self.fused_lazy_info)
+        st.ring_infos[k] = info
         if not self.fused_lazy_info:
             info._resolve()
         loss = _FusedPPOLoss.apply(self._param_list[-1], self, st, loss_dev)

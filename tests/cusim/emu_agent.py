@@ -119,7 +119,7 @@ def run_ppo_epoch(agent, data, fused, splits=((0, 6), (6, 11))):
         batch = {k: v[lo:hi] for k, v in data.items()}
         loss, info = ppo.compute_loss(agent, batch, 0.2, 0.5, 0.01)
         loss.backward()
-        infos.append((float(loss.item()), info))
+        infos.append((float(loss.item()), dict(info)))
     grads = torch.cat([p.grad.reshape(-1) for p in agent.parameters()]).clone()
     return infos, grads
 
