@@ -2,11 +2,14 @@
 // Compiled by nvcc for sm_100a (product) or by g++ -DMGB_CUSIM against tests/cusim/cusim.h (kernel-logic tests).
 #include "plan.cuh"
 #include "mlp_tc.cuh"
+#include "mix_tc.cuh"
 #include "cov_backward.cuh"
 #include "internal.cuh"
 #include "optim.cuh"
 
 using namespace mgb;
+
+constexpr size_t kMaxDynSmemMix = 227 * 1024;
 
 #define MGB_LAUNCH_OK(what)                                                                             \
   do {                                                                                                  \
@@ -36,8 +39,59 @@ static int launch_mix_rows_co(const mgb_cov_plan* plan, int level, int B, const 
   // measured slower at C2: every CTA stages the ell's weights for fewer rows)
   return launch_mix_rows_ks<CO, BACKWARD, 8>(plan, level, B, w, A_out, out, st);
 }
+// tensor-core channel mix (mix_tc.cuh): even channel counts whose real-expanded output fits 3 or 4 n-tiles (Cout 9..16), wide
+// enough inner dimensions.  Measured on B200 (profiles/r2n_mix_tc.md): the forward wins from a few thousand atoms per minibatch
+// on (C5 b256: 130 / 144 us against 182 / 243 us), the backward does not (its FFMA version is already bound by the dcat
+// writes), small minibatches are launch-latency bound either way.  Default: forward only, large minibatches.
+// MGB_MIX_TC=0: never; MGB_MIX_TC=1: always, both directions (parity tests).
+static int mix_tc_ntiles(const LevelDesc& L, long long atoms, bool backward) {
+  const char* e = std::getenv("MGB_MIX_TC");
+  if (e && e[0] == '0') return 0;
+  const bool forced = e && e[0] == '1';
+  if (!forced && (backward || atoms < 2048)) return 0;
+  const int nt = (2 * L.Cout + 7) / 8;
+  if (nt != 3 && nt != 4) return 0;
+  int kmax = 0;
+  if (L.totA % 2) return 0;
+  for (int l = 0; l < kNL; ++l) {
+    if (L.catA[l] % 2 || L.offA[l] % 2 || L.catA[l] <= 0) return 0;   // 16-byte aligned cat rows
+    kmax = std::max(kmax, L.catA[l]);
+  }
+  if (kmax < 32 || mix_tc_ksteps(kmax) > kMixTcWarps * kMixTcKsw) return 0;   // the forward keeps a warp's weight fragments in registers
+  if (mix_tc_fwd_smem_bytes(kmax, nt) > kMaxDynSmemMix || mix_tc_bwd_smem_bytes(kmax, nt) > kMaxDynSmemMix) return 0;
+  return nt;
+}
+template <int NT, bool BACKWARD>
+static int launch_mix_rows_tc(const mgb_cov_plan* plan, int level, int B, const float* P, const CovWs& w, const float* A_out, float* out,
+                              cudaStream_t st) {
+  const CovDesc& d = plan->desc;
+  const LevelDesc& L = d.lv[level];
+  int kmax = 0;
+  for (int l = 0; l < kNL; ++l) kmax = std::max(kmax, L.catA[l]);
+  const long long tiles = ((long long)B * d.N * kM + kMixTcRows - 1) / kMixTcRows + kNL;
+  static const int c0 = [] { const char* e = std::getenv("MGB_MIX_C0"); return e ? std::atoi(e) : 256; }();   // per-tile constant of the CTA deal
+  if (!BACKWARD) {
+    const size_t smem = mix_tc_fwd_smem_bytes(kmax, NT);
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_mix_rows_tc_fwd<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::max<long long>(kNL, std::min<long long>(tiles, 148));
+    MGB_LAUNCH(k_mix_rows_tc_fwd<NT>, grid, kMixTcThreads, smem, st, plan->d_desc, level, P, w.atom_off, w.atom_list, B, w.cat[level], out, c0);
+  } else {
+    const size_t smem = mix_tc_bwd_smem_bytes(kmax, NT);
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_mix_rows_tc_bwd<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::max<long long>(kNL, std::min<long long>(tiles, 148));
+    MGB_LAUNCH(k_mix_rows_tc_bwd<NT>, grid, kMixTcThreads, smem, st, plan->d_desc, level, P, w.atom_off, w.atom_list, B, A_out, out, c0);
+  }
+  MGB_LAUNCH_OK("k_mix_rows_tc");
+  return MGB_OK;
+}
 template <bool BACKWARD>
-static int launch_mix_rows(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
+static int launch_mix_rows(const mgb_cov_plan* plan, int level, int B, const float* P, const CovWs& w, const float* A_out, float* out,
+                           cudaStream_t st) {
+  switch (mix_tc_ntiles(plan->desc.lv[level], (long long)B * plan->desc.N, BACKWARD)) {
+    case 3: return launch_mix_rows_tc<3, BACKWARD>(plan, level, B, P, w, A_out, out, st);
+    case 4: return launch_mix_rows_tc<4, BACKWARD>(plan, level, B, P, w, A_out, out, st);
+    default: break;
+  }
   switch (pick_co_rows(plan->desc.lv[level].Cout)) {
     case 4: return launch_mix_rows_co<4, BACKWARD>(plan, level, B, w, A_out, out, st);
     case 8: return launch_mix_rows_co<8, BACKWARD>(plan, level, B, w, A_out, out, st);
@@ -73,8 +127,7 @@ static int launch_atom_fwd(const mgb_cov_plan* plan, int level, int B, const flo
   int rc = launch_atom_cat<NLM2>(plan, level, B, pos, w, small_atoms(B, d.N) ? kAtomPhaseA : kAtomPhaseA | kAtomPhaseB, st);
   if (rc != MGB_OK) return rc;
   if (small_atoms(B, d.N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[level], 0));   // the square / pass-through blocks (side3)
-  (void)P;
-  return launch_mix_rows<false>(plan, level, B, w, nullptr, w.A[level + 1], st);
+  return launch_mix_rows<false>(plan, level, B, P, w, nullptr, w.A[level + 1], st);
 }
 
 // Row MLPs (focus head, value transform): shared-memory resident weights when they fit, else the generic kernels.

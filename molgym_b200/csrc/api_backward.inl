@@ -27,9 +27,8 @@ static int launch_atom_bwd_ct(const mgb_cov_plan* plan, int level, int B, const 
 template <int NLM2>
 static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
                            int accumulate_dE, cudaStream_t st) {
-  (void)P;
   // dcat = W^H dA_{level+1}, row-parallel, into HBM; the atom kernel stages its atom's slice in shared memory
-  int rc = launch_mix_rows<true>(plan, level, B, w, w.dA[(level + 1) & 1], w.dcat, st);
+  int rc = launch_mix_rows<true>(plan, level, B, P, w, w.dA[(level + 1) & 1], w.dcat, st);
   if (rc != MGB_OK) return rc;
 
   return plan->desc.lv[level].C == 10 ? launch_atom_bwd_ct<NLM2, 10>(plan, level, B, pos, w, accumulate_dE, st)

@@ -37,6 +37,8 @@ struct dim3 {
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct int2 { int x, y; };
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct int4 { int x, y, z, w; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }

@@ -95,6 +95,7 @@ def test_large_decomposition_and_high_occupancy_against_oracle(which, batch, sta
     if large:
         monkeypatch.setenv('MGB_EDGE_MODE', '0')
         monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
+        monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
     cfg = synth.CONFIGS[which]
     torch.manual_seed(13)
     agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
@@ -187,6 +188,7 @@ def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
     monkeypatch.setenv('MGB_EDGE_MODE', mode)
     if mode == '0':   # together with the large-minibatch atom path (combined atom kernels, tiled InputLinear weight gradient)
         monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
+        monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
     cfg = synth.CONFIGS['C3']
     torch.manual_seed(5)
     agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())

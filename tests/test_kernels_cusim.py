@@ -50,6 +50,7 @@ def test_fresh_canvases_against_oracle(levels, beta, zs, canvas, edge_mode, monk
         monkeypatch.setenv('MGB_EDGE_MODE', edge_mode)
         if edge_mode == '0':    # ... and the large-minibatch atom path (combined atom kernels, tiled InputLinear gradient)
             monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
+            monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
     cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=canvas, network_width=32, num_cg_levels=levels, beta=beta,
                               bag={z: 2 for z in zs if z}, bag_scale=4, seed=levels)
     torch.manual_seed(levels)
@@ -83,6 +84,7 @@ def test_high_occupancy_canvases_against_oracle(which, batch, start, large, monk
     if large:
         monkeypatch.setenv('MGB_EDGE_MODE', '0')
         monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
+        monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
     cfg = dataclasses.replace(synth.CONFIGS[which], network_width=32)
     torch.manual_seed(8)
     oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
