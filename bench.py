@@ -16,9 +16,10 @@ at N = 1 C5 runs its one-GPU shard of 1024 canvases).
                      graph per slot; the better of (a) sequential replays, L2 flushed between steps, an event pair per step and
                      (b) K steps replayed round-robin over independent slots on two streams, one event pair around all of them, the
                      rotation's workspaces larger than L2 (both reported: sequential_ms_per_step / pipelined_ms_per_step); max over ranks.
-  e2e              : ppo.train's inner loop (ppo.py:117-146) through the public API on HOST observation tuples: per epoch
-                     zero_grad, EPOCH_LEN x (compute_loss -> fused CUDA-graph step, loss.backward()), gradient norm, clipping and
-                     optimizer.step(); wall clock around the whole loop, L2 flush counted inside.
+  e2e              : ppo.train (ppo.py:99-160) through the public API on HOST observation tuples, TRAIN_ITERS optimizer steps per call
+                     (the reference default): per optimizer step zero_grad, EPOCH_LEN x (compute_loss -> fused CUDA-graph step,
+                     loss.backward()), KL check, gradient norm, clipping and optimizer.step(); wall clock around the whole loop, L2
+                     flush (once per call) counted inside.
   e2e_unchanged_ppo: the same loop with the arithmetic of the reference's own compute_loss (agent.step + torch ops + autograd).
   roofline / cpu_baseline / per_config : see DESIGN.md.
 """
@@ -41,6 +42,7 @@ CLIP, VF, ENT = 0.2, 0.5, 0.01   # arg_parser.py:84-86
 LR, GRAD_CLIP = 3e-4, 0.5         # arg_parser.py:80,88
 METRIC = 'ppo_minibatch_fwd_bwd_canvases_per_sec'
 EPOCH_LEN = 4                     # minibatches per optimizer step in the e2e loop
+TRAIN_ITERS = 7                   # optimizer steps per ppo.train call: the reference's default --max_num_train_iters (tools/arg_parser.py:87)
 FFMA_PEAK_TFLOPS = 72.3           # measured on this pool's B200 (tools/ffma_peak.cu, profiles/r1_ffma_peak.txt); nominal 74.4
 
 
@@ -416,8 +418,8 @@ class Timer:
         return self.max_over_ranks((time.perf_counter() - t0) * 1e3)
 
 
-def e2e_epoch_fn(case, fused, tail=True):
-    """One optimizer step of the PPO update through the public API: molgym_b200.ppo.train (the restatement of ppo.py:99-160) over
+def e2e_epoch_fn(case, fused, tail=True, iters=1):
+    """`iters` optimizer steps of the PPO update (one ppo.train call, as ppo.py:337 makes it) through the public API: molgym_b200.ppo.train (the restatement of ppo.py:99-160) over
     EPOCH_LEN minibatches of host observation tuples.  fused: compute_loss takes the fused CUDA-graph step and the optimizer is
     molgym_b200.optim.FlatAdam (gradient norm + clipping + Adam as two kernels); else the arithmetic of the reference's own
     compute_loss (agent.step + torch ops + autograd) with torch.optim.Adam, compute_gradient_norm and clip_grad_norm_ exactly as the
@@ -438,11 +440,12 @@ def e2e_epoch_fn(case, fused, tail=True):
         np.random.seed(1234)   # get_batch_generator permutes with numpy's global generator: the same minibatches on every rank
         if tail:
             return ppo.train(agent, optimizer, case.epoch_data, mini_batch_size=n, clip_ratio=CLIP, target_kl=1e9, vf_coef=VF,
-                             entropy_coef=ENT, gradient_clip=GRAD_CLIP, max_num_steps=1)
-        optimizer.zero_grad()
-        for idx in ppo.get_batch_generator(np.arange(len(case.epoch_data['obs'])), n):
-            loss, _ = ppo.compute_loss(agent, ppo.collect_data_batch(case.epoch_data, idx), CLIP, VF, ENT)
-            loss.backward()
+                             entropy_coef=ENT, gradient_clip=GRAD_CLIP, max_num_steps=iters)
+        for _ in range(iters):
+            optimizer.zero_grad()
+            for idx in ppo.get_batch_generator(np.arange(len(case.epoch_data['obs'])), n):
+                loss, _ = ppo.compute_loss(agent, ppo.collect_data_batch(case.epoch_data, idx), CLIP, VF, ENT)
+                loss.backward()
     return epoch
 
 
@@ -540,26 +543,29 @@ def run_ours(args):
     value = n_global / (ms_per_step * 1e-3)
 
     # ---- e2e through the public API: wall clock over whole optimizer steps (>= 50 minibatches)
-    epochs = max(13, args.steps // EPOCH_LEN // 2)
+    calls = max(3, args.steps // (EPOCH_LEN * TRAIN_ITERS))
+    per_call = EPOCH_LEN * TRAIN_ITERS
     e2e = {}
     for key, fused in (('e2e', True), ('e2e_unchanged_ppo', False)):
-        fn = e2e_epoch_fn(case, fused)
-        ms = timer.wall(fn, epochs, 3, flush=True)
-        ms_nf = timer.wall(fn, epochs, 1, flush=False)
-        ms_loop = timer.wall(e2e_epoch_fn(case, fused, tail=False), epochs, 1, flush=False)
-        per_mb, per_mb_nf = ms / (epochs * EPOCH_LEN), ms_nf / (epochs * EPOCH_LEN)
-        e2e[key] = {'value': n_global / (per_mb * 1e-3), 'unit': 'canvases/s', 'ms_per_step': per_mb, 'steps': epochs * EPOCH_LEN,
+        fn = e2e_epoch_fn(case, fused, iters=TRAIN_ITERS)
+        ms = timer.wall(fn, calls, 2, flush=True)
+        ms_nf = timer.wall(fn, calls, 1, flush=False)
+        ms_loop = timer.wall(e2e_epoch_fn(case, fused, tail=False, iters=TRAIN_ITERS), calls, 1, flush=False)
+        per_mb, per_mb_nf = ms / (calls * per_call), ms_nf / (calls * per_call)
+        e2e[key] = {'value': n_global / (per_mb * 1e-3), 'unit': 'canvases/s', 'ms_per_step': per_mb, 'steps': calls * per_call,
                     'no_flush_value': n_global / (per_mb_nf * 1e-3), 'no_flush_ms_per_step': per_mb_nf,
-                    'minibatch_loop_only_ms_per_step': ms_loop / (epochs * EPOCH_LEN)}
+                    'minibatch_loop_only_ms_per_step': ms_loop / (calls * per_call)}
     e2e['e2e'].update({
         'h2d_bytes_per_step': int(case.h2d_bytes), 'd2h_bytes_per_step': 64,
         'timing': 'time.perf_counter() around the loop, device synchronised (+ barrier) on both sides, max over ranks; the 256 MiB L2 '
-                  'flush per optimizer step is INSIDE the timed region (no_flush_*: the same loop without it)',
-        'note': f'molgym_b200.ppo.train (ppo.py:99-160 restated) on host observation tuples, one optimizer step per call: zero_grad, {EPOCH_LEN} '
-                'x (compute_loss -> pack into pinned staging, one H2D copy, CUDA-graph replays of forward + PPO loss and of the backward, '
-                '64-byte D2H of the loss info; loss.backward()), then FlatAdam: gradient norm (read back for the loss info), clipping + Adam '
-                'update as two kernels; consecutive minibatches alternate between two pipeline slots; data-parallel: one all-reduce of the '
-                'info block per minibatch and ONE gradient all-reduce per optimizer step; ms_per_step = time per minibatch'})
+                  'flush per ppo.train call is INSIDE the timed region (no_flush_*: the same loop without it)',
+        'note': f'molgym_b200.ppo.train (ppo.py:99-160 restated) on host observation tuples, called as ppo.py:337 calls it with the reference default '
+                f'max_num_train_iters = {TRAIN_ITERS} optimizer steps per call; per optimizer step: zero_grad, {EPOCH_LEN} x (compute_loss -> pack into '
+                'pinned staging, one H2D copy, CUDA-graph replays of forward + PPO loss and of the backward, 64-byte D2H of the loss info; '
+                'loss.backward()), read of the loss infos (KL early-stop check, waits for the forward passes only), then FlatAdam: gradient norm, '
+                'clipping + Adam update as two kernels (the norm is read back once per call, for the returned infos); consecutive minibatches '
+                'alternate between two pipeline slots; data-parallel: one all-reduce of the pending info blocks and ONE gradient all-reduce per '
+                'optimizer step; ms_per_step = time per minibatch'})
     e2e['e2e_unchanged_ppo'].update({
         'note': 'the same loop as the unchanged reference runs it: compute_loss = agent.step(obs, act) (pack, H2D, CUDA-graph replay on a '
                 'persistent evaluation slot) + the loss as torch ops + six .item() syncs, autograd backward (graph replay + one accumulate '

@@ -92,6 +92,7 @@ def train(ac, optimizer, data: dict, mini_batch_size: int, clip_ratio: float, ta
     start_time = time.time()
     num_epochs = 0
     flat = isinstance(optimizer, FlatAdam)
+    kept_norm = None   # FlatAdam: the gradient norm of the last completed step stays on the device until the loop is over
     for i in range(max_num_steps):
         optimizer.zero_grad()
         batch_infos = []
@@ -101,18 +102,25 @@ def train(ac, optimizer, data: dict, mini_batch_size: int, clip_ratio: float, ta
                                                   device=device)
             batch_loss.backward(retain_graph=False)
             batch_infos.append(batch_info)
+        # the loss numbers come from the forward passes: reading them does not wait for the backward of the last minibatch
         loss_info = {key: np.mean([d[key] for d in batch_infos]) for key in batch_infos[0].keys()}
-        loss_info['grad_norm'] = float(optimizer.grad_norm().item()) if flat else compute_gradient_norm(ac.parameters())
+        if flat:
+            norm = optimizer.grad_norm().clone()   # only the infos of the last completed step are returned (ppo.py:150): no read-back here
+        else:
+            loss_info['grad_norm'] = compute_gradient_norm(ac.parameters())
         if loss_info['approx_kl'] > 1.5 * target_kl:
             break
         if flat:
             optimizer.step(max_grad_norm=gradient_clip, reuse_norm=True)
+            kept_norm = norm
         else:
             torch.nn.utils.clip_grad_norm_(ac.parameters(), max_norm=gradient_clip)
             optimizer.step()
         optimizer.zero_grad()
         num_epochs += 1
         infos.update(loss_info)
+    if kept_norm is not None:
+        infos['grad_norm'] = float(kept_norm.item())
     infos['num_opt_steps'] = num_epochs
     infos['time'] = time.time() - start_time
     return infos
