@@ -151,9 +151,19 @@ class LazyLossInfo(dict):
         for info in todo:
             info._pending[2].synchronize()
         blocks = torch.stack([info._pending[1] for info in todo])            # [k, 8] float64 (host)
-        dev = blocks.to(agent.device) if agent._rt.is_cuda else blocks.clone()
-        torch.distributed.all_reduce(dev, op=torch.distributed.ReduceOp.SUM)
-        vals = dev.cpu().numpy()
+        if agent._rt.is_cuda:
+            # on a stream of its own: the caller's stream is queued behind the backward passes (gradient accumulation), the loss
+            # numbers are not — the ranks exchange them while the last backward is still running
+            if getattr(agent, '_info_stream', None) is None:
+                agent._info_stream = agent._rt.new_stream()
+            with agent._rt.stream_ctx(agent._info_stream):
+                dev = blocks.to(agent.device)
+                torch.distributed.all_reduce(dev, op=torch.distributed.ReduceOp.SUM)
+                vals = dev.cpu().numpy()
+        else:
+            dev = blocks.clone()
+            torch.distributed.all_reduce(dev, op=torch.distributed.ReduceOp.SUM)
+            vals = dev.numpy()
         for info, row in zip(todo, vals):
             info._fill(row)
         return self
@@ -391,7 +401,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ('_rt', '_plan', '_cfg', '_ws_cache', '_fused_cache', '_eval_cache', '_fused_streams', '_fused_acc_event', '_one', '_pending_infos',
+        for k in ('_rt', '_plan', '_cfg', '_ws_cache', '_fused_cache', '_eval_cache', '_fused_streams', '_fused_acc_event', '_one', '_pending_infos', '_info_stream',
                   '_flat', '_flat_grad', '_grad_local', '_grad_pending', '_views', '_grad_views', '_param_list'):
             state.pop(k, None)
         return state
