@@ -1,6 +1,7 @@
 """Target of compute-sanitizer (memcheck / racecheck / synccheck): two PPO minibatch steps of the covariant agent through the fused
 CUDA-graph-free path (eager launches: the sanitizer instruments kernels launched directly), one evaluate-mode step + backward, and
-one step of the internal-coordinate (SchNet) agent.
+one FlatAdam step, rollouts (sample + greedy), and one step of the internal-coordinate (SchNet) agent.  MGB_MIX_TC=1 routes the channel mix
+through the tensor-core kernels.
     compute-sanitizer --tool memcheck python tools/sanitize_step.py [workload] [batch]"""
 import dataclasses
 import os
@@ -34,6 +35,10 @@ for _ in range(2):
     agent.zero_grad()
     loss, info = ppo.compute_loss(agent, data, 0.2, 0.5, 0.01)
     loss.backward()
+from molgym_b200.optim import FlatAdam  # noqa: E402
+opt = FlatAdam(agent, lr=3e-4)
+opt.grad_norm()
+opt.step(max_grad_norm=0.5, reuse_norm=True)   # k_grad_norm + k_adam_step
 torch.cuda.synchronize()
 print('covariant', which, batch, 'loss', float(loss), 'grad norm', float(torch.cat([p.grad.reshape(-1) for p in agent.parameters()]).norm()))
 for training in (True, False):
