@@ -235,10 +235,16 @@ static int launch_policy_fwd(const mgb_cov_plan* plan, int B, const float* bags,
                              const CovWs& w, const mgb_cov_outputs* out, cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const size_t sm = sizeof(float) * policy_smem_floats(d);
-  MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int grid = std::min(B, 148 * 4);
-  MGB_LAUNCH(k_policy_fwd, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
-             w.flogit, w.trans, reinterpret_cast<float2*>(w.lse), w.pol_state, *out);
+  if (B <= 148) {   // at most one canvas per SM: the spill-free instantiation
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    MGB_LAUNCH(k_policy_fwd<1>, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
+               w.flogit, w.trans, reinterpret_cast<float2*>(w.lse), w.pol_state, *out);
+  } else {          // two resident CTAs per SM
+    MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    MGB_LAUNCH(k_policy_fwd<2>, grid, kPolicyThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[d.K], w.inv,
+               w.flogit, w.trans, reinterpret_cast<float2*>(w.lse), w.pol_state, *out);
+  }
   MGB_LAUNCH_OK("k_policy_fwd");
   return MGB_OK;
 }

@@ -58,7 +58,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     PolicyBwdOut o{w.finv, w.he, w.einv, w.hd, w.vf, w.hv, w.dhe, w.dye, w.dhd, w.dyd, w.dhv, w.dyv, w.dvf, w.dflogit, w.dinv, w.dA[K & 1]};
     const size_t sm = sizeof(float) * (policy_smem_floats(d) + policy_bwd_extra_floats(d));
     MGB_CUDA_OK(cudaFuncSetAttribute(k_policy_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const int grid = std::min(B, 148 * 2);
+    const int grid = std::min(B, 148 * MGB_POLICY_BWD_MIN_CTAS);
     MGB_LAUNCH(k_policy_bwd, grid, kPolicyBwdThreads, sm, st, plan->d_desc, P, w.Wt, B, w.n_atoms, bags, actions, w.A[K], w.inv, w.flogit,
                w.trans, w.pol_state, g_logp, g_ent, g_v, o, w.mix_stage, grad);
     MGB_LAUNCH_OK("k_policy_bwd");

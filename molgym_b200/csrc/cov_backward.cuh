@@ -76,7 +76,7 @@ __device__ __forceinline__ void gemv_n(const float* __restrict__ W, const float*
   }
 }
 
-__global__ void __launch_bounds__(kPolicyBwdThreads)
+__global__ void __launch_bounds__(kPolicyBwdThreads, MGB_POLICY_BWD_MIN_CTAS)
 k_policy_bwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,

@@ -13,6 +13,12 @@ constexpr int kRowTile = 8;
 constexpr int kHeadThreads = 128;     // row-MLP kernels
 constexpr int kPolicyThreads = 512;   // per-canvas policy forward (one CTA per canvas; the GEMV phases are latency-bound)
 constexpr int kPolicyBwdThreads = 256;
+// resident CTAs per SM the policy kernels are compiled for.  Backward: 2 (128 registers; measured C3 b1024 341 -> 225 us, C2 unchanged).
+// Forward: a template parameter — 1 for minibatches of at most one canvas per SM (no spills: C2 46 us against 55 us), 2 above that
+// (64 registers, some spills, but two canvases' latency chains overlap: C3 b1024 236 -> 184 us).
+#ifndef MGB_POLICY_BWD_MIN_CTAS
+#define MGB_POLICY_BWD_MIN_CTAS 2
+#endif
 constexpr float kF32Eps = 1.1920928955078125e-07f;
 constexpr float kLogSqrt2Pi = 0.9189385332046727f;
 constexpr float kLog4Pi = 2.5310242469692907f;
@@ -797,7 +803,8 @@ __device__ __forceinline__ void policy_write_extras(const CovDesc& d, const floa
   }
 }
 
-__global__ void __launch_bounds__(kPolicyThreads)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kPolicyThreads, MIN_CTAS)
 k_policy_fwd(const CovDesc* __restrict__ dp, const float* __restrict__ P, const float* __restrict__ Wt, int B,
              const int* __restrict__ n_atoms, const float* __restrict__ bags, const float* __restrict__ actions,
              const float* __restrict__ A_last, const float* __restrict__ inv, const float* __restrict__ flogit,
