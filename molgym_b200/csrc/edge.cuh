@@ -51,16 +51,32 @@ k_dot_fwd(const CovDesc* __restrict__ dp, int level, const int* __restrict__ n_a
   for (int idx = threadIdx.x; idx < n * NLM * C; idx += blockDim.x) sA[idx] = Ab[idx];
   __syncthreads();
   float2* Db = reinterpret_cast<float2*>(D) + (long long)b * N * N * kNL * C;
-  const int per = NLIN * C, total = n * n * per;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pr = idx / per, r = idx - pr * per, lp = r / C, c = r - lp * C;
-    const int i = pr / n, j = pr - i * n;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int m = -lp; m <= lp; ++m) {
-      const float2 v = cmul(sA[(i * NLM + lm_index(lp, m)) * C + c], sA[(j * NLM + lm_index(lp, -m)) * C + c]);
-      if (m & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+  // D is symmetric in (i, j): a task is (pair i <= j, channel c) — all NLIN ells of it in one straight-line pass (the index decode,
+  // one division and one square root, is paid once per 25 complex products), both orientations written
+  const int npairs = n * (n + 1) / 2, total = npairs * C;
+  const float tn = (float)(2 * n + 1);
+  for (int task = threadIdx.x; task < total; task += blockDim.x) {
+    const int pr = task / C, c = task - pr * C;
+    int i = (int)((tn - sqrtf(tn * tn - 8.f * (float)pr)) * 0.5f);
+    i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    while (i > 0 && pr < i * n - i * (i - 1) / 2) --i;                 // row i holds the pairs [i n - i (i - 1) / 2, ...) of j = i .. n - 1
+    while (pr >= (i + 1) * n - (i + 1) * i / 2) ++i;
+    const int j = i + (pr - (i * n - i * (i - 1) / 2));
+    const float2* ai = sA + (i * NLM) * C + c;
+    const float2* aj = sA + (j * NLM) * C + c;
+    float2* dij = Db + ((long long)i * N + j) * kNL * C + c;
+    float2* dji = Db + ((long long)j * N + i) * kNL * C + c;
+    MGB_UNROLL
+    for (int lp = 0; lp < NLIN; ++lp) {
+      float2 acc = make_float2(0.f, 0.f);
+      MGB_UNROLL
+      for (int m = -lp; m <= lp; ++m) {
+        const float2 v = cmul(ai[(lp * lp + lp + m) * C], aj[(lp * lp + lp - m) * C]);
+        if (m & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+      }
+      dij[lp * C] = acc;
+      if (i != j) dji[lp * C] = acc;
     }
-    Db[((long long)i * N + j) * kNL * C + r] = acc;
   }
 }
 
