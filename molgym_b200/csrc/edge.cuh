@@ -228,13 +228,16 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
     const PairId id = decode_pair(p, B, pair_off, n_atoms);
     const PairGeom g = pair_geom(pos + (long long)id.b * N * 3, id.i, id.j, d.cut_rad, d.cut_width);
     const long long pair = ((long long)id.b * N + id.i) * N + id.j;
+    const bool pairable = (C & 1) == 0;   // even channel count: two complex channels per 16-byte store (rows are 8 C bytes)
     float f[kRadFeat], df[kRadFeat];
     rad_features_all(g, P + L.p_scales, P + L.p_phases, f, nullptr);
     const int l_begin = SPLIT ? (int)blockIdx.y : 0, l_end = SPLIT ? (int)blockIdx.y + 1 : kNL;
     MGB_UNROLL
-    for (int t = 0; t < kRadFeat; ++t) {
-      df[t] = 0.f;
-      if (l_begin == 0) sc.f[(long long)p * kRadFeat + t] = f[t];
+    for (int t = 0; t < kRadFeat; ++t) df[t] = 0.f;
+    if (l_begin == 0) {   // 16-byte stores: the thread's rows of the scratch are contiguous and 16-byte aligned
+      MGB_UNROLL
+      for (int t = 0; t < kRadFeat; t += 4)
+        *reinterpret_cast<float4*>(sc.f + (long long)p * kRadFeat + t) = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
     }
     float2 dDacc[NLIN * kEdgeC];
     MGB_UNROLL
@@ -244,20 +247,50 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
     for (int l = l_begin; l < l_end; ++l) {
       float2 dpre[kEdgeC];
       const float2* g_in = reinterpret_cast<const float2*>(dE) + pair * kNL * C + l * C;
-      MGB_UNROLL
-      for (int c = 0; c < kEdgeC; ++c) {
-        dpre[c] = c < C ? make_float2(g_in[c].x * g.s, g_in[c].y * g.s) : make_float2(0.f, 0.f);
-        if (c < C) reinterpret_cast<float2*>(sc.dpre)[((long long)p * kNL + l) * C + c] = dpre[c];
+      if (pairable) {
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; c += 2) {
+          const float4 v = c < C ? *reinterpret_cast<const float4*>(g_in + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dpre[c] = make_float2(v.x * g.s, v.y * g.s);
+          dpre[c + 1] = make_float2(v.z * g.s, v.w * g.s);
+        }
+      } else {
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) dpre[c] = c < C ? make_float2(g_in[c].x * g.s, g_in[c].y * g.s) : make_float2(0.f, 0.f);
+      }
+      {
+        float2* o = reinterpret_cast<float2*>(sc.dpre) + ((long long)p * kNL + l) * C;
+        if (pairable) {
+          MGB_UNROLL
+          for (int c = 0; c < kEdgeC; c += 2)
+            if (c < C) *reinterpret_cast<float4*>(o + c) = make_float4(dpre[c].x, dpre[c].y, dpre[c + 1].x, dpre[c + 1].y);
+        } else {
+          MGB_UNROLL
+          for (int c = 0; c < kEdgeC; ++c)
+            if (c < C) o[c] = dpre[c];
+        }
       }
       const float2* Wl = sW + off * kEdgeC;
       int kk = 0;
       if (L.has_prev) {
         float2* o = reinterpret_cast<float2*>(dE_prev) + pair * kNL * C + l * C;
-        for (int k = 0; k < C; ++k) {
-          float2 a = make_float2(0.f, 0.f);
-          MGB_UNROLL
-          for (int c = 0; c < kEdgeC; ++c) cfmacl(a, Wl[(kk + k) * kEdgeC + c], dpre[c]);
-          o[k] = a;
+        if (pairable) {
+          for (int k = 0; k < C; k += 2) {
+            float2 a = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+            MGB_UNROLL
+            for (int c = 0; c < kEdgeC; ++c) {
+              cfmacl(a, Wl[(kk + k) * kEdgeC + c], dpre[c]);
+              cfmacl(a2, Wl[(kk + k + 1) * kEdgeC + c], dpre[c]);
+            }
+            *reinterpret_cast<float4*>(o + k) = make_float4(a.x, a.y, a2.x, a2.y);
+          }
+        } else {
+          for (int k = 0; k < C; ++k) {
+            float2 a = make_float2(0.f, 0.f);
+            MGB_UNROLL
+            for (int c = 0; c < kEdgeC; ++c) cfmacl(a, Wl[(kk + k) * kEdgeC + c], dpre[c]);
+            o[k] = a;
+          }
         }
         kk += C;
       }
@@ -286,20 +319,29 @@ k_edge_pairs_bwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
           im = fmaf(wr[kRadFeat + t], f[t], im);
           df[t] = fmaf(wr[t], a.x, fmaf(wr[kRadFeat + t], a.y, df[t]));
         }
-        sc.R[((long long)p * kNL + l) * C2 + 2 * k] = re;
-        sc.R[((long long)p * kNL + l) * C2 + 2 * k + 1] = im;
-        sc.dR[((long long)p * kNL + l) * C2 + 2 * k] = a.x;
-        sc.dR[((long long)p * kNL + l) * C2 + 2 * k + 1] = a.y;
+        *reinterpret_cast<float2*>(sc.R + ((long long)p * kNL + l) * C2 + 2 * k) = make_float2(re, im);
+        *reinterpret_cast<float2*>(sc.dR + ((long long)p * kNL + l) * C2 + 2 * k) = a;
       }
       off += L.catE[l];
     }
     float2* od = reinterpret_cast<float2*>(dD) + (SPLIT ? (long long)blockIdx.y * slice_stride : 0ll) + pair * kNL * C;
-    if (!SPLIT || l_begin < NLIN)
-    MGB_UNROLL
-    for (int lp = 0; lp < NLIN; ++lp)
-      MGB_UNROLL
-      for (int cc = 0; cc < kEdgeC; ++cc)
-        if (cc < C) od[lp * C + cc] = dDacc[lp * kEdgeC + cc];
+    if (!SPLIT || l_begin < NLIN) {
+      if (pairable) {
+        MGB_UNROLL
+        for (int lp = 0; lp < NLIN; ++lp)
+          MGB_UNROLL
+          for (int cc = 0; cc < kEdgeC; cc += 2)
+            if (cc < C)
+              *reinterpret_cast<float4*>(od + lp * C + cc) =
+                  make_float4(dDacc[lp * kEdgeC + cc].x, dDacc[lp * kEdgeC + cc].y, dDacc[lp * kEdgeC + cc + 1].x, dDacc[lp * kEdgeC + cc + 1].y);
+      } else {
+        MGB_UNROLL
+        for (int lp = 0; lp < NLIN; ++lp)
+          MGB_UNROLL
+          for (int cc = 0; cc < kEdgeC; ++cc)
+            if (cc < C) od[lp * C + cc] = dDacc[lp * kEdgeC + cc];
+      }
+    }
     {   // f is no longer needed: reuse its registers for d f[t] / d arg_t = cos(arg) r^-p
       float tmp[kRadFeat];
       rad_features_all(g, P + L.p_scales, P + L.p_phases, tmp, f);
@@ -507,10 +549,8 @@ k_edge_pairs_bwd_cs(const CovDesc* __restrict__ dp, int level, int B, const floa
           im = fmaf(wr[kRadFeat + t], f[t], im);
           df[t] = fmaf(wr[t], a.x, fmaf(wr[kRadFeat + t], a.y, df[t]));
         }
-        sc.R[((long long)p * kNL + l) * C2 + 2 * k] = re;
-        sc.R[((long long)p * kNL + l) * C2 + 2 * k + 1] = im;
-        sc.dR[((long long)p * kNL + l) * C2 + 2 * k] = a.x;
-        sc.dR[((long long)p * kNL + l) * C2 + 2 * k + 1] = a.y;
+        *reinterpret_cast<float2*>(sc.R + ((long long)p * kNL + l) * C2 + 2 * k) = make_float2(re, im);
+        *reinterpret_cast<float2*>(sc.dR + ((long long)p * kNL + l) * C2 + 2 * k) = a;
       }
     }
     {   // f is no longer needed: reuse its registers for d f[t] / d arg_t = cos(arg) r^-p
