@@ -117,22 +117,46 @@ k_edge_pairs_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
   MGB_UNROLL
   for (int c = 0; c < kEdgeC; ++c) acc[c] = make_float2(0.f, 0.f);
   int kk = 0;
+  const bool pairable = (C & 1) == 0;   // even channel count: the pair's rows are read / written two complex channels (16 bytes) at a time
   if (L.has_prev) {
     const float2* x = reinterpret_cast<const float2*>(E_prev) + pair * kNL * C + l * C;
-    for (int k = 0; k < C; ++k) {
-      const float2 xv = x[k];
-      MGB_UNROLL
-      for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+    if (pairable) {
+      for (int k = 0; k < C; k += 2) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + k);
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) {
+          cfma(acc[c], sW[(kk + k) * kEdgeC + c], make_float2(xv.x, xv.y));
+          cfma(acc[c], sW[(kk + k + 1) * kEdgeC + c], make_float2(xv.z, xv.w));
+        }
+      }
+    } else {
+      for (int k = 0; k < C; ++k) {
+        const float2 xv = x[k];
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+      }
     }
     kk += C;
   }
   if (l < NLIN) {
     const float2* x = reinterpret_cast<const float2*>(D) + pair * kNL * C;
+    if (pairable) {
 #pragma unroll 2
-    for (int k = 0; k < NLIN * C; ++k) {
-      const float2 xv = x[k];
-      MGB_UNROLL
-      for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+      for (int k = 0; k < NLIN * C; k += 2) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + k);
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) {
+          cfma(acc[c], sW[(kk + k) * kEdgeC + c], make_float2(xv.x, xv.y));
+          cfma(acc[c], sW[(kk + k + 1) * kEdgeC + c], make_float2(xv.z, xv.w));
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int k = 0; k < NLIN * C; ++k) {
+        const float2 xv = x[k];
+        MGB_UNROLL
+        for (int c = 0; c < kEdgeC; ++c) cfma(acc[c], sW[(kk + k) * kEdgeC + c], xv);
+      }
     }
     kk += NLIN * C;
   }
@@ -150,9 +174,15 @@ k_edge_pairs_fwd(const CovDesc* __restrict__ dp, int level, int B, const float* 
     }
   }
   float2* Eo = reinterpret_cast<float2*>(E_out) + pair * kNL * C + l * C;
-  MGB_UNROLL
-  for (int c = 0; c < kEdgeC; ++c)
-    if (c < C) Eo[c] = make_float2(acc[c].x * g.s, acc[c].y * g.s);
+  if (pairable) {
+    MGB_UNROLL
+    for (int c = 0; c < kEdgeC; c += 2)
+      if (c < C) *reinterpret_cast<float4*>(Eo + c) = make_float4(acc[c].x * g.s, acc[c].y * g.s, acc[c + 1].x * g.s, acc[c + 1].y * g.s);
+  } else {
+    MGB_UNROLL
+    for (int c = 0; c < kEdgeC; ++c)
+      if (c < C) Eo[c] = make_float2(acc[c].x * g.s, acc[c].y * g.s);
+  }
 }
 
 // scale / phase cotangents of a CTA: warp reduction, shared-memory reduction over the warps, then ONE global atomic per CTA
