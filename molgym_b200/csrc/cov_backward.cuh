@@ -344,13 +344,18 @@ __host__ __device__ inline int policy_bwd_extra_floats(const CovDesc& d) {
 constexpr int kAtomBwdThreads = 256;
 constexpr int kEdgeCMax = 10;   // hidden channels <= 10 (checked at plan creation)
 constexpr int kJChunkBwd = 8;
+// Level 0 (scalar inputs, NLM2 = 1) has almost no arithmetic per neighbour: its chunks are 32 neighbours, so that a canvas row is
+// one or two passes with eight loads in flight per thread instead of 3-5 latency-exposed passes (C5 b256: 315 us per launch with chunks of 8)
+constexpr int kJChunkBwd0 = 32;
+__host__ __device__ constexpr int atom_bwd_chunk(int nlm2) { return nlm2 == 1 ? kJChunkBwd0 : kJChunkBwd; }
 // The neighbour chunks are software-pipelined through registers: while a chunk is consumed out of shared memory the next one
 // is already in flight from L2 (kAtomPre float2 per thread cover a chunk of E_ij and A_j rows for C <= 10).
 constexpr int kAtomPre = (kJChunkBwd * (kNL + kM) * kEdgeCMax + kAtomBwdThreads - 1) / kAtomBwdThreads;
+static_assert(kJChunkBwd0 * (kNL + 1) * kEdgeCMax <= kAtomPre * kAtomBwdThreads, "level-0 chunk must fit the register staging");
 
 __host__ __device__ inline int atom_bwd_smem_floats(const LevelDesc& L, int N) {
   const int nlm2 = L.nlm_in;
-  const int stage = kJChunkBwd * (kNL * L.C + nlm2 * L.C + kM * L.C) * 2;
+  const int stage = atom_bwd_chunk(nlm2) * (kNL * L.C + nlm2 * L.C + kM * L.C) * 2;
   return L.totA * 2 + stage + nlm2 * L.C * 2 + N * kM * 2;
 }
 
@@ -387,6 +392,7 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const CovDesc& d = *dp;
   const LevelDesc& L = d.lv[level];
   const int N = d.N, C = CT ? CT : L.C;
+  constexpr int JC = atom_bwd_chunk(NLM2);   // neighbours per staged chunk
   if ((int)blockIdx.x >= atom_off[B]) return;
   const int slot = atom_list[blockIdx.x];
   const int b = slot / N, i = slot - b * N;
@@ -394,9 +400,9 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   MGB_DYN_SMEM(float2, smem);
   float2* sDcat = smem;                         // [totA]  cotangent of the cat vector (written by k_mix_rows<.., true>)
   float2* sE = sDcat + L.totA;                  // [JC][5][C]
-  float2* sAj = sE + kJChunkBwd * kNL * C;      // [JC][NLM2][C]
-  float2* sU = sAj + kJChunkBwd * NLM2 * C;     // [JC][25][C]   column pass: E * Y ; row pass: per-thread dE contributions
-  float2* sAi = sU + kJChunkBwd * kM * C;       // [NLM2][C]
+  float2* sAj = sE + JC * kNL * C;      // [JC][NLM2][C]
+  float2* sU = sAj + JC * NLM2 * C;     // [JC][25][C]   column pass: E * Y ; row pass: per-thread dE contributions
+  float2* sAi = sU + JC * kM * C;       // [NLM2][C]
   float2* sYall = sAi + NLM2 * C;               // [n][25]
   const float2* Ab = reinterpret_cast<const float2*>(A_in) + (long long)b * N * NLM2 * C;
   const float2* E_i = reinterpret_cast<const float2*>(E) + ((long long)b * N + i) * N * kNL * C;
@@ -429,13 +435,13 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       for (int y = 0; y < NLM2; ++y) dTrow[y] = pair_scatter<kCgPad>(L.ag.pad_pair, x * NLM2 + y, sDcat, c);
     }
     float2 pre[kAtomPre];
-    chunk_fetch<NLM2>(Ab, E_i, C, 0, min(kJChunkBwd, n), pre);
-    for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
-      const int nj = min(kJChunkBwd, n - j0);
+    chunk_fetch<NLM2>(Ab, E_i, C, 0, min(JC, n), pre);
+    for (int j0 = 0; j0 < n; j0 += JC) {
+      const int nj = min(JC, n - j0);
       __syncthreads();
       chunk_commit<NLM2>(C, nj, pre, sE, sAj);
       __syncthreads();
-      if (j0 + kJChunkBwd < n) chunk_fetch<NLM2>(Ab, E_i, C, j0 + kJChunkBwd, min(kJChunkBwd, n - j0 - kJChunkBwd), pre);
+      if (j0 + JC < n) chunk_fetch<NLM2>(Ab, E_i, C, j0 + JC, min(JC, n - j0 - JC), pre);
       if (owner) {
         for (int jj = 0; jj < nj; ++jj) {
           // contribution of m1 = x to dE_ij[l1, c]: conj(Y[x]) * sum_y conj(A_j[y, c]) dT[x][y]
@@ -466,9 +472,15 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   // ---- (C) column pass + own-atom terms
   if (do_cols) {
     float2 dTcol[kM];     // dT[y][x], y < 25   (threads x < NLM2)
+    float2* sT = sAj;     // NLM2 == 1: dT[y][0] per channel, [25][C] (the column pass does not stage A_j)
+    if (NLM2 == 1) {
+      if (owner) sT[x * C + c] = pair_scatter<kCgPad>(L.ag.pad_pair, x, sDcat, c);
+    }
     if (col_owner) {
-      MGB_UNROLL
-      for (int y = 0; y < kM; ++y) dTcol[y] = pair_scatter<kCgPad>(L.ag.pad_pair, y * NLM2 + x, sDcat, c);
+      if (NLM2 != 1) {
+        MGB_UNROLL
+        for (int y = 0; y < kM; ++y) dTcol[y] = pair_scatter<kCgPad>(L.ag.pad_pair, y * NLM2 + x, sDcat, c);
+      }
       // own atom: pass-through block and CG square
       const int base = L.offA[l1] + (x - l1 * l1) * L.catA[l1];
       float2 dai = sDcat[base + L.in_block[l1] * C + c];
@@ -479,17 +491,30 @@ k_atom_bwd(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
       atomic_add2(dAb + (long long)i * NLM2 * C + x * C + c, dai);
     }
     float2 pre[kAtomPre];
-    chunk_fetch<0>(Ab, E_i, C, 0, min(kJChunkBwd, n), pre);
-    for (int j0 = 0; j0 < n; j0 += kJChunkBwd) {
-      const int nj = min(kJChunkBwd, n - j0);
+    chunk_fetch<0>(Ab, E_i, C, 0, min(JC, n), pre);
+    for (int j0 = 0; j0 < n; j0 += JC) {
+      const int nj = min(JC, n - j0);
       __syncthreads();
       chunk_commit<0>(C, nj, pre, sE, sAj);
       __syncthreads();
-      if (j0 + kJChunkBwd < n) chunk_fetch<0>(Ab, E_i, C, j0 + kJChunkBwd, min(kJChunkBwd, n - j0 - kJChunkBwd), pre);
+      if (j0 + JC < n) chunk_fetch<0>(Ab, E_i, C, j0 + JC, min(JC, n - j0 - JC), pre);
       if (owner)
         for (int jj = 0; jj < nj; ++jj) sU[(jj * kM + x) * C + c] = cmul(sE[(jj * kNL + l1) * C + c], sYall[(j0 + jj) * kM + x]);
       __syncthreads();
-      if (col_owner) {
+      if (NLM2 == 1) {
+        // scalar inputs: dT[.][0] depends on the channel only (staged in sT); all threads share the (neighbour, channel) sums
+        // instead of the C column owners walking every neighbour
+        for (int idx = threadIdx.x; idx < nj * C; idx += blockDim.x) {
+          const int jj = idx / C, cc = idx - jj * C;
+          float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+          const float2* u = sU + jj * kM * C + cc;
+          MGB_UNROLL
+          for (int y = 0; y < kM; ++y) {
+            if (y & 1) cfmacl(v1, u[y * C], sT[y * C + cc]); else cfmacl(v0, u[y * C], sT[y * C + cc]);
+          }
+          atomic_add2(dAb + (long long)(j0 + jj) * C + cc, make_float2(v0.x + v1.x, v0.y + v1.y));
+        }
+      } else if (col_owner) {
         for (int jj = 0; jj < nj; ++jj) {
           // dA_j[x, c] += sum_y conj(E_ij[l(y), c] Y[y]) dT[y][x]
           float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
