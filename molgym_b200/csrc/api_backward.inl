@@ -26,10 +26,12 @@ static int launch_atom_bwd_ct(const mgb_cov_plan* plan, int level, int B, const 
 
 template <int NLM2>
 static int launch_atom_bwd(const mgb_cov_plan* plan, int level, int B, const float* P, const float* pos, const CovWs& w,
-                           int accumulate_dE, cudaStream_t st) {
+                           int accumulate_dE, bool mix_done, cudaStream_t st) {
   // dcat = W^H dA_{level+1}, row-parallel, into HBM; the atom kernel stages its atom's slice in shared memory
-  int rc = launch_mix_rows<true>(plan, level, B, P, w, w.dA[(level + 1) & 1], w.dcat, st);
-  if (rc != MGB_OK) return rc;
+  if (!mix_done) {
+    int rc = launch_mix_rows<true>(plan, level, B, P, w, w.dA[(level + 1) & 1], w.dcat, st);
+    if (rc != MGB_OK) return rc;
+  }
 
   return plan->desc.lv[level].C == 10 ? launch_atom_bwd_ct<NLM2, 10>(plan, level, B, pos, w, accumulate_dE, st)
                                       : launch_atom_bwd_ct<NLM2, 0>(plan, level, B, pos, w, accumulate_dE, st);
@@ -107,8 +109,16 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
     if (k < K - 1) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join[k + 1], 0));   // mix_dw(k+1) still reads dA[(k+2)&1] == dA[k&1]
     if (k < K - 1 && small_atoms(B, N)) MGB_CUDA_OK(cudaStreamWaitEvent(st, plan->ev_join3[k + 1], 0));   // column pass of level k+1: dA_{k+1} complete, dcat free
     MGB_CUDA_OK(cudaMemsetAsync(w.dA[k & 1], 0, sizeof(float) * BN * kM * cmax * 2, st));
+    // large minibatches: the weight gradient (streams cat_k from HBM) is forked BEHIND the dcat mix (streams dcat to HBM), so that it
+    // runs beside the FP32-bound atom kernel instead of competing with the other bandwidth-bound kernel of the level
+    bool mix_first = !small_atoms(B, N);
+    if (const char* e = std::getenv("MGB_MIXDW_LATE")) mix_first = e[0] == '1';
+    if (mix_first) {
+      int rc0 = launch_mix_rows<true>(plan, k, B, P, w, w.dA[(k + 1) & 1], w.dcat, st);
+      if (rc0 != MGB_OK) return rc0;
+    }
     {
-      // fork: the atom-mix weight gradient (reads cat_k and dA_{k+1}, both complete here) runs beside the whole level
+      // fork: the atom-mix weight gradient (reads cat_k and dA_{k+1}, both complete here) runs beside the level
       MGB_CUDA_OK(cudaEventRecord(plan->ev_fork[k], st));
       MGB_CUDA_OK(cudaStreamWaitEvent(side, plan->ev_fork[k], 0));
       const int chunks = (int)std::max<size_t>(1, std::min<size_t>((BN + kMixDwAtoms - 1) / kMixDwAtoms, 148 * 2));
@@ -140,7 +150,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       MGB_CUDA_OK(cudaEventRecord(plan->ev_join[k], side));
     }
     const int acc_dE = (k < K - 1) ? 1 : 0;
-    int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, st);
+    int rc = k == 0 ? launch_atom_bwd<1>(plan, k, B, P, pos, w, acc_dE, mix_first, st) : launch_atom_bwd<kM>(plan, k, B, P, pos, w, acc_dE, mix_first, st);
     if (rc != MGB_OK) return rc;
     {
       const unsigned pair_blocks = (unsigned)((BN * N + kPairThreads - 1) / kPairThreads);
