@@ -629,14 +629,32 @@ __global__ void k_dot_bwd(const CovDesc* __restrict__ dp, int level, const int* 
   for (int idx = threadIdx.x; idx < NLM * C; idx += blockDim.x) {
     const int lm = idx / C, c = idx % C, l = ell_of_lm(lm), m = lm - l * l - l;
     float2 acc = make_float2(0.f, 0.f);
-    for (int j = 0; j < n; ++j) {
+    const float2* arow = Ab + lm_index(l, -m) * C + c;
+    const float2* drow = dDb + (long long)i * N * kNL * C + l * C + c;   // (i, j) entries: j strides kNL C
+    const float2* dcol = dDb + (long long)i * kNL * C + l * C + c;       // (j, i) entries: j strides N kNL C
+    int j = 0;
+    if (n_slices == 1) {
+      // four neighbours per pass: twelve independent loads in flight instead of a dependent chain per neighbour
+      for (; j + 3 < n; j += 4) {
+        float2 g1[4], g2[4], a[4];
+        MGB_UNROLL
+        for (int q = 0; q < 4; ++q) {
+          g1[q] = drow[(long long)(j + q) * kNL * C];
+          g2[q] = dcol[(long long)(j + q) * N * kNL * C];
+          a[q] = arow[(long long)(j + q) * NLM * C];
+        }
+        MGB_UNROLL
+        for (int q = 0; q < 4; ++q) cfmacl(acc, a[q], make_float2(g1[q].x + g2[q].x, g1[q].y + g2[q].y));
+      }
+    }
+    for (; j < n; ++j) {
       float2 g = make_float2(0.f, 0.f);
       for (int s = 0; s < n_slices; ++s) {
-        const float2 g1 = dDb[s * slice_stride + ((long long)i * N + j) * kNL * C + l * C + c];
-        const float2 g2 = dDb[s * slice_stride + ((long long)j * N + i) * kNL * C + l * C + c];
+        const float2 g1 = drow[s * slice_stride + (long long)j * kNL * C];
+        const float2 g2 = dcol[s * slice_stride + (long long)j * N * kNL * C];
         g.x += g1.x + g2.x; g.y += g1.y + g2.y;
       }
-      cfmacl(acc, Ab[(long long)j * NLM * C + lm_index(l, -m) * C + c], g);
+      cfmacl(acc, arow[(long long)j * NLM * C], g);
     }
     const float sg = (m & 1) ? -1.f : 1.f;
     atomic_add2(dst + idx, make_float2(sg * acc.x, sg * acc.y));   // the atom level's column pass may still be adding to dA_k
