@@ -11,7 +11,13 @@ def main(path, header=''):
     rows = []
     for row in csv.DictReader(lines):
         if row.get('Metric Name') == 'gpu__time_duration.sum':
-            rows.append((row['Kernel Name'], float(row['Metric Value']), row['Grid Size'], row['Block Size']))
+            try:
+                v = float(row['Metric Value'].replace(',', ''))
+            except ValueError:
+                continue
+            if v != v:   # a launch ncu could not time (n/a)
+                continue
+            rows.append((row['Kernel Name'], v, row['Grid Size'], row['Block Size']))
     if header:
         print(header)
     agg = collections.OrderedDict()
