@@ -17,21 +17,28 @@ constexpr size_t kMaxDynSmemMix = 227 * 1024;
     if (e_ != cudaSuccess) return fail(MGB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e_)); \
   } while (0)
 
-template <int CO, bool BACKWARD, int KS>
-static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
+template <int CO, bool BACKWARD, int KS, int THREADS>
+static int launch_mix_rows_kt(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
   const CovDesc& d = plan->desc;
   const LevelDesc& L = d.lv[level];
   int kmax = 0;
   for (int l = 0; l < kNL; ++l) kmax = std::max(kmax, L.catA[l]);
   const size_t smem = sizeof(float2) * (size_t)kmax * kMixStride<CO>;
-  MGB_CUDA_OK(cudaFuncSetAttribute((k_mix_rows<CO, BACKWARD, KS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long rows_per_cta = kMixThreads / KS;
+  MGB_CUDA_OK(cudaFuncSetAttribute((k_mix_rows<CO, BACKWARD, KS, THREADS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long rows_per_cta = THREADS / KS;
   const long long groups = ((long long)B * d.N * 9 + rows_per_cta - 1) / rows_per_cta;
   dim3 grid((unsigned)std::min<long long>(groups, 148 * (KS == 32 ? 3 : 2)), kNL);   // ~10-15 CTAs per SM over the five ells; each loops over row groups
-  MGB_LAUNCH((k_mix_rows<CO, BACKWARD, KS>), grid, kMixThreads, smem, st, plan->d_desc, level, w.Wt, w.atom_off, w.atom_list, B,
+  MGB_LAUNCH((k_mix_rows<CO, BACKWARD, KS, THREADS>), grid, THREADS, smem, st, plan->d_desc, level, w.Wt, w.atom_off, w.atom_list, B,
              w.cat[level], A_out, out);
   MGB_LAUNCH_OK("k_mix_rows");
   return MGB_OK;
+}
+template <int CO, bool BACKWARD, int KS>
+static int launch_mix_rows_ks(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
+  // the dcat mix of large minibatches runs 512-thread CTAs (fewer stagings of W_l per row); small minibatches are latency-bound and
+  // faster with 128-thread CTAs (C2: 21 against 28 us per launch)
+  if (BACKWARD && large_atoms(B, plan->desc.N)) return launch_mix_rows_kt<CO, BACKWARD, KS, kMixThreadsLarge>(plan, level, B, w, A_out, out, st);
+  return launch_mix_rows_kt<CO, BACKWARD, KS, kMixThreads>(plan, level, B, w, A_out, out, st);
 }
 template <int CO, bool BACKWARD>
 static int launch_mix_rows_co(const mgb_cov_plan* plan, int level, int B, const CovWs& w, const float* A_out, float* out, cudaStream_t st) {
@@ -44,11 +51,11 @@ static int launch_mix_rows_co(const mgb_cov_plan* plan, int level, int B, const 
 // on (C5 b256: 130 / 144 us against 182 / 243 us), the backward does not (its FFMA version is already bound by the dcat
 // writes), small minibatches are launch-latency bound either way.  Default: forward only, large minibatches.
 // MGB_MIX_TC=0: never; MGB_MIX_TC=1: always, both directions (parity tests).
-static int mix_tc_ntiles(const LevelDesc& L, long long atoms, bool backward) {
+static int mix_tc_ntiles(const LevelDesc& L, bool large, bool backward) {
   const char* e = std::getenv("MGB_MIX_TC");
   if (e && e[0] == '0') return 0;
   const bool forced = e && e[0] == '1';
-  if (!forced && (backward || atoms < 2048)) return 0;
+  if (!forced && (backward || !large)) return 0;
   const int nt = (2 * L.Cout + 7) / 8;
   if (nt != 3 && nt != 4) return 0;
   int kmax = 0;
@@ -87,7 +94,7 @@ static int launch_mix_rows_tc(const mgb_cov_plan* plan, int level, int B, const 
 template <bool BACKWARD>
 static int launch_mix_rows(const mgb_cov_plan* plan, int level, int B, const float* P, const CovWs& w, const float* A_out, float* out,
                            cudaStream_t st) {
-  switch (mix_tc_ntiles(plan->desc.lv[level], (long long)B * plan->desc.N, BACKWARD)) {
+  switch (mix_tc_ntiles(plan->desc.lv[level], large_atoms(B, plan->desc.N), BACKWARD)) {
     case 3: return launch_mix_rows_tc<3, BACKWARD>(plan, level, B, P, w, A_out, out, st);
     case 4: return launch_mix_rows_tc<4, BACKWARD>(plan, level, B, P, w, A_out, out, st);
     default: break;

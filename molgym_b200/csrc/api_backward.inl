@@ -128,7 +128,7 @@ int mgb_cov_backward(mgb_cov_plan* plan, int32_t B, const float* pos, const int3
       int co = std::min(pick_co_rows(L.Cout), 16 + 4 * (L.Cout == 20));   // more than 20 channels: passes of 16
       // 20 channels in one pass need 238 registers (8 warps per SM): from a few thousand atoms on two passes of 10 (96 registers)
       // are faster although cat is read twice (C3 b1024 step 6.27 -> 6.11 ms, C4 b1024 12.74 -> 12.48 ms; no difference at b128)
-      if (L.Cout == 20 && (long long)B * N >= 2048) co = 10;
+      if (L.Cout == 20 && large_atoms(B, N)) co = 10;
       const size_t sm = sizeof(float2) * kMixDwAtoms * 9 * co;
 #define MGB_MIXDW_CASE(CO)                                                                                                        \
   case CO:                                                                                                                        \

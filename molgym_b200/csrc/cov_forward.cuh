@@ -456,11 +456,12 @@ k_atom_cat(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
 // are registers; no cross-lane reduction.  grid = (row blocks, 5 ells).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kMixThreads = 128;
+constexpr int kMixThreadsLarge = 512;   // backward (dcat) mix of large minibatches: 64 rows per CTA share one staging of W_l (C5 b256: 215 / 253 -> 180 / 178 us)
 template <int CO> constexpr int kMixStride = (CO % 4 == 2) ? CO : ((CO % 2 == 0) ? CO + 2 : CO);
 inline int mix_stride_of(int co) { return (co % 4 == 2) ? co : ((co % 2 == 0) ? co + 2 : co); }
 
-template <int CO, bool BACKWARD, int KS>
-__global__ void __launch_bounds__(kMixThreads)
+template <int CO, bool BACKWARD, int KS, int THREADS = kMixThreads>
+__global__ void __launch_bounds__(THREADS)
 k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ Wt, const int* __restrict__ atom_off,
            const int* __restrict__ atom_list, int B, const float* __restrict__ cat, const float* __restrict__ A_out,
            float* __restrict__ out) {
@@ -470,7 +471,7 @@ k_mix_rows(const CovDesc* __restrict__ dp, int level, const float* __restrict__ 
   const LevelDesc& L = d.lv[level];
   const int l = blockIdx.y, K = L.catA[l], nm = 2 * l + 1, Cout = L.Cout;
   const int rows = atom_off[B] * nm;
-  constexpr int kRowsPerCta = kMixThreads / KS;
+  constexpr int kRowsPerCta = THREADS / KS;
   if ((int)(blockIdx.x * kRowsPerCta) >= rows) return;   // uniform per CTA: the whole CTA leaves before any barrier
   // row stride of the staged weights: KS lanes of a quarter-warp read KS different k at once, so the stride (in float2) is
   // kept = 2 mod 4 — 16-byte aligned rows whose 16-byte slots fall into different bank groups (CO = 16 would otherwise put

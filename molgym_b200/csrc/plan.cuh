@@ -182,6 +182,13 @@ inline bool small_atoms(int B, int N) {
   const long long limit = e ? std::atoll(e) : 2560;   // measured: helps up to ~1.5 k atom slots (C2/140, C3/128), hurts at C4/512
   return (long long)B * N < limit;
 }
+// large minibatches (a few thousand atom slots and more): tensor-core forward mix, 512-thread dcat mix, two-pass 20-channel mix weight
+// gradient.  MGB_LARGE_ATOMS overrides the slot threshold (the parity tests force the large path on small batches with 1).
+inline bool large_atoms(int B, int N) {
+  const char* e = std::getenv("MGB_LARGE_ATOMS");
+  const long long limit = e ? std::atoll(e) : 2048;
+  return (long long)B * N >= limit;
+}
 // a few thousand pairs only: five threads per (pair, ell) (k_edge_pairs_*_cs)
 inline bool edge_small(int B, int N) {
   const int m = edge_mode_override();

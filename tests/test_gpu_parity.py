@@ -95,7 +95,9 @@ def test_large_decomposition_and_high_occupancy_against_oracle(which, batch, sta
     if large:
         monkeypatch.setenv('MGB_EDGE_MODE', '0')
         monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
-        monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
+        if which == 'C4':   # the tensor-core channel mix in both directions; the other cases take the default large path (tensor-core forward, 512-thread FFMA backward)
+            monkeypatch.setenv('MGB_MIX_TC', '1')
+        monkeypatch.setenv('MGB_LARGE_ATOMS', '1')   # ... and the rest of the large-minibatch choices (512-thread dcat mix, two-pass mix weight gradient)
     cfg = synth.CONFIGS[which]
     torch.manual_seed(13)
     agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
@@ -189,6 +191,7 @@ def test_edge_kernel_decompositions_agree_with_oracle(mode, monkeypatch):
     if mode == '0':   # together with the large-minibatch atom path (combined atom kernels, tiled InputLinear weight gradient)
         monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
         monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
+        monkeypatch.setenv('MGB_LARGE_ATOMS', '1')   # ... and the rest of the large-minibatch choices (512-thread dcat mix, two-pass mix weight gradient)
     cfg = synth.CONFIGS['C3']
     torch.manual_seed(5)
     agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())

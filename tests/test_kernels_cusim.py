@@ -51,6 +51,7 @@ def test_fresh_canvases_against_oracle(levels, beta, zs, canvas, edge_mode, monk
         if edge_mode == '0':    # ... and the large-minibatch atom path (combined atom kernels, tiled InputLinear gradient)
             monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
             monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
+            monkeypatch.setenv('MGB_LARGE_ATOMS', '1')   # ... and the rest of the large-minibatch choices (512-thread dcat mix, two-pass mix weight gradient)
     cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=canvas, network_width=32, num_cg_levels=levels, beta=beta,
                               bag={z: 2 for z in zs if z}, bag_scale=4, seed=levels)
     torch.manual_seed(levels)
@@ -84,7 +85,9 @@ def test_high_occupancy_canvases_against_oracle(which, batch, start, large, monk
     if large:
         monkeypatch.setenv('MGB_EDGE_MODE', '0')
         monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
-        monkeypatch.setenv('MGB_MIX_TC', '1')   # ... and the tensor-core channel mix (both directions)
+        if which == 'C4':   # the tensor-core channel mix in both directions; the other cases take the default large path (tensor-core forward, 512-thread FFMA backward)
+            monkeypatch.setenv('MGB_MIX_TC', '1')
+        monkeypatch.setenv('MGB_LARGE_ATOMS', '1')   # ... and the rest of the large-minibatch choices (512-thread dcat mix, two-pass mix weight gradient)
     cfg = dataclasses.replace(synth.CONFIGS[which], network_width=32)
     torch.manual_seed(8)
     oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
