@@ -151,14 +151,20 @@ def test_six_species_24_output_channels_against_oracle():
     assert_grads_close(grads_of(agent), ref_grads)
 
 
-def test_odd_hyperparameters_against_oracle():
+@pytest.mark.parametrize('hidden,edge_mode', [(6, None), (5, '0')])
+def test_odd_hyperparameters_against_oracle(hidden, edge_mode, monkeypatch):
     """6 hidden channels (run-time channel stride, zero-padded edge tiles), 3 channels per element (9 output channels), width 30
-    (the row MLPs fall back from the bulk-copy kernels; unaligned bulk copies fall back to plain loads), 2 Gaussians."""
+    (the row MLPs fall back from the bulk-copy kernels; unaligned bulk copies fall back to plain loads), 2 Gaussians.
+    5 hidden channels with the thread-per-pair edge kernels: odd channel counts take 8-byte instead of 16-byte row accesses."""
     from oracle.molgym_oracle import CovariantOracle, ppo_loss
     from molgym_b200 import ppo
+    if edge_mode is not None:
+        monkeypatch.setenv('MGB_EDGE_MODE', edge_mode)
+        monkeypatch.setenv('MGB_SMALL_ATOMS', '0')
+        monkeypatch.setenv('MGB_LARGE_ATOMS', '1')
     zs = [0, 1, 8]
     cfg = dataclasses.replace(synth.CONFIGS['C3'], zs=zs, canvas_size=5, network_width=30, num_cg_levels=2, beta=-3.0,
-                              num_channels_hidden=6, num_channels_per_element=3, num_gaussians=2, bag={1: 3, 8: 2}, bag_scale=4, seed=5)
+                              num_channels_hidden=hidden, num_channels_per_element=3, num_gaussians=2, bag={1: 3, 8: 2}, bag_scale=4, seed=5)
     torch.manual_seed(4)
     agent = make_agent(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
     oracle = CovariantOracle(cfg.zs, cfg.canvas_size, **cfg.agent_kwargs())
