@@ -673,8 +673,15 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
     # ------------------------------------------------------------------------------------------------------
     # fused PPO minibatch step: pack -> one H2D copy -> CUDA-graph replay of forward + PPO-clip loss, then of the backward
     # ------------------------------------------------------------------------------------------------------
+    def train_shard(self, n: int):
+        """(lo, hi) of a minibatch of n canvases when the caller may hand over just this rank's slice (molgym_b200.ppo.train does:
+        on a data-parallel agent with the fused step it collects data[lo:hi] only and passes n_global = n), else None."""
+        if not (self._is_sharded() and self.fused_ppo):
+            return None
+        return self._shard(n)
+
     def fused_ppo_loss(self, observations: List, actions, old_logp, adv, ret, clip_ratio: float, vf_coef: float,
-                       entropy_coef: float):
+                       entropy_coef: float, n_global: Optional[int] = None):
         """The arithmetic of ppo.compute_loss (ppo.py:18-63) on this agent, as one pinned staging copy and two CUDA-graph
         replays: forward + PPO-clip loss (float64, k_ppo_loss), then the backward into a scratch gradient, enqueued right away
         (ppo.train always differentiates the loss it just computed, ppo.py:126-131).  Returns (loss, info) like compute_loss;
@@ -700,9 +707,14 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
             self._realias()
         actions_np = _as_numpy_actions(actions, n, 6)
         self._check_actions(actions_np)
-        lo, hi = self._shard(n)
-        B = hi - lo
         sharded = self._is_sharded()
+        if n_global is not None and sharded:
+            lo, hi = 0, n           # the caller collected this rank's slice of a minibatch of n_global canvases (train_shard)
+            n = int(n_global)
+        else:
+            lo, hi = self._shard(n)
+        B = hi - lo
+        presliced = n_global is not None and sharded
         if self._fused_streams is None:
             self._fused_streams = [rt.new_stream(), rt.new_stream()]
         slot = self._fused_turn
@@ -718,7 +730,7 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         if st.ring_infos[k] is not None:
             st.ring_infos[k]._resolve()   # a block is read out before it is overwritten (sixteen steps later: a no-op in practice)
         st.copied.synchronize()        # ... and its previous staging copy has left the pinned buffer (two steps ago: no wait in practice)
-        pack_observations(observations[lo:hi] if sharded else observations, self.zs, self.canvas_size, cfg=self._cfg,
+        pack_observations(observations[lo:hi] if (sharded and not presliced) else observations, self.zs, self.canvas_size, cfg=self._cfg,
                           out=(st.h_pos, st.h_charges, st.h_bags), lib=rt.lib())
         st.h_act[...] = actions_np[lo:hi]
         st.h_old[...] = old_logp[lo:hi]

@@ -4,7 +4,7 @@
 on machines where the reference tree is not present (the GPU box), and so that `train` can take the fused step and the fused
 optimizer tail (molgym_b200.optim.FlatAdam) when the caller hands them over."""
 import time
-from typing import Dict, Tuple
+from typing import Optional, Dict, Tuple
 
 import numpy as np
 import torch
@@ -18,19 +18,31 @@ def _to_device(x, device):
     return torch.as_tensor(x, device=device)
 
 
-def compute_loss(ac, data: dict, clip_ratio: float, vf_coef: float, entropy_coef: float, device=None) -> Tuple[torch.Tensor, Dict[str, float]]:
+def _takes_fused_step(ac, data: dict, device) -> bool:
+    """The agent offers the fused step and the buffers have the dtypes ppo.train hands over (buffer.py:106-116)."""
+    same_device = device is None or torch.device(device) == getattr(ac, 'device', None) or \
+        (torch.device(device).type == 'cuda' and torch.device(device).index is None and getattr(ac, 'device', torch.device('cpu')).type == 'cuda')
+    return bool(getattr(ac, 'fused_ppo', False) and same_device and torch.is_grad_enabled() and isinstance(data['adv'], np.ndarray)
+                and data['adv'].dtype == np.float64 and isinstance(data['ret'], np.ndarray) and data['ret'].dtype == np.float64
+                and isinstance(data['logp'], np.ndarray) and data['logp'].dtype == np.float32 and len(data['obs']) > 0)
+
+
+def compute_loss(ac, data: dict, clip_ratio: float, vf_coef: float, entropy_coef: float, device=None,
+                 n_global: Optional[int] = None) -> Tuple[torch.Tensor, Dict[str, float]]:
     """ppo.py:18-63, same operations in the same order (adv / ret arrive as float64 numpy -> float64 loss).
 
     Agents that offer `fused_ppo_loss` (CovariantAC) take the whole step — packing, one H2D copy, forward, the same loss
     arithmetic in float64 on the device (k_ppo_loss, checked against this function by the tests) and the backward — as CUDA-graph
     replays when the buffers have the dtypes ppo.train hands over (buffer.py:106-116); set `ac.fused_ppo = False` for the
-    op-by-op path below."""
-    same_device = device is None or torch.device(device) == getattr(ac, 'device', None) or \
-        (torch.device(device).type == 'cuda' and torch.device(device).index is None and getattr(ac, 'device', torch.device('cpu')).type == 'cuda')
-    if (getattr(ac, 'fused_ppo', False) and same_device and torch.is_grad_enabled() and isinstance(data['adv'], np.ndarray)
-            and data['adv'].dtype == np.float64 and isinstance(data['ret'], np.ndarray) and data['ret'].dtype == np.float64
-            and isinstance(data['logp'], np.ndarray) and data['logp'].dtype == np.float32 and len(data['obs']) > 0):
+    op-by-op path below.  `n_global` (data-parallel agents, fused step only): `data` is already this rank's slice
+    (`ac.train_shard`) of a minibatch of n_global canvases."""
+    if _takes_fused_step(ac, data, device):
+        if n_global is not None:
+            return ac.fused_ppo_loss(data['obs'], data['act'], data['logp'], data['adv'], data['ret'], clip_ratio, vf_coef, entropy_coef,
+                                     n_global=n_global)
         return ac.fused_ppo_loss(data['obs'], data['act'], data['logp'], data['adv'], data['ret'], clip_ratio, vf_coef, entropy_coef)
+    if n_global is not None:
+        raise ValueError('compute_loss: n_global (a pre-sliced minibatch) needs the fused step')
     pred = ac.step(data['obs'], data['act'])
     device = device if device is not None else pred['logp'].device
     old_logp = _to_device(data['logp'], device)
@@ -97,9 +109,17 @@ def train(ac, optimizer, data: dict, mini_batch_size: int, clip_ratio: float, ta
         optimizer.zero_grad()
         batch_infos = []
         for batch_indices in get_batch_generator(indices=np.arange(len(data['obs'])), batch_size=mini_batch_size):
-            data_batch = collect_data_batch(data, indices=batch_indices)
-            batch_loss, batch_info = compute_loss(ac, data=data_batch, clip_ratio=clip_ratio, vf_coef=vf_coef, entropy_coef=entropy_coef,
-                                                  device=device)
+            # data-parallel agent on the fused step: collect only this rank's slice of the minibatch (every rank draws the same
+            # permutation), so that the host work per rank does not grow with the number of ranks
+            shard = ac.train_shard(len(batch_indices)) if (hasattr(ac, 'train_shard') and _takes_fused_step(ac, data, device)) else None
+            if shard is not None:
+                data_batch = collect_data_batch(data, indices=batch_indices[shard[0]:shard[1]])
+                batch_loss, batch_info = compute_loss(ac, data=data_batch, clip_ratio=clip_ratio, vf_coef=vf_coef, entropy_coef=entropy_coef,
+                                                      device=device, n_global=len(batch_indices))
+            else:
+                data_batch = collect_data_batch(data, indices=batch_indices)
+                batch_loss, batch_info = compute_loss(ac, data=data_batch, clip_ratio=clip_ratio, vf_coef=vf_coef, entropy_coef=entropy_coef,
+                                                      device=device)
             batch_loss.backward(retain_graph=False)
             batch_infos.append(batch_info)
         # the loss numbers come from the forward passes: reading them does not wait for the backward of the last minibatch

@@ -124,6 +124,21 @@ def run_ppo_epoch(agent, data, fused, splits=((0, 6), (6, 11))):
     return infos, grads
 
 
+def run_train(agent, data, steps=2, mini_batch_size=6):
+    """molgym_b200.ppo.train for `steps` optimizer steps (plain SGD, so that the parameter trajectory is easy to compare):
+    returned infos without the wall-clock entry, final flat parameters."""
+    import numpy as np
+
+    from molgym_b200 import ppo
+    agent.fused_ppo = True
+    np.random.seed(7)   # get_batch_generator permutes with numpy's global generator
+    opt = torch.optim.SGD(torch.nn.Module.parameters(agent), lr=0.05)
+    infos = ppo.train(agent, opt, data, mini_batch_size=mini_batch_size, clip_ratio=0.2, target_kl=1e9, vf_coef=0.5, entropy_coef=0.01,
+                      gradient_clip=0.5, max_num_steps=steps)
+    infos.pop('time', None)
+    return {k: float(v) for k, v in infos.items()}, agent._flat.detach().numpy().copy()
+
+
 def sharded_worker(rank, world, port, out):
     """World-size-2 gloo worker: the data-parallel agent on every rank is handed the SAME minibatches (as under torchrun with
     the unchanged ppo.train) and evaluates its shard."""
@@ -155,5 +170,9 @@ def sharded_worker(rank, world, port, out):
     pending_before = agent._grad_pending
     opt.step()
     res['hook'] = (pending_before, agent._grad_pending, agent._flat.detach().numpy().copy())
+    # the restated ppo.train on the sharded agent: every rank collects only its slice of each minibatch (train_shard / n_global)
+    _, agent_t, data_t = make_emu_case()
+    parallel.shard_agent(agent_t)
+    res['train'] = run_train(agent_t, data_t)
     out[rank] = res
     dist.destroy_process_group()

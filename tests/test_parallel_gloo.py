@@ -73,4 +73,14 @@ def test_sharded_agent_world2_matches_single_process():
     for rank in (0, 1):
         pending_before, pending_after, _ = out[rank]['hook']
         assert pending_before and not pending_after
+    # molgym_b200.ppo.train on the sharded agent (each rank collects only its slice of every minibatch) = the single-process run
+    _, agent_t, data_t = emu_agent.make_emu_case()
+    ref_info, ref_params = emu_agent.run_train(agent_t, data_t)
+    for rank in (0, 1):
+        info, params = out[rank]['train']
+        assert info.keys() == ref_info.keys()
+        for key in ref_info:
+            assert abs(info[key] - ref_info[key]) <= 1e-5 * max(1.0, abs(ref_info[key])), (rank, key, info[key], ref_info[key])
+        assert float(np.abs(params - ref_params).max()) <= 1e-5, rank
+    assert np.array_equal(out[0]['train'][1], out[1]['train'][1])   # both ranks hold the same parameters
     np.testing.assert_array_equal(out[0]['hook'][2], out[1]['hook'][2])   # the replicas stayed in lockstep
