@@ -148,6 +148,19 @@ class FlatParamMixin:
                 if p.grad is not None and p.grad.data_ptr() != self._flat_grad.data_ptr():
                     p.grad.zero_()
 
+    def zero_grad_flat(self) -> None:
+        """zero_grad for callers that own the flat layout (FlatAdam): ONE memset of the flat gradient, the `.grad` views stay
+        attached (detaching and re-attaching ~100 views costs ~0.3 ms of host time per optimizer step, right where the next forward
+        waits for the host).  `_grads_fresh` records that nothing was accumulated since, so that an optimizer step without a backward
+        still skips the update like torch does for `.grad is None`."""
+        self._grad_pending = False
+        first = self._param_list[0]
+        if first.grad is not None and first.grad.data_ptr() == self._flat_grad.data_ptr() + 4 * self._p_offsets[0]:
+            self._flat_grad.zero_()
+            self._grads_fresh = True
+        else:
+            self.zero_grad(set_to_none=True)
+
     # ------------------------------------------------------------------------------------------------------
     # data-parallel gradient exchange
     # ------------------------------------------------------------------------------------------------------
@@ -158,6 +171,7 @@ class FlatParamMixin:
     def _grad_target(self, keep: bool):
         """(tensor the backward kernels write into, accumulate flag).  Sharded: the shard-local accumulation buffer, reduced
         later by sync_grads(); else the flat gradient itself."""
+        self._grads_fresh = False       # a backward is about to write gradients
         if self._is_sharded():
             if self._grad_local is None:
                 self._grad_local = torch.zeros_like(self._flat_grad)

@@ -59,6 +59,10 @@ class FlatAdam(torch.optim.Adam):
         self.param_groups[0]['foreach'] = False
         self._bind_state()                    # ... which are folded back into the flat buffers
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """One memset of the flat gradient buffer; the parameters' `.grad` views stay attached (agents/_flat.py::zero_grad_flat)."""
+        self._agent.zero_grad_flat()
+
     def grad_norm(self) -> torch.Tensor:
         """||grad||_2 over all parameters as a 0-d float64 device tensor (compute_gradient_norm, tools/util.py:61-69)."""
         agent = self._agent
@@ -82,8 +86,8 @@ class FlatAdam(torch.optim.Adam):
         agent = self._agent
         if not agent._params_aliased() or agent._flat.data_ptr() != self._flat_ptr:
             raise RuntimeError('FlatAdam: the agent\'s parameters moved (unpickled / .to()); build a new optimizer for it')
-        if all(p.grad is None for p in agent._param_list):
-            return loss
+        if getattr(agent, '_grads_fresh', False) or all(p.grad is None for p in agent._param_list):
+            return loss        # nothing was differentiated since zero_grad(): torch skips parameters without gradients
         norm = None
         if max_grad_norm is not None:
             norm = self._norm[0] if reuse_norm else self.grad_norm()       # also flushes a pending gradient all-reduce
