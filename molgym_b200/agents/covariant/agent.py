@@ -452,7 +452,10 @@ class CovariantAC(FlatParamMixin, AbstractActorCritic):
         return shapes, offs, o
 
     def _slot_outputs(self, st, block: torch.Tensor):
-        return tuple(block[o:o + int(np.prod(sh))].view(sh) for sh, o in zip(st.out_shapes, st.out_offs))
+        sizes = getattr(st, 'out_sizes', None)
+        if sizes is None:
+            sizes = st.out_sizes = [int(np.prod(sh)) for sh in st.out_shapes]
+        return tuple(block[o:o + k].view(sh) for sh, o, k in zip(st.out_shapes, st.out_offs, sizes))
 
     def _cov_outputs(self, block: torch.Tensor, B: int, want_extras: bool):
         shapes, offs, _ = self._out_layout(B)
