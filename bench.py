@@ -568,7 +568,7 @@ def run_ours(args):
                 'optimizer step; ms_per_step = time per minibatch'})
     e2e['e2e_unchanged_ppo'].update({
         'note': 'the same loop as the unchanged reference runs it: compute_loss = agent.step(obs, act) (pack, H2D, CUDA-graph replay on a '
-                'persistent evaluation slot) + the loss as the reference's torch ops, the six info numbers read back in one stacked copy (the reference issues six .item() calls), autograd backward (graph replay + one accumulate '
+                'persistent evaluation slot) + the loss as the torch ops of ppo.py:28-52, the six info numbers read back in one stacked copy (the reference issues six .item() calls), autograd backward (graph replay + one accumulate '
                 'kernel); per optimizer step compute_gradient_norm (one torch.norm per parameter tensor, tools/util.py:61-69), '
                 'clip_grad_norm_ and torch.optim.Adam; minibatch_loop_only_* leaves the optimizer tail out'})
 
