@@ -54,6 +54,36 @@ def test_zmat_matches_oracle_restatement_of_reference():
         zmat.position_atom_helper([np.zeros(3)], 2, 1.0, 1.0, 1.0)
 
 
+def test_batched_molecule_builder_matches_the_per_canvas_statement():
+    """zmat.build_molecules (the whole minibatch at once) against build_molecules_loop (one canvas at a time, the reference's
+    placement): canvases with 0 .. N atoms incl. full ones, null slots between atoms, both dihedral signs; same errors."""
+    rng = np.random.default_rng(3)
+    zs, N, B = [0, 1, 6, 8], 5, 40
+    obs, act = [], np.zeros((B, 7), dtype=np.float32)
+    for b in range(B):
+        n = b % (N + 1)
+        slots = sorted(rng.choice(N, size=n, replace=False).tolist()) if b % 3 == 0 else list(range(n))   # some canvases with gaps
+        canvas = [(0, (0.0, 0.0, 0.0))] * N
+        for s_ in slots:
+            canvas[s_] = (int(rng.integers(1, len(zs))), tuple((rng.normal(size=3) * 1.5).tolist()))
+        obs.append((tuple(canvas), tuple(int(x) for x in rng.integers(0, 3, size=len(zs)))))
+        act[b] = [0, rng.integers(0, max(n, 1)), rng.integers(1, len(zs)), rng.uniform(0.9, 2.0), rng.uniform(0.3, 2.8),
+                  rng.uniform(0.1, 3.0), rng.integers(0, 2)]
+    ref = zmat.build_molecules_loop(obs, act, zs, N)
+    got = zmat.build_molecules(obs, act, zs, N)
+    assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[2], got[2])
+    np.testing.assert_allclose(got[1], ref[1], rtol=0, atol=1e-6)
+    bad = act.copy()
+    bad[1, 1] = 3            # canvas 1 holds one atom: focus 3 is past it
+    for fn in (zmat.build_molecules_loop, zmat.build_molecules):
+        with pytest.raises((RuntimeError, IndexError)):
+            fn(obs, bad, zs, N)
+    worse = [((( 9, (0.0, 0.0, 0.0)), ) * N, (0, 0, 0, 0))]
+    for fn in (zmat.build_molecules_loop, zmat.build_molecules):
+        with pytest.raises(RuntimeError):
+            fn(worse, act[:1], zs, N)
+
+
 def test_emulator_forward_backward_against_golden():
     from tests.cusim import runner
     g, cfg, kw = _golden()
